@@ -1,0 +1,73 @@
+"""Multi-process integration on CPU: gloo, world sizes 2/3/4 on localhost.
+Oracle: monolithic fp64 attention over the concatenated KV."""
+import pytest
+import torch
+import torch.distributed as dist
+
+from _dist_utils import run_distributed
+
+
+def _gather_kv(k, v, world):
+    ks = [torch.empty_like(k) for _ in range(world)]
+    vs = [torch.empty_like(v) for _ in range(world)]
+    dist.all_gather(ks, k)
+    dist.all_gather(vs, v)
+    return torch.cat(ks, 2), torch.cat(vs, 2)
+
+
+def _worker(rank, world, cfg):
+    import tree_attention_b200 as ta
+    from tree_attention_b200.ops import reference as ref
+
+    b, hq, hkv, sq, s, d, causal = cfg
+    q, k, v = ta.make_data((b, hq, s, d), rank, "cpu", dtype=torch.float32, sq=sq, num_kv_heads=hkv, log=False)
+    kf, vf = _gather_kv(k, v, world)
+    o_ref, l_ref = ref.attention_ref(q, kf, vf, causal=causal)
+    for sched in ("allreduce3", "allgather", "butterfly", "oneshot"):
+        out, lse = ta.tree_attention(q, k, v, causal=causal, return_lse=True, schedule=sched)
+        assert torch.allclose(out.double(), o_ref, atol=1e-5), (sched, (out.double() - o_ref).abs().max())
+        assert torch.allclose(lse.double(), l_ref, atol=1e-5), sched
+        # every rank holds the same answer
+        outs = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(outs, out.contiguous())
+        for o in outs:
+            assert torch.allclose(o, outs[0], atol=1e-6)
+        if sched in ("allgather", "butterfly", "oneshot") and (world & (world - 1)) == 0:
+            for o in outs:
+                assert torch.equal(o, outs[0]), f"{sched}: not bitwise identical across ranks"
+    # reference-compatible shim (scale 1.0, non-causal)
+    out = ta.tree_decode(q[:, :, :1], k, v, rank, world, torch.device("cpu"))
+    o_ref1, _ = ref.attention_ref(q[:, :, :1], kf, vf, softmax_scale=1.0)
+    assert torch.allclose(out.double(), o_ref1, atol=1e-5)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_tree_attention_gloo(world, port):
+    run_distributed(_worker, world, port, args=((2, 4, 2, 3, 24, 16, True),))
+
+
+def test_baseline_config_1_single_head_seq1024_world2(port):
+    """BASELINE.json config #1: tree_attention() single-head seq=1024 world_size=2 on CPU/gloo."""
+    run_distributed(_worker, 2, port, args=((1, 1, 1, 1, 512, 64, False),))
+
+
+def _worker_unequal(rank, world):
+    """Unequal shards + explicit kv_offset, including a rank whose shard is fully masked."""
+    import tree_attention_b200 as ta
+    from tree_attention_b200.ops import reference as ref
+
+    lens = [5, 9, 2][:world]
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(1, 2, 1, 8, generator=g)
+    kf = torch.randn(1, 2, sum(lens), 8, generator=g)
+    vf = torch.randn(1, 2, sum(lens), 8, generator=g)
+    off = sum(lens[:rank])
+    k, v = kf[:, :, off:off + lens[rank]].contiguous(), vf[:, :, off:off + lens[rank]].contiguous()
+    q_pos = 7  # rank 2 (positions 14..15) is fully masked, rank 1 partially
+    out = ta.tree_attention(q, k, v, causal=True, kv_offset=off, q_offset=q_pos, schedule="allgather")
+    o_ref, _ = ref.attention_partial_ref(q, kf, vf, causal=True, q_pos0=q_pos)
+    assert torch.allclose(out, o_ref, atol=1e-5)
+
+
+def test_unequal_shards_and_masked_rank(port):
+    run_distributed(_worker_unequal, 3, port)

@@ -1,0 +1,187 @@
+// Python bindings (torch extension) for the sm_100a kernels and the symmetric-memory runtime.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <pybind11/stl.h>
+#include <torch/extension.h>
+
+#include <cstring>
+
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace py = pybind11;
+using ta::AttnShape;
+using ta::CommCtxHost;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Symmetric memory: cudaMalloc + CUDA IPC handles.  One buffer per rank, opened by every peer on the
+// node; NVLink P2P access is enabled lazily by cudaIpcOpenMemHandle.  Handle exchange happens in
+// Python over the bootstrap process group (parallel/symm.py).
+// ---------------------------------------------------------------------------------------------
+py::tuple symm_alloc(int64_t nbytes) {
+  void* p = nullptr;
+  TA_CUDA_CHECK(cudaMalloc(&p, (size_t)nbytes));
+  TA_CUDA_CHECK(cudaMemset(p, 0, (size_t)nbytes));
+  TA_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  TA_CUDA_CHECK(cudaIpcGetMemHandle(&h, p));
+  return py::make_tuple((int64_t) reinterpret_cast<uintptr_t>(p),
+                        py::bytes(reinterpret_cast<const char*>(&h), sizeof(h)));
+}
+int64_t symm_open(const std::string& handle) {
+  if (handle.size() != sizeof(cudaIpcMemHandle_t)) throw std::runtime_error("symm_open: bad handle size");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle.data(), sizeof(h));
+  void* p = nullptr;
+  TA_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  return (int64_t) reinterpret_cast<uintptr_t>(p);
+}
+void symm_close(int64_t ptr) { TA_CUDA_CHECK(cudaIpcCloseMemHandle(reinterpret_cast<void*>(ptr))); }
+void symm_free(int64_t ptr) { TA_CUDA_CHECK(cudaFree(reinterpret_cast<void*>(ptr))); }
+void symm_memset(int64_t ptr, int value, int64_t nbytes) {
+  TA_CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<void*>(ptr), value, (size_t)nbytes,
+                                at::cuda::getCurrentCUDAStream()));
+}
+std::vector<uint32_t> symm_read_u32(int64_t ptr, int n) {
+  std::vector<uint32_t> v(n);
+  TA_CUDA_CHECK(cudaMemcpy(v.data(), reinterpret_cast<void*>(ptr), n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  return v;
+}
+
+struct Comm {
+  CommCtxHost h;
+  Comm(int rank, int world, std::vector<int64_t> data, std::vector<int64_t> flags, int64_t epoch, int64_t status,
+       int64_t data_bytes, int64_t flag_bytes, double timeout_s) {
+    if (world > ta::kMaxWorldHost) throw std::runtime_error("world size > 16 not supported");
+    if ((int)data.size() != world || (int)flags.size() != world) throw std::runtime_error("Comm: pointer table size");
+    h.rank = rank;
+    h.world = world;
+    for (int i = 0; i < world; ++i) {
+      h.data[i] = reinterpret_cast<void*>(data[i]);
+      h.flags[i] = reinterpret_cast<void*>(flags[i]);
+    }
+    h.epoch = reinterpret_cast<void*>(epoch);
+    h.status = reinterpret_cast<void*>(status);
+    h.data_bytes = (size_t)data_bytes;
+    h.flag_bytes = (size_t)flag_bytes;
+    h.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  }
+};
+
+AttnShape make_shape(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& out,
+                     double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
+  TORCH_CHECK(q.is_cuda() && k.is_cuda() && v.is_cuda() && out.is_cuda(), "tensors must be CUDA");
+  TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4 && out.dim() == 4, "expected (B, H, S, D) tensors");
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
+  TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type() &&
+                  out.scalar_type() == q.scalar_type(), "q, k, v, out must share a dtype");
+  TORCH_CHECK(q.stride(3) == 1 && k.stride(3) == 1 && v.stride(3) == 1 && out.stride(3) == 1,
+              "head_dim must be contiguous");
+  TORCH_CHECK(k.sizes() == v.sizes(), "k and v shapes differ");
+  TORCH_CHECK(q.size(0) == k.size(0) && q.size(3) == k.size(3), "batch / head_dim mismatch");
+  TORCH_CHECK(out.sizes() == q.sizes(), "out must have q's shape");
+  AttnShape s;
+  s.B = (int)q.size(0); s.Hq = (int)q.size(1); s.Sq = (int)q.size(2); s.D = (int)q.size(3);
+  s.Hkv = (int)k.size(1); s.S = (int)k.size(2);
+  s.is_bf16 = q.scalar_type() == at::kBFloat16;
+  s.softmax_scale = (float)scale;
+  s.causal = causal;
+  s.q_pos0 = q_pos0; s.kv_pos0 = kv_pos0;
+  s.q_sb = q.stride(0); s.q_sh = q.stride(1); s.q_ss = q.stride(2);
+  s.k_sb = k.stride(0); s.k_sh = k.stride(1); s.k_ss = k.stride(2);
+  s.v_sb = v.stride(0); s.v_sh = v.stride(1); s.v_ss = v.stride(2);
+  s.o_sb = out.stride(0); s.o_sh = out.stride(1); s.o_ss = out.stride(2);
+  return s;
+}
+
+py::tuple decode_plan(int B, int Hq, int Hkv, int Sq, int S, int D) {
+  AttnShape s;
+  s.B = B; s.Hq = Hq; s.Hkv = Hkv; s.Sq = Sq; s.S = S; s.D = D;
+  int grid, mp, R;
+  size_t pf, cf, cfl;
+  ta::decode_simt_plan(s, ta::num_sms(), &grid, &mp, &R, &pf, &cf, &cfl);
+  return py::make_tuple(grid, mp, R, (int64_t)pf, (int64_t)cf, (int64_t)cfl);
+}
+
+void decode_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out,
+                c10::optional<at::Tensor> lse, at::Tensor& part, at::Tensor& tickets, py::object comm, double scale,
+                bool causal, int64_t q_pos0, int64_t kv_pos0) {
+  c10::cuda::CUDAGuard guard(q.device());
+  AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
+  TORCH_CHECK(part.scalar_type() == at::kFloat && part.is_contiguous(), "part must be contiguous fp32");
+  TORCH_CHECK(tickets.scalar_type() == at::kInt && tickets.numel() >= s.B * s.Hkv + 2, "tickets too small");
+  int grid, mp, R;
+  size_t pf, cf, cfl;
+  ta::decode_simt_plan(s, ta::num_sms(), &grid, &mp, &R, &pf, &cf, &cfl);
+  TORCH_CHECK((size_t)part.numel() >= pf, "part workspace too small: need ", pf, " floats");
+  float* lse_p = nullptr;
+  if (lse.has_value()) {
+    TORCH_CHECK(lse->scalar_type() == at::kFloat && lse->is_contiguous() && lse->numel() == (int64_t)s.B * s.Hq * s.Sq,
+                "lse must be contiguous fp32 (B, Hq, Sq)");
+    lse_p = lse->data_ptr<float>();
+  }
+  CommCtxHost c;
+  if (!comm.is_none()) c = comm.cast<Comm&>().h;
+  ta::decode_simt_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
+                         reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(),
+                         at::cuda::getCurrentCUDAStream());
+}
+
+void combine(const at::Tensor& o_part, const at::Tensor& lse_part, at::Tensor& out, c10::optional<at::Tensor> lse_out,
+             Comm& comm, int mode) {
+  c10::cuda::CUDAGuard guard(o_part.device());
+  TORCH_CHECK(o_part.scalar_type() == at::kFloat && o_part.is_contiguous(), "o_part must be contiguous fp32");
+  TORCH_CHECK(lse_part.scalar_type() == at::kFloat && lse_part.is_contiguous(), "lse_part must be contiguous fp32");
+  TORCH_CHECK(out.is_contiguous() && out.numel() == o_part.numel(), "out must be contiguous with o_part's size");
+  const int D = (int)o_part.size(-1);
+  const int64_t rows = o_part.numel() / D;
+  TORCH_CHECK(lse_part.numel() == rows, "lse_part must have one entry per row");
+  int dt = out.scalar_type() == at::kFloat ? 0 : out.scalar_type() == at::kBFloat16 ? 1 : 2;
+  TORCH_CHECK(dt != 2 || out.scalar_type() == at::kHalf, "out must be fp32, bf16 or fp16");
+  float* lo = nullptr;
+  if (lse_out.has_value()) {
+    TORCH_CHECK(lse_out->scalar_type() == at::kFloat && lse_out->is_contiguous() && lse_out->numel() == rows);
+    lo = lse_out->data_ptr<float>();
+  }
+  ta::combine_launch(o_part.data_ptr<float>(), lse_part.data_ptr<float>(), out.data_ptr(), dt, lo, rows, D, comm.h,
+                     mode, at::cuda::getCurrentCUDAStream());
+}
+
+void umma_probe(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, bool b_mn_major, bool a_from_tmem) {
+  c10::cuda::CUDAGuard guard(a.device());
+  TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && c.scalar_type() == at::kFloat);
+  TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && c.is_contiguous());
+  TORCH_CHECK(a.size(0) == 128);
+  const int K = (int)a.size(1);
+  const int N = b_mn_major ? (int)b.size(1) : (int)b.size(0);
+  TORCH_CHECK((b_mn_major ? b.size(0) : b.size(1)) == K);
+  TORCH_CHECK(c.size(0) == 128 && c.size(1) == N);
+  ta::umma_probe_launch(a.data_ptr(), b.data_ptr(), c.data_ptr<float>(), N, K, b_mn_major, a_from_tmem,
+                        at::cuda::getCurrentCUDAStream());
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "tree_attention_b200 native extension (sm_100a)";
+  m.def("symm_alloc", &symm_alloc);
+  m.def("symm_open", &symm_open);
+  m.def("symm_close", &symm_close);
+  m.def("symm_free", &symm_free);
+  m.def("symm_memset", &symm_memset);
+  m.def("symm_read_u32", &symm_read_u32);
+  py::class_<Comm>(m, "Comm")
+      .def(py::init<int, int, std::vector<int64_t>, std::vector<int64_t>, int64_t, int64_t, int64_t, int64_t, double>())
+      .def_property("skip_publish", [](Comm& c) { return c.h.skip_publish; }, [](Comm& c, int v) { c.h.skip_publish = v; })
+      .def_property("timeout_s", [](Comm& c) { return c.h.timeout_ns * 1e-9; },
+                    [](Comm& c, double v) { c.h.timeout_ns = (unsigned long long)(v * 1e9); })
+      .def_property_readonly("rank", [](Comm& c) { return c.h.rank; })
+      .def_property_readonly("world", [](Comm& c) { return c.h.world; });
+  m.def("decode_plan", &decode_plan);
+  m.def("decode_fwd", &decode_fwd);
+  m.def("combine", &combine);
+  m.def("umma_probe", &umma_probe);
+  m.def("num_sms", []() { return ta::num_sms(); });
+}

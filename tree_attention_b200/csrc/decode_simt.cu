@@ -1,0 +1,582 @@
+// attn_tree_fused_decode -- split-KV streaming decode attention for sm_100a with the whole
+// tree combine in its epilogue.
+//
+// Replaces, in ONE launch per rank, everything the reference runs for a decode step
+// (/root/reference/model.py:74-80 local attention, :103-124 combine; SURVEY.md 2.3 rows K1-K13 and
+// the three NCCL all-reduces N1-N3):
+//
+//   1. persistent CTAs stream this rank's K/V shard with TMA (cp.async.bulk.tensor, 128B swizzle)
+//      through a 3-6 stage mbarrier ring; work is stream-K balanced over (batch, kv-head, tile);
+//   2. online-softmax partials per warp -> per CTA -> (atomic ticket) per (batch, kv-head);
+//   3. the last-arriving CTA of a head publishes the normalised partial (o, lse) with plain P2P
+//      stores into every peer's symmetric buffer, then releases a per-(head, source) epoch flag with
+//      st.release.sys;  after finishing its remaining tiles it acquires the peers' flags and merges
+//      the W partials in fixed rank order (bitwise identical output on every rank).
+//
+// The math is CUDA-core (decode is a GEMV per head: ~1 FMA per byte of KV, HBM bound).  Query rows
+// R = (GQA group) x Sq <= 4 per pass; larger Sq goes to the tcgen05 kernel (attn_fwd_sm100.cu).
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace ta {
+
+namespace {
+
+constexpr int kTileRows = 128;
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = kConsumerThreads + 32;
+constexpr int kRowsPerWarp = kTileRows / kConsumerWarps;  // 16
+constexpr int kMaxPending = 64;
+
+struct DecodeParams {
+  const void* q;
+  void* out;
+  float* lse;
+  float* part;
+  uint32_t* tickets;  // [BH] tickets, [BH] = done-CTA counter
+  int B, Hq, Hkv, G, Sq, S;
+  int rows_valid;     // G * Sq - r_base, clipped to R
+  int r_base;
+  float scale_log2;
+  int causal;
+  long long q_pos0, kv_pos0;
+  long long q_sb, q_sh, q_ss, o_sb, o_sh, o_ss;
+  int tph;            // tiles per head
+  int total_tiles;
+  int tiles_q, tiles_rem;  // stream-K split: first `rem` CTAs get q+1 tiles
+  int max_parts;
+  CommCtx comm;
+};
+
+template <int D>
+struct SmemLayout {
+  static constexpr int kAtoms = D / 64;
+  static constexpr int kTensorBytes = kTileRows * D * 2;  // one of K or V
+  static constexpr int kStageBytes = 2 * kTensorBytes;
+  static constexpr int kStages = (D == 128) ? 3 : 6;
+};
+
+template <int D, int R>
+constexpr size_t smem_bytes() {
+  return 1024 /*align slack*/ + size_t(SmemLayout<D>::kStages) * SmemLayout<D>::kStageBytes +
+         sizeof(float) * (R * D + kConsumerWarps * R * kRowsPerWarp + kConsumerWarps * R * (D + 4)) +
+         sizeof(int) * (kMaxPending + 8) + sizeof(uint64_t) * 2 * SmemLayout<D>::kStages;
+}
+
+__device__ __forceinline__ int cta_lo(const DecodeParams& p, int c) {
+  return c * p.tiles_q + min(c, p.tiles_rem);
+}
+__device__ __forceinline__ int cta_of_tile(const DecodeParams& p, int t) {
+  const int big = p.tiles_rem * (p.tiles_q + 1);
+  return t < big ? t / (p.tiles_q + 1) : p.tiles_rem + (t - big) / p.tiles_q;
+}
+
+template <bool BF16>
+__device__ __forceinline__ void cvt8(const uint4& w, float (&f)[8]) {
+  if constexpr (BF16) {
+    f[0] = bf16lo(w.x); f[1] = bf16hi(w.x); f[2] = bf16lo(w.y); f[3] = bf16hi(w.y);
+    f[4] = bf16lo(w.z); f[5] = bf16hi(w.z); f[6] = bf16lo(w.w); f[7] = bf16hi(w.w);
+  } else {
+    f[0] = f16lo(w.x); f[1] = f16hi(w.x); f[2] = f16lo(w.y); f[3] = f16hi(w.y);
+    f[4] = f16lo(w.z); f[5] = f16hi(w.z); f[6] = f16lo(w.w); f[7] = f16hi(w.w);
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ float cvt1(uint16_t h) {
+  if constexpr (BF16) return __uint_as_float(uint32_t(h) << 16);
+  else return __half2float(__ushort_as_half(h));
+}
+template <bool BF16>
+__device__ __forceinline__ uint16_t to16(float f) {
+  if constexpr (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  else return __half_as_ushort(__float2half_rn(f));
+}
+
+__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+
+template <int D, int R, bool BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
+                   const DecodeParams p) {
+  using L = SmemLayout<D>;
+  constexpr int NS = L::kStages;
+  constexpr int EPL = D / 32;  // output elements per lane in the PV phase
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  float* q_s = reinterpret_cast<float*>(smem + size_t(NS) * L::kStageBytes);  // [R][D], pre-scaled
+  float* p_s = q_s + R * D;                                                    // [warps][R][16]
+  float* merge_s = p_s + kConsumerWarps * R * kRowsPerWarp;                    // [warps][R][D+4]
+  int* pending = reinterpret_cast<int*>(merge_s + kConsumerWarps * R * (D + 4));
+  int* s_misc = pending + kMaxPending;  // [0]=ticket, [1]=n_pending, [2]=combine ok
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_misc + 8);
+  uint64_t* empty_bar = full_bar + NS;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int t_lo = cta_lo(p, cta);
+  const int t_hi = cta_lo(p, cta + 1);
+  const int world = p.comm.world;
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], kConsumerWarps);
+    }
+    fence_mbar_init();
+    s_misc[1] = 0;
+  }
+  if (warp == kConsumerWarps && lane == 0) {
+    tma_prefetch_desc(&kmap);
+    tma_prefetch_desc(&vmap);
+  }
+  __syncthreads();
+
+  // The epoch of this launch.  Every CTA reads the counter before any CTA can have bumped it (the
+  // bump happens after ALL CTAs passed their end-of-kernel arrival).
+  uint32_t epoch = 0;
+  if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
+  const int parity = epoch & 1;
+  const int BH = p.B * p.Hkv;
+  const long long q_pos_max = p.q_pos0 + p.Sq - 1;
+
+  auto tile_visible = [&](int j) -> bool {
+    return !p.causal || (p.kv_pos0 + (long long)j * kTileRows <= q_pos_max);
+  };
+
+  if (warp == kConsumerWarps) {
+    // ------------------------------- TMA producer --------------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_lo; t < t_hi; ++t) {
+        const int x = t / p.tph, j = t - x * p.tph;
+        if (!tile_visible(j)) continue;
+        const int b = x / p.Hkv, h = x - b * p.Hkv;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+        uint8_t* ks = stage_base + size_t(stage) * L::kStageBytes;
+        uint8_t* vs = ks + L::kTensorBytes;
+#pragma unroll
+        for (int a = 0; a < L::kAtoms; ++a) {
+          tma_load_4d(ks + a * (kTileRows * 128), &kmap, &full_bar[stage], a * 64, j * kTileRows, h, b);
+          tma_load_4d(vs + a * (kTileRows * 128), &vmap, &full_bar[stage], a * 64, j * kTileRows, h, b);
+        }
+        if (++stage == NS) { stage = 0; phase ^= 1; }
+      }
+    }
+    return;
+  }
+
+  // --------------------------------- consumers ----------------------------------------------
+  const int r16 = lane & 15;
+  const int half = lane >> 4;
+  float m_run[R], l_run[R], o_acc[R][EPL];
+  int cur_x = -1;
+  int stage = 0;
+  uint32_t phase = 0;
+
+  auto reset_state = [&]() {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      m_run[r] = neg_inf();
+      l_run[r] = 0.f;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) o_acc[r][e] = 0.f;
+    }
+  };
+
+  auto load_q = [&](int x) {
+    const int b = x / p.Hkv, h = x - b * p.Hkv;
+    for (int idx = tid; idx < R * D; idx += kConsumerThreads) {
+      const int r = idx / D, d = idx - r * D;
+      float val = 0.f;
+      if (r < p.rows_valid) {
+        const int rr = p.r_base + r;
+        const int g = rr / p.Sq, i = rr - g * p.Sq;
+        const uint16_t* qp = reinterpret_cast<const uint16_t*>(p.q) + (long long)b * p.q_sb +
+                             (long long)(h * p.G + g) * p.q_sh + (long long)i * p.q_ss + d;
+        val = cvt1<BF16>(*qp) * p.scale_log2;
+      }
+      q_s[idx] = val;
+    }
+    named_bar_sync(1, kConsumerThreads);
+  };
+
+  // write a finished (b, kv-head) result (normalised o, log2-domain lse) to the user tensors
+  auto store_out = [&](int x, int r, int d, float o_norm, float lse2) {
+    const int b = x / p.Hkv, h = x - b * p.Hkv;
+    const int rr = p.r_base + r;
+    const int g = rr / p.Sq, i = rr - g * p.Sq;
+    uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)b * p.o_sb + (long long)(h * p.G + g) * p.o_sh +
+                   (long long)i * p.o_ss + d;
+    *op = to16<BF16>(o_norm);
+    if (d == 0 && p.lse != nullptr)
+      p.lse[((long long)b * p.Hq + (h * p.G + g)) * p.Sq + i] = lse2 * 0.6931471805599453f;
+  };
+
+  auto slot_ptr = [&](int dst, int src, int x) -> float* {
+    return p.comm.data[dst] + ((size_t)(parity * world + src) * BH + x) * (size_t)(R * (D + 4));
+  };
+  auto flag_ptr = [&](int dst, int src, int x) -> uint32_t* {
+    return p.comm.flags[dst] + ((size_t)(parity * world + src) * BH + x);
+  };
+
+  // merge the W published partials of head x (all in LOCAL memory by now) in rank order
+  auto combine_ranks = [&](int x) {
+    if (tid < world) {
+      bool ok = spin_flag_acquire(flag_ptr(p.comm.rank, tid, x), epoch, p.comm.timeout_ns);
+      if (!ok) {
+        p.comm.status[0] = kCommTimeout; p.comm.status[1] = x; p.comm.status[2] = tid; p.comm.status[3] = epoch;
+        s_misc[2] = 0;
+      }
+    }
+    named_bar_sync(1, kConsumerThreads);
+    const bool ok = s_misc[2] != 0;
+    for (int idx = tid; idx < p.rows_valid * D; idx += kConsumerThreads) {
+      const int r = idx / D, d = idx - r * D;
+      float mx = neg_inf();
+      for (int s = 0; s < world; ++s) mx = fmaxf(mx, ld_relaxed_sys_f(slot_ptr(p.comm.rank, s, x) + r * (D + 4) + D));
+      const float ms = (mx == neg_inf()) ? 0.f : mx;
+      float num = 0.f, den = 0.f;
+      for (int s = 0; s < world; ++s) {
+        const float* sp = slot_ptr(p.comm.rank, s, x) + r * (D + 4);
+        const float w = fast_exp2(ld_relaxed_sys_f(sp + D) - ms);
+        num = fmaf(w, ld_relaxed_sys_f(sp + d), num);
+        den += w;
+      }
+      float o_norm = den > 0.f ? num / den : 0.f;
+      float lse2 = den > 0.f ? ms + fast_log2(den) : neg_inf();
+      if (!ok) { o_norm = __int_as_float(0x7fc00000); lse2 = o_norm; }
+      store_out(x, r, d, o_norm, lse2);
+    }
+    named_bar_sync(1, kConsumerThreads);
+  };
+
+  // per-CTA partial of head x is complete: merge warps, write partial, take a ticket, maybe finish the head
+  auto finalize_segment = [&](int x) {
+    // (a) warps -> smem
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float lt = l_run[r];
+      lt += __shfl_xor_sync(0xffffffffu, lt, 8);
+      lt += __shfl_xor_sync(0xffffffffu, lt, 4);
+      lt += __shfl_xor_sync(0xffffffffu, lt, 2);
+      lt += __shfl_xor_sync(0xffffffffu, lt, 1);
+      float* ms = merge_s + (warp * R + r) * (D + 4);
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) ms[lane * EPL + e] = o_acc[r][e];
+      if (lane == 0) { ms[D] = m_run[r]; ms[D + 1] = lt; }
+    }
+    named_bar_sync(1, kConsumerThreads);
+    // (b) CTA partial -> global
+    const int first_cta = cta_of_tile(p, x * p.tph);
+    const int nparts = cta_of_tile(p, (x + 1) * p.tph - 1) - first_cta + 1;
+    const int pidx = cta - first_cta;
+    float* my_part = p.part + ((size_t)x * p.max_parts + pidx) * (size_t)(R * (D + 4));
+    for (int idx = tid; idx < R * D; idx += kConsumerThreads) {
+      const int r = idx / D, d = idx - r * D;
+      float M = neg_inf();
+#pragma unroll
+      for (int w = 0; w < kConsumerWarps; ++w) M = fmaxf(M, merge_s[(w * R + r) * (D + 4) + D]);
+      const float Ms = (M == neg_inf()) ? 0.f : M;
+      float acc = 0.f, Lsum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kConsumerWarps; ++w) {
+        const float* ms = merge_s + (w * R + r) * (D + 4);
+        const float sc = fast_exp2(ms[D] - Ms);
+        acc = fmaf(ms[d], sc, acc);
+        Lsum = fmaf(ms[D + 1], sc, Lsum);
+      }
+      if (nparts == 1) {
+        // keep in smem-free registers: write straight to the part buffer anyway (uniform path)
+      }
+      __stcg(my_part + r * (D + 4) + d, acc);
+      if (d == 0) { __stcg(my_part + r * (D + 4) + D, M); __stcg(my_part + r * (D + 4) + D + 1, Lsum); }
+    }
+    __threadfence();
+    named_bar_sync(1, kConsumerThreads);
+    if (tid == 0) s_misc[0] = (int)atomicAdd(&p.tickets[x], 1u);
+    named_bar_sync(1, kConsumerThreads);
+    const bool last = (s_misc[0] == nparts - 1);
+    if (!last) return;
+    __threadfence();
+    // (c) last arriver: merge all CTA partials of this head in part order (deterministic)
+    if (tid == 0) p.tickets[x] = 0;
+    const float* parts = p.part + (size_t)x * p.max_parts * (size_t)(R * (D + 4));
+    for (int idx = tid; idx < p.rows_valid * D; idx += kConsumerThreads) {
+      const int r = idx / D, d = idx - r * D;
+      float M = neg_inf();
+      for (int q = 0; q < nparts; ++q) M = fmaxf(M, __ldcg(parts + (size_t)q * (R * (D + 4)) + r * (D + 4) + D));
+      const float Ms = (M == neg_inf()) ? 0.f : M;
+      float acc = 0.f, Lsum = 0.f;
+      for (int q = 0; q < nparts; ++q) {
+        const float* pp = parts + (size_t)q * (R * (D + 4)) + r * (D + 4);
+        const float sc = fast_exp2(__ldcg(pp + D) - Ms);
+        acc = fmaf(__ldcg(pp + d), sc, acc);
+        Lsum = fmaf(__ldcg(pp + D + 1), sc, Lsum);
+      }
+      const float o_norm = Lsum > 0.f ? acc / Lsum : 0.f;
+      const float lse2 = Lsum > 0.f ? Ms + fast_log2(Lsum) : neg_inf();
+      if (world == 1) {
+        store_out(x, r, d, o_norm, lse2);
+      } else if (!p.comm.skip_publish) {
+        // (d) publish to every rank's slot [parity][my rank][x] (own slot included)
+        for (int dst = 0; dst < world; ++dst) {
+          float* sp = slot_ptr(dst, p.comm.rank, x) + r * (D + 4);
+          sp[d] = o_norm;
+          if (d == 0) sp[D] = lse2;
+        }
+      }
+    }
+    if (world > 1) {
+      named_bar_sync(1, kConsumerThreads);
+      if (tid < world && !p.comm.skip_publish) {
+        fence_acq_rel_sys();
+        st_release_sys_u32(flag_ptr(tid, p.comm.rank, x), epoch);
+      }
+      if (tid == 0) {
+        const int n = s_misc[1];
+        if (n < kMaxPending) { pending[n] = x; s_misc[1] = n + 1; }
+        else s_misc[3] = x + 1;  // list full: combine inline below
+      }
+      named_bar_sync(1, kConsumerThreads);
+      if (s_misc[3] != 0) {
+        if (tid == 0) s_misc[3] = 0;
+        combine_ranks(x);
+      }
+    }
+  };
+
+  if (tid == 0) { s_misc[2] = 1; s_misc[3] = 0; }
+
+  for (int t = t_lo; t < t_hi; ++t) {
+    const int x = t / p.tph, j = t - x * p.tph;
+    if (x != cur_x) {
+      if (cur_x >= 0) finalize_segment(cur_x);
+      load_q(x);
+      reset_state();
+      cur_x = x;
+    }
+    if (!tile_visible(j)) continue;
+    mbar_wait(&full_bar[stage], phase);
+    const uint8_t* ks = stage_base + size_t(stage) * L::kStageBytes;
+    const uint8_t* vs = ks + L::kTensorBytes;
+
+    // ---------------- S = q . K^T : lane = (row r16 of this warp's 16 rows, half of D) -------------
+    const int row = warp * kRowsPerWarp + r16;
+    float s_acc[R][4];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { s_acc[r][0] = s_acc[r][1] = s_acc[r][2] = s_acc[r][3] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < D / 16; ++c) {
+      const int cg = half * (D / 16) + c;
+      const int atom = cg >> 3, cia = cg & 7;
+      const uint4 kw = *reinterpret_cast<const uint4*>(ks + atom * (kTileRows * 128) + row * 128 + ((cia ^ (row & 7)) << 4));
+      float kf[8];
+      cvt8<BF16>(kw, kf);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 qa = *reinterpret_cast<const float4*>(q_s + r * D + cg * 8);
+        const float4 qb = *reinterpret_cast<const float4*>(q_s + r * D + cg * 8 + 4);
+        s_acc[r][0] = fmaf(kf[0], qa.x, s_acc[r][0]);
+        s_acc[r][1] = fmaf(kf[1], qa.y, s_acc[r][1]);
+        s_acc[r][2] = fmaf(kf[2], qa.z, s_acc[r][2]);
+        s_acc[r][3] = fmaf(kf[3], qa.w, s_acc[r][3]);
+        s_acc[r][0] = fmaf(kf[4], qb.x, s_acc[r][0]);
+        s_acc[r][1] = fmaf(kf[5], qb.y, s_acc[r][1]);
+        s_acc[r][2] = fmaf(kf[6], qb.z, s_acc[r][2]);
+        s_acc[r][3] = fmaf(kf[7], qb.w, s_acc[r][3]);
+      }
+    }
+    const long long grow = (long long)j * kTileRows + row;
+    const bool inb = grow < p.S;
+    const long long kvpos = p.kv_pos0 + grow;
+    float alpha[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float s = (s_acc[r][0] + s_acc[r][1]) + (s_acc[r][2] + s_acc[r][3]);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      const int i = (p.r_base + r) % p.Sq;
+      const bool vis = inb && (!p.causal || kvpos <= p.q_pos0 + i);
+      s = vis ? s : neg_inf();
+      float mx = s;
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      const float m_new = fmaxf(m_run[r], mx);
+      const float m_safe = (m_new == neg_inf()) ? 0.f : m_new;
+      alpha[r] = fast_exp2(m_run[r] - m_safe);
+      const float pv = fast_exp2(s - m_safe);
+      l_run[r] = fmaf(l_run[r], alpha[r], pv);
+      m_run[r] = m_new;
+      if (half == 0) p_s[(warp * R + r) * kRowsPerWarp + r16] = pv;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) o_acc[r][e] *= alpha[r];
+    }
+    __syncwarp();
+
+    // ---------------- O += P . V : lane = EPL consecutive output columns ---------------------------
+    {
+      const int c0 = lane * EPL;                 // first element of this lane
+      const int atom = (c0 * 2) >> 7;            // 64 elements (128 B) per atom
+      const int inner = (c0 * 2) & 127;
+      const int chunk = inner >> 4, off = inner & 15;
+      const uint8_t* vb = vs + atom * (kTileRows * 128) + off;
+#pragma unroll
+      for (int jj = 0; jj < kRowsPerWarp; jj += 4) {
+        float4 pr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          pr[r] = *reinterpret_cast<const float4*>(p_s + (warp * R + r) * kRowsPerWarp + jj);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int vrow = warp * kRowsPerWarp + jj + u;
+          const uint8_t* vp = vb + vrow * 128 + ((chunk ^ (vrow & 7)) << 4);
+          float vf[EPL];
+          if constexpr (EPL == 4) {
+            const uint2 w = *reinterpret_cast<const uint2*>(vp);
+            if constexpr (BF16) { vf[0] = bf16lo(w.x); vf[1] = bf16hi(w.x); vf[2] = bf16lo(w.y); vf[3] = bf16hi(w.y); }
+            else { vf[0] = f16lo(w.x); vf[1] = f16hi(w.x); vf[2] = f16lo(w.y); vf[3] = f16hi(w.y); }
+          } else {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(vp);
+            if constexpr (BF16) { vf[0] = bf16lo(w); vf[1] = bf16hi(w); }
+            else { vf[0] = f16lo(w); vf[1] = f16hi(w); }
+          }
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float pp = (u == 0) ? pr[r].x : (u == 1) ? pr[r].y : (u == 2) ? pr[r].z : pr[r].w;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) o_acc[r][e] = fmaf(pp, vf[e], o_acc[r][e]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+    if (++stage == NS) { stage = 0; phase ^= 1; }
+  }
+  if (cur_x >= 0) finalize_segment(cur_x);
+
+  // ------------- deferred cross-GPU merges for the heads this CTA finished -----------------------
+  if (world > 1) {
+    named_bar_sync(1, kConsumerThreads);
+    const int n = s_misc[1];
+    for (int i = 0; i < n; ++i) combine_ranks(pending[i]);
+    // end-of-kernel arrival; the last CTA bumps the device-resident epoch for the next launch
+    if (tid == 0) {
+      __threadfence();
+      const uint32_t done = atomicAdd(&p.tickets[BH], 1u);
+      if (done == gridDim.x - 1) {
+        p.tickets[BH] = 0;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(p.comm.epoch) = epoch;
+      }
+    }
+  }
+}
+
+inline CommCtx to_device_ctx(const CommCtxHost& h) {
+  CommCtx c;
+  c.rank = h.rank;
+  c.world = h.world;
+  for (int i = 0; i < kMaxWorld; ++i) {
+    c.data[i] = reinterpret_cast<float*>(h.data[i]);
+    c.flags[i] = reinterpret_cast<uint32_t*>(h.flags[i]);
+  }
+  c.epoch = reinterpret_cast<uint32_t*>(h.epoch);
+  c.status = reinterpret_cast<uint32_t*>(h.status);
+  c.timeout_ns = h.timeout_ns;
+  c.skip_publish = h.skip_publish;
+  return c;
+}
+
+template <int D, int R, bool BF16>
+void launch_one(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeParams& p, int grid,
+                cudaStream_t stream) {
+  auto kern = decode_simt_kernel<D, R, BF16>;
+  constexpr size_t smem = smem_bytes<D, R>();
+  static bool configured = false;
+  if (!configured) {
+    TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  kern<<<grid, kThreads, smem, stream>>>(kmap, vmap, p);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
+
+int pick_rows(int total_rows) { return total_rows >= 4 ? 4 : (total_rows >= 2 ? 2 : 1); }
+
+}  // namespace
+
+void decode_simt_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, int* rows_per_pass,
+                      size_t* part_floats, size_t* comm_floats, size_t* comm_flags) {
+  const int BH = s.B * s.Hkv;
+  const int tph = (s.S + kTileRows - 1) / kTileRows;
+  const long long total = (long long)BH * tph;
+  int g = (int)std::min<long long>(nsm, std::max<long long>(total, 1));
+  const int q = (int)(total / g);
+  int mp = std::min(g, (tph + std::max(q, 1) - 1) / std::max(q, 1) + 1);
+  mp = std::max(mp, 1);
+  const int R = pick_rows((s.Hq / s.Hkv) * s.Sq);
+  *grid = g;
+  *max_parts = mp;
+  *rows_per_pass = R;
+  *part_floats = (size_t)BH * mp * R * (s.D + 4);
+  *comm_floats = (size_t)2 * kMaxWorldHost * BH * R * (s.D + 4);
+  *comm_flags = (size_t)2 * kMaxWorldHost * BH;
+}
+
+void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                        float* part, uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream) {
+  if (s.D != 64 && s.D != 128) throw std::runtime_error("decode_simt: head_dim must be 64 or 128");
+  if (s.Hq % s.Hkv != 0) throw std::runtime_error("decode_simt: Hq must be a multiple of Hkv");
+  if (s.S <= 0) throw std::runtime_error("decode_simt: empty KV shard");
+  int grid, max_parts, R;
+  size_t pf, cf, cfl;
+  decode_simt_plan(s, nsm, &grid, &max_parts, &R, &pf, &cf, &cfl);
+  const int G = s.Hq / s.Hkv;
+  const int total_rows = G * s.Sq;
+  if (comm.world > 1) {
+    const size_t need_data = (size_t)2 * comm.world * s.B * s.Hkv * R * (s.D + 4) * sizeof(float);
+    const size_t need_flags = (size_t)2 * comm.world * s.B * s.Hkv * sizeof(uint32_t);
+    if (need_data > comm.data_bytes || need_flags > comm.flag_bytes)
+      throw std::runtime_error("decode_simt: symmetric buffer too small for this problem");
+  }
+  CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, s.D, s.k_sb, s.k_sh, s.k_ss, 64, kTileRows,
+                                    CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap vmap = make_tmap_bhsd(v, 2, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 64, kTileRows,
+                                    CU_TENSOR_MAP_SWIZZLE_128B);
+  DecodeParams p;
+  p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
+  p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S;
+  p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
+  p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;
+  p.q_sb = s.q_sb; p.q_sh = s.q_sh; p.q_ss = s.q_ss; p.o_sb = s.o_sb; p.o_sh = s.o_sh; p.o_ss = s.o_ss;
+  p.tph = (s.S + kTileRows - 1) / kTileRows;
+  p.total_tiles = s.B * s.Hkv * p.tph;
+  p.tiles_q = p.total_tiles / grid;
+  p.tiles_rem = p.total_tiles % grid;
+  p.max_parts = max_parts;
+  p.comm = to_device_ctx(comm);
+  for (int r_base = 0; r_base < total_rows; r_base += R) {
+    p.r_base = r_base;
+    p.rows_valid = std::min(R, total_rows - r_base);
+#define TA_LAUNCH(DD, RR)                                                              \
+  if (s.is_bf16) launch_one<DD, RR, true>(kmap, vmap, p, grid, stream);                \
+  else launch_one<DD, RR, false>(kmap, vmap, p, grid, stream);
+    if (s.D == 128) {
+      if (R == 4) { TA_LAUNCH(128, 4) } else if (R == 2) { TA_LAUNCH(128, 2) } else { TA_LAUNCH(128, 1) }
+    } else {
+      if (R == 4) { TA_LAUNCH(64, 4) } else if (R == 2) { TA_LAUNCH(64, 2) } else { TA_LAUNCH(64, 1) }
+    }
+#undef TA_LAUNCH
+  }
+}
+
+}  // namespace ta

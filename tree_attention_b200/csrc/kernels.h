@@ -1,0 +1,60 @@
+// Plain-C++ launcher interface between the CUDA translation units and the torch bindings.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ta {
+
+constexpr int kMaxWorldHost = 16;
+
+struct CommCtxHost {
+  int rank = 0;
+  int world = 1;
+  void* data[kMaxWorldHost] = {nullptr};
+  void* flags[kMaxWorldHost] = {nullptr};
+  void* epoch = nullptr;
+  void* status = nullptr;
+  unsigned long long timeout_ns = 10ull * 1000 * 1000 * 1000;
+  int skip_publish = 0;
+  size_t data_bytes = 0;
+  size_t flag_bytes = 0;
+};
+
+struct AttnShape {
+  int B = 1, Hq = 1, Hkv = 1, Sq = 1, S = 0, D = 128;
+  int is_bf16 = 1;
+  float softmax_scale = 1.f;
+  int causal = 0;
+  int64_t q_pos0 = 0;   // global position of query row 0
+  int64_t kv_pos0 = 0;  // global position of local key row 0
+  // element strides, innermost (D) contiguous
+  int64_t q_sb = 0, q_sh = 0, q_ss = 0;
+  int64_t k_sb = 0, k_sh = 0, k_ss = 0;
+  int64_t v_sb = 0, v_sh = 0, v_ss = 0;
+  int64_t o_sb = 0, o_sh = 0, o_ss = 0;
+};
+
+// ---- split-KV streaming decode (CUDA-core math, TMA-fed), fused split merge + cross-GPU combine ----
+// workspace sizes for a given problem; `grid` is returned so that callers can cache it.
+void decode_simt_plan(const AttnShape& s, int num_sms, int* grid, int* max_parts, int* rows_per_pass,
+                      size_t* part_floats, size_t* comm_floats, size_t* comm_flags);
+// out: same dtype as q.  lse: fp32 (B, Hq, Sq) natural log, may be null.
+// part: float workspace, tickets: uint32 [B*Hkv + 2] zero-initialised once.
+void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                        float* part, uint32_t* tickets, const CommCtxHost& comm, int num_sms,
+                        cudaStream_t stream);
+
+// ---- stand-alone combine of W per-rank partials (o fp32 normalised, lse natural log) ----
+// local: o_part (rows, D) fp32 + lse_part (rows); result written to out (dtype of `is_bf16`/fp16/fp32)
+// mode 0: one-shot push (every rank publishes to every peer, merges all W in rank order)
+// mode 1: butterfly (log2 W rounds of pairwise exchange)
+void combine_launch(const float* o_part, const float* lse_part, void* out, int out_dtype, float* lse_out,
+                    int64_t rows, int D, const CommCtxHost& comm, int mode, cudaStream_t stream);
+
+// ---- tcgen05 probes / attention forward (attn_fwd_sm100.cu) ----
+// C[M=128, N] (fp32) = A[128, K] * B^T ; a, b bf16.  b_mn_major: B given as (K, N) row-major (V-like).
+// a_from_tmem: A is first staged through TMEM (tcgen05.st) and consumed with the .ts MMA form.
+void umma_probe_launch(const void* a, const void* b, float* c, int N, int K, int b_mn_major, int a_from_tmem,
+                       cudaStream_t stream);
+
+}  // namespace ta

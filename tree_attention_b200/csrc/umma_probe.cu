@@ -1,0 +1,136 @@
+// umma_probe -- a one-CTA tcgen05 GEMM used by tests to pin down, on real hardware, every layout
+// convention the attention kernels rely on: TMA 128B-swizzled tiles, K-major and MN-major shared
+// memory descriptors, the instruction descriptor, A-operand-from-TMEM, and the tcgen05.ld lane map.
+//
+//   C[128, N] (fp32) = A[128, K] (bf16, row-major) x B
+//     b_mn_major = 0 : B is (N, K) row-major  ("K-major", like K in Q K^T)
+//     b_mn_major = 1 : B is (K, N) row-major  ("MN-major", like V in P V)
+//     a_from_tmem = 1: A is written to TMEM with tcgen05.st and consumed by the .ts MMA form (like P)
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace ta {
+namespace {
+
+struct ProbeParams {
+  const uint16_t* a;
+  float* c;
+  int N, K, b_mn_major, a_from_tmem;
+};
+
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
+                  const ProbeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N, K = p.K;
+  uint8_t* a_s = smem;                       // [K/64][128][128B]
+  uint8_t* b_s = smem + (K / 64) * 16384;    // K-major: [K/64][N][128B] ; MN-major: [N/64][K][128B]
+
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {
+    const uint32_t bytes = 128 * K * 2 + N * K * 2;
+    mbar_arrive_expect_tx(&bar_load, bytes);
+    for (int ka = 0; ka < K / 64; ++ka) tma_load_2d(a_s + ka * 16384, &amap, &bar_load, ka * 64, 0);
+    if (!p.b_mn_major) {
+      for (int ka = 0; ka < K / 64; ++ka) tma_load_2d(b_s + ka * (N * 128), &bmap, &bar_load, ka * 64, 0);
+    } else {
+      for (int na = 0; na < N / 64; ++na) tma_load_2d(b_s + na * (K * 128), &bmap, &bar_load, na * 64, 0);
+    }
+  }
+  if (p.a_from_tmem) {
+    // thread t owns row t of A: pack bf16 pairs, 32 columns (64 elements) per tcgen05.st
+    const uint16_t* arow = p.a + (size_t)tid * K;
+    for (int c0 = 0; c0 < K / 2; c0 += 32) {
+      uint32_t v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = uint32_t(arow[(c0 + i) * 2]) | (uint32_t(arow[(c0 + i) * 2 + 1]) << 16);
+      tmem_st_32x32b_x32(tmem + (uint32_t(warp * 32) << 16) + 256 + c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    mbar_wait(&bar_load, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc(1, 1, 128, N, 0, p.b_mn_major ? 1 : 0);
+      for (int kk = 0; kk < K / 16; ++kk) {
+        uint64_t bdesc;
+        if (!p.b_mn_major)
+          bdesc = umma_smem_desc_sw128(smem_u32(b_s) + (kk / 4) * (N * 128) + (kk % 4) * 32, 0, 1024);
+        else
+          bdesc = umma_smem_desc_sw128(smem_u32(b_s) + kk * 2048, K * 128, 1024);
+        if (p.a_from_tmem) {
+          umma_ts_f16(tmem, tmem + 256 + kk * 8, bdesc, idesc, kk > 0 ? 1u : 0u);
+        } else {
+          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(a_s) + (kk / 4) * 16384 + (kk % 4) * 32, 0, 1024);
+          umma_ss_f16(tmem, adesc, bdesc, idesc, kk > 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(&bar_mma);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(tmem + (uint32_t(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p.c[(size_t)tid * N + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace
+
+void umma_probe_launch(const void* a, const void* b, float* c, int N, int K, int b_mn_major, int a_from_tmem,
+                       cudaStream_t stream) {
+  if (K % 64 != 0 || K > 256 || N % 16 != 0 || N < 16 || N > 256) throw std::runtime_error("umma_probe: bad N/K");
+  if (b_mn_major && N % 64 != 0) throw std::runtime_error("umma_probe: MN-major B needs N % 64 == 0");
+  // the 2-D TMA instruction needs rank-2 maps
+  CUtensorMap amap, bmap;
+  {
+    auto enc = get_encode_tiled();
+    auto mk = [&](const void* base, uint64_t inner, uint64_t outer, uint32_t box_in, uint32_t box_out) {
+      CUtensorMap m;
+      cuuint64_t dims[2] = {inner, outer};
+      cuuint64_t strides[1] = {inner * 2};
+      cuuint32_t box[2] = {box_in, box_out};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) throw std::runtime_error("umma_probe: cuTensorMapEncodeTiled failed " + std::to_string((int)r));
+      return m;
+    };
+    amap = mk(a, K, 128, 64, 128);
+    bmap = b_mn_major ? mk(b, N, K, 64, K) : mk(b, K, N, 64, N);
+  }
+  ProbeParams p{reinterpret_cast<const uint16_t*>(a), c, N, K, b_mn_major, a_from_tmem};
+  const size_t smem = 1024 + (size_t)128 * K * 2 + (size_t)N * K * 2;
+  TA_CUDA_CHECK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_probe_kernel<<<1, 128, smem, stream>>>(amap, bmap, p);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace ta

@@ -1,0 +1,140 @@
+"""Local (single-shard) attention partial: ``(o, lse)`` of ``q`` against this rank's K/V.
+
+Reference parity: ``flash_res_lse`` (``/root/reference/model.py:60-83``) -- same name, signature and
+``(res, lse)`` contract, with ``lse`` the logsumexp of the scaled logits (fix of D2) and a true
+``-inf`` causal mask (fix of D6).  On CUDA the work is done by the hand-written sm_100a kernels:
+
+* ``decode``  -- ``csrc/decode_simt.cu``   (Sq x GQA-group small: HBM-bound streaming, split-KV)
+* ``fwd``     -- ``csrc/attn_fwd_sm100.cu`` (tcgen05/TMEM/TMA flash forward)
+
+and on CPU by the PyTorch oracle in ``ops/reference.py``.  There is no silent CUDA->PyTorch fallback:
+if the extension is missing on a GPU machine, importing it raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from .. import _build
+from . import reference as ref
+
+_WS: Dict[tuple, Dict[str, torch.Tensor]] = {}
+
+DECODE_MAX_ROWS = 16  # Sq * (Hq / Hkv) handled by the streaming decode kernel (4 rows per pass)
+
+
+def _as_bhsd(x: torch.Tensor) -> torch.Tensor:
+    """Accept any strides as long as head_dim is contiguous (BHSD or BSHD-strided views)."""
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    return x
+
+
+def _workspace(device: torch.device, tag: str, nfloats: int, nticket: int) -> Dict[str, torch.Tensor]:
+    key = (device.index, tag)
+    ws = _WS.get(key)
+    if ws is None or ws["part"].numel() < nfloats or ws["tickets"].numel() < nticket:
+        ws = {
+            "part": torch.empty(max(nfloats, 1), dtype=torch.float32, device=device),
+            "tickets": torch.zeros(max(nticket, 64), dtype=torch.int32, device=device),
+        }
+        _WS[key] = ws
+    return ws
+
+
+def decode_eligible(q: torch.Tensor, k: torch.Tensor) -> bool:
+    if not q.is_cuda or q.dtype not in (torch.bfloat16, torch.float16):
+        return False
+    d = q.shape[-1]
+    g = q.shape[1] // k.shape[1]
+    return d in (64, 128) and q.shape[2] * g <= DECODE_MAX_ROWS
+
+
+def decode_attention(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    softmax_scale: float,
+    causal: bool = False,
+    q_pos0: int = 0,
+    kv_pos0: int = 0,
+    comm=None,
+    out: Optional[torch.Tensor] = None,
+    lse: Optional[torch.Tensor] = None,
+    return_lse: bool = True,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Launch the fused streaming decode kernel.  With ``comm`` (a ``_C.Comm``) the kernel also performs
+    the cross-GPU tree combine and ``out``/``lse`` are the GLOBAL results, identical on every rank."""
+    C = _build.load()
+    q, k, v = _as_bhsd(q), _as_bhsd(k), _as_bhsd(v)
+    b, hq, sq, d = q.shape
+    hkv, s = k.shape[1], k.shape[2]
+    grid, max_parts, rows, part_floats, _, _ = C.decode_plan(b, hq, hkv, sq, s, d)
+    ws = _workspace(q.device, "decode", part_floats, b * hkv + 2)
+    if out is None:
+        out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
+    if lse is None and return_lse:
+        lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
+    C.decode_fwd(q, k, v, out, lse, ws["part"], ws["tickets"], comm, float(softmax_scale), bool(causal),
+                 int(q_pos0), int(kv_pos0))
+    return out, lse
+
+
+def decode_comm_bytes(b: int, hq: int, hkv: int, sq: int, s: int, d: int, world: int) -> Tuple[int, int]:
+    """(data_bytes, flag_bytes) the decode family needs in symmetric memory."""
+    rows = min(4, max(1, (hq // hkv) * sq))
+    rows = 4 if rows >= 4 else (2 if rows >= 2 else 1)
+    data = 2 * world * b * hkv * rows * (d + 4) * 4
+    flags = 2 * world * b * hkv * 4
+    return data, flags
+
+
+def attention_partial(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    softmax_scale: Optional[float] = None,
+    causal: bool = False,
+    q_pos0: int = 0,
+    kv_pos0: int = 0,
+    impl: str = "auto",
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Shard-local attention: returns ``(o, lse)`` with ``o`` in q's dtype (fp32 on CPU) and ``lse`` fp32."""
+    scale = ref.default_scale(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
+    if q.is_cuda:
+        if impl in ("auto", "decode") and decode_eligible(q, k):
+            return decode_attention(q, k, v, scale, causal, q_pos0, kv_pos0)
+        if impl in ("auto", "fwd"):
+            from . import flash
+
+            if flash.fwd_eligible(q, k):
+                return flash.attention_fwd(q, k, v, scale, causal, q_pos0, kv_pos0)
+        if impl == "torch":
+            o, l = ref.attention_partial_ref(q, k, v, scale, causal, q_pos0, kv_pos0, torch.float32, block=8192)
+            return o.to(q.dtype), l
+        raise RuntimeError(
+            f"no sm_100a kernel covers q={tuple(q.shape)} k={tuple(k.shape)} dtype={q.dtype}; "
+            "pass impl='torch' explicitly to use the (slow) PyTorch path"
+        )
+    o, l = ref.attention_partial_ref(q, k, v, scale, causal, q_pos0, kv_pos0, torch.float32,
+                                     block=8192 if q.shape[2] * k.shape[2] > (1 << 26) else 0)
+    return o, l
+
+
+def flash_res_lse(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    softmax_scale: float = 1.0,
+    is_causal: bool = False,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Drop-in for the reference's ``flash_res_lse`` (model.py:60): ``(res, lse)`` for BHSD inputs.
+
+    ``softmax_scale`` keeps the reference default of 1.0 for signature parity (D7); ``lse`` has shape
+    ``res.shape[:-1]`` and is the logsumexp of the scaled logits.  With ``is_causal`` the queries are
+    taken to be the LAST ``Sq`` positions of the key sequence.
+    """
+    q_pos0 = k.shape[2] - q.shape[2]
+    res, lse = attention_partial(q, k, v, softmax_scale, is_causal, q_pos0, 0)
+    return res, lse

@@ -1,0 +1,247 @@
+"""Tree Attention: sequence-parallel attention over a KV sequence sharded across ranks.
+
+Reference parity: ``tree_decode(q, k, v, rank, world_size, device)`` (``/root/reference/model.py:85-124``)
+and the ``tree_attention()`` entry point named by BASELINE.json.  Q is replicated, every rank owns a
+contiguous KV shard, each rank computes a local partial ``(o_r, lse_r)`` and the partials are merged
+with the exact associative combine ``out = sum_r o_r e^{lse_r - m} / sum_r e^{lse_r - m}``.
+
+Backends
+--------
+``fused``   one hand-written sm_100a kernel per rank: local attention + split merge + cross-GPU combine
+            over symmetric memory (P2P stores, release/acquire epoch flags).  No NCCL on the path.
+``symm``    local attention kernel, then the stand-alone ``combine_partials`` kernel over symmetric
+            memory (one-shot or butterfly).  No NCCL on the path.
+``nccl`` / ``gloo``  local partial + ``torch.distributed`` collectives: the reference's structure
+            (``schedule="allreduce3"`` = MAX, SUM, SUM exactly as model.py:108-115, but with an
+            ``|O| + 2``-scalar payload instead of ``3|O|``), or one packed ``allgather``, or a real
+            pairwise ``butterfly`` tree.  This is the baseline and the CPU plumbing path.
+``local``   world size 1.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import torch
+import torch.distributed as dist
+
+from ..ops import local as local_ops
+from ..ops import reference as ref
+from . import symm
+from .runtime import get_runtime
+
+_BACKENDS = ("auto", "fused", "symm", "nccl", "gloo", "collective", "local")
+_SCHEDULES = ("oneshot", "butterfly", "allreduce3", "allgather")
+
+
+def _world(group) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def _resolve_backend(backend: str, q: torch.Tensor, world: int) -> str:
+    if backend not in _BACKENDS:
+        raise ValueError(f"backend must be one of {_BACKENDS}")
+    if world == 1:
+        return "local"
+    if backend in ("nccl", "gloo"):
+        return "collective"
+    if backend == "auto":
+        return "fused" if q.is_cuda else "collective"
+    return backend
+
+
+# ------------------------------------------------------------------------------------------------
+# collective-based combines (baseline / CPU)
+# ------------------------------------------------------------------------------------------------
+def _combine_allreduce3(o: torch.Tensor, lse: torch.Tensor, group) -> Tuple[torch.Tensor, torch.Tensor]:
+    """MAX, SUM, SUM -- the reference's schedule (model.py:108,114,115) with fp32 statistics and a
+    per-row (not per-element) max/denominator payload (fixes D8/D9)."""
+    o32 = o.float()
+    m = lse.clone()
+    dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
+    dead = torch.isinf(m) & (m < 0)
+    m_safe = torch.where(dead, torch.zeros_like(m), m)
+    w = torch.exp(lse - m_safe)
+    num = o32 * w[..., None]
+    den = w.clone()
+    dist.all_reduce(num, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(den, op=dist.ReduceOp.SUM, group=group)
+    den_safe = torch.where(dead, torch.ones_like(den), den)
+    out = num / den_safe[..., None]
+    lse_g = torch.where(dead, torch.full_like(m, float("-inf")), m_safe + torch.log(den_safe))
+    return out, lse_g
+
+
+def _combine_allgather(o: torch.Tensor, lse: torch.Tensor, group) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One packed all-gather of (o, lse), then a local merge in fixed rank order (deterministic)."""
+    world = dist.get_world_size(group)
+    packed = torch.cat([o.float(), lse[..., None]], dim=-1).contiguous()
+    gathered = [torch.empty_like(packed) for _ in range(world)]
+    dist.all_gather(gathered, packed, group=group)
+    os_ = [g[..., :-1] for g in gathered]
+    ls_ = [g[..., -1] for g in gathered]
+    return ref.merge_many(os_, ls_)
+
+
+def _combine_butterfly(o: torch.Tensor, lse: torch.Tensor, group) -> Tuple[torch.Tensor, torch.Tensor]:
+    """log2(W) rounds of pairwise exchange; both partners apply merge(lower, higher) => identical bits."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world & (world - 1):
+        return _combine_allgather(o, lse, group)
+    cur = torch.cat([o.float(), lse[..., None]], dim=-1).contiguous()
+    k = 1
+    while k < world:
+        partner = rank ^ k
+        other = torch.empty_like(cur)
+        gp = dist.get_global_rank(group, partner) if group is not None else partner
+        ops = [dist.P2POp(dist.isend, cur, gp, group), dist.P2POp(dist.irecv, other, gp, group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        lo, hi = (cur, other) if rank < partner else (other, cur)
+        o_m, l_m = ref.merge_pair(lo[..., :-1], lo[..., -1], hi[..., :-1], hi[..., -1])
+        cur = torch.cat([o_m, l_m[..., None]], dim=-1).contiguous()
+        k <<= 1
+    return cur[..., :-1], cur[..., -1]
+
+
+def combine_partials(
+    o: torch.Tensor,
+    lse: torch.Tensor,
+    group=None,
+    backend: str = "auto",
+    schedule: str = "oneshot",
+    out_dtype: Optional[torch.dtype] = None,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge per-rank partials ``(o, lse)`` across ``group``; the result is replicated on every rank."""
+    rank, world = _world(group)
+    out_dtype = out_dtype or o.dtype
+    if world == 1:
+        return o.to(out_dtype), lse
+    use_symm = o.is_cuda and backend in ("auto", "symm", "fused")
+    if use_symm:
+        from .. import _build
+
+        C = _build.load()
+        mode = 1 if schedule == "butterfly" and (world & (world - 1)) == 0 else 0
+        d = o.shape[-1]
+        rows = o.numel() // d
+        nchunks = (rows + 7) // 8
+        import math
+
+        rounds = max(1, int(math.ceil(math.log2(world))))
+        slots = world if mode == 0 else rounds
+        reg = symm.get_region("combine", 2 * slots * rows * (d + 4) * 4, 2 * slots * nchunks * 4, group)
+        o32 = o.float().contiguous()
+        lse32 = lse.float().contiguous()
+        out = torch.empty(o.shape, dtype=out_dtype if out_dtype in (torch.float32, torch.bfloat16, torch.float16)
+                          else torch.float32, device=o.device)
+        lse_out = torch.empty_like(lse32)
+        C.combine(o32, lse32, out, lse_out, reg.comm, mode)
+        return out.to(out_dtype), lse_out
+    if schedule == "allreduce3":
+        out, lse_g = _combine_allreduce3(o, lse, group)
+    elif schedule == "butterfly":
+        out, lse_g = _combine_butterfly(o, lse, group)
+    else:
+        out, lse_g = _combine_allgather(o, lse, group)
+    return out.to(out_dtype), lse_g
+
+
+# ------------------------------------------------------------------------------------------------
+# public API
+# ------------------------------------------------------------------------------------------------
+def tree_attention(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    *,
+    group=None,
+    causal: bool = False,
+    softmax_scale: Optional[float] = None,
+    kv_offset: Optional[int] = None,
+    q_offset: Optional[int] = None,
+    return_lse: bool = False,
+    backend: str = "auto",
+    schedule: str = "oneshot",
+    layout: str = "bhsd",
+) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+    """Exact attention of replicated ``q`` over a KV sequence sharded across the ranks of ``group``.
+
+    q: ``(B, Hq, Sq, D)``; k, v: ``(B, Hkv, S_local, D)`` -- this rank's contiguous shard (``layout="bshd"``
+    takes ``(B, S, H, D)`` tensors instead).  ``softmax_scale=None`` means ``1/sqrt(D)``.
+
+    Causal masking uses GLOBAL positions: key ``j`` of this shard sits at ``kv_offset + j`` (default
+    ``rank * S_local``: equal contiguous shards) and query ``i`` at ``q_offset + i`` (default: the last
+    ``Sq`` positions of the global sequence, i.e. decode / chunked-prefill convention).
+
+    Returns the global attention output (replicated, bitwise identical across ranks for the fused and
+    symm backends) and optionally the global ``lse``.
+    """
+    if layout == "bshd":
+        q, k, v = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+    elif layout != "bhsd":
+        raise ValueError("layout must be 'bhsd' or 'bshd'")
+    rank, world = _world(group)
+    scale = ref.default_scale(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
+    s_local = k.shape[2]
+    kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
+    q_pos0 = (world * s_local - q.shape[2]) if q_offset is None else int(q_offset)
+    be = _resolve_backend(backend, q, world)
+
+    if be == "local":
+        o, lse = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0)
+    elif be == "fused":
+        if not q.is_cuda:
+            raise RuntimeError("backend='fused' needs CUDA tensors")
+        if local_ops.decode_eligible(q, k):
+            b, hq, sq, d = q.shape
+            data, flags = local_ops.decode_comm_bytes(b, hq, k.shape[1], sq, s_local, d, world)
+            reg = symm.get_region("decode", data, flags, group)
+            o, lse = local_ops.decode_attention(q, k, v, scale, causal, q_pos0, kv_pos0, comm=reg.comm,
+                                                return_lse=return_lse)
+        else:
+            from ..ops import flash
+
+            o, lse = flash.attention_fwd_fused(q, k, v, scale, causal, q_pos0, kv_pos0, group=group,
+                                               return_lse=return_lse)
+    else:  # symm | collective
+        o_p, lse_p = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0)
+        sched = schedule
+        if be == "collective" and schedule == "oneshot":
+            sched = "allgather"
+        o, lse = combine_partials(o_p, lse_p, group, "symm" if be == "symm" else "collective", sched,
+                                  out_dtype=o_p.dtype)
+    if layout == "bshd":
+        o = o.transpose(1, 2)
+    return (o, lse) if return_lse else o
+
+
+def tree_decode(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    rank: int = 0,
+    world_size: int = 1,
+    device=None,
+    *,
+    softmax_scale: float = 1.0,
+    backend: str = "auto",
+    schedule: str = "oneshot",
+    group=None,
+) -> torch.Tensor:
+    """Signature-compatible shim for the reference's ``tree_decode`` (model.py:85).
+
+    ``rank``/``world_size``/``device`` are accepted for parity (the reference only uses them for log
+    lines and the distributed-branch gate); the process group decides the real topology.  Like the
+    reference it applies NO ``1/sqrt(d)`` scaling by default (model.py:60,100 -- D7) and is non-causal.
+    Accepts BHSD ``q: (B, nh, 1, C)``, ``k, v: (B, nh, T, C)``.
+    """
+    _, world = _world(group)
+    if world_size > 1 and world == 1:
+        raise RuntimeError(
+            f"tree_decode called with world_size={world_size} but no process group is initialised; "
+            "call setup(rank, world_size) first"
+        )
+    return tree_attention(q, k, v, group=group, causal=False, softmax_scale=softmax_scale, backend=backend,
+                          schedule=schedule)

@@ -1,0 +1,79 @@
+"""Configuration: one dataclass, argparse + environment overrides.
+
+The reference has no config system; every value is a literal in ``main()``
+(``/root/reference/model.py:140-145``, ``:20-22``, ``:160``).  The defaults below
+ARE those literals, so a bare ``python3 model.py`` reproduces the reference's problem shape.
+"""
+from __future__ import annotations
+
+import argparse
+import dataclasses
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+_DTYPES = {"fp16": torch.float16, "float16": torch.float16, "bf16": torch.bfloat16,
+           "bfloat16": torch.bfloat16, "fp32": torch.float32, "float32": torch.float32}
+
+
+@dataclass
+class TreeAttentionConfig:
+    # problem shape -- model.py:140-145
+    batch: int = 1
+    num_heads: int = 16
+    num_kv_heads: Optional[int] = None
+    seq_len: int = 64000            # per-rank KV length (the reference's weak-scaling convention)
+    head_dim: int = 128
+    q_len: int = 1                  # decode; the reference's only mode
+    dtype: str = "fp16"             # model.py:51-53
+    layout: str = "bhsd"
+    causal: bool = False
+    softmax_scale: Optional[float] = None
+    # execution
+    backend: str = "auto"           # auto | fused | nccl | gloo | local
+    schedule: str = "oneshot"       # oneshot | butterfly | allreduce3 | allgather
+    steps: int = 1                  # the reference times exactly one call (model.py:149-151)
+    warmup: int = 0
+    check: bool = True              # validate against the oracle
+    # rendezvous -- model.py:20-21
+    master_addr: str = "127.0.0.1"
+    master_port: int = 12355
+    # logging -- model.py:160
+    log_file: str = "tree_attention_log.log"
+    log_rotation: str = "10 MB"
+    json: bool = False
+    seed: int = 0
+
+    @property
+    def torch_dtype(self) -> torch.dtype:
+        return _DTYPES[self.dtype]
+
+    @property
+    def kv_heads(self) -> int:
+        return self.num_heads if self.num_kv_heads is None else self.num_kv_heads
+
+
+def add_args(p: argparse.ArgumentParser) -> argparse.ArgumentParser:
+    for f in dataclasses.fields(TreeAttentionConfig):
+        name = "--" + f.name.replace("_", "-")
+        env = os.environ.get("TREE_ATTN_" + f.name.upper())
+        default = f.default
+        if f.type in ("bool", bool):
+            if env is not None:
+                default = env.lower() in ("1", "true", "yes")
+            p.add_argument(name, action=argparse.BooleanOptionalAction, default=default)
+            continue
+        typ = {"int": int, "float": float, "str": str, "Optional[int]": int,
+               "Optional[float]": float}.get(str(f.type), str)
+        if env is not None:
+            default = typ(env)
+        p.add_argument(name, type=typ, default=default)
+    return p
+
+
+def from_args(argv=None) -> TreeAttentionConfig:
+    p = add_args(argparse.ArgumentParser(description="Tree Attention (B200-native) CLI"))
+    ns = p.parse_args(argv)
+    return TreeAttentionConfig(**vars(ns))
