@@ -1,0 +1,407 @@
+"""Headline benchmark (driver contract): ``python bench.py --gpus N --steps K --warmup W [--impl reference]``.
+
+Metric (BASELINE.json): attention forward tokens/sec, whole box, device-timed, max over ranks, at
+seq = 128K, 32 heads, d = 128, bf16, synthetic Q/K/V.  The step is the reference's only mode -- ONE
+tree-decode attention forward (Sq = 1) over the full 128K-token KV sequence, which is sharded across the
+N GPUs (strong scaling: the sequence is fixed, S/N keys per rank).  ``value`` = B * S_global / latency
+(sequence tokens attended per second); ``decode_tokens_per_s`` = B / latency is reported alongside.
+
+Own arm: one fused sm_100a kernel per rank per step (local split-KV attention + in-kernel cross-GPU
+combine over symmetric memory, no NCCL on the path).
+Reference arm (``--impl reference``): the UNMODIFIED ``baseline/_ref/model.py`` ``tree_decode`` through its
+own public API on BHSD tensors.  For N > 1 it raises at model.py:111 and the arm reports
+``unavailable``.
+
+Timing rules implemented here: W >= 3 warm-ups; CUDA events on the launching stream bracketed by barrier +
+synchronize; max over ranks; the KV working set cycled per step is > 4x the 126 MB L2 (several KV buffers
+are rotated like layers of a model) so no step is served from L2; SM clocks / throttle reasons are sampled
+with nvidia-smi DURING the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+L2_BYTES = 126 << 20
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=400)
+    p.add_argument("--warmup", type=int, default=20)
+    p.add_argument("--impl", default="own", choices=["own", "reference"])
+    p.add_argument("--seq", type=int, default=131072, help="GLOBAL KV sequence length")
+    p.add_argument("--heads", type=int, default=32)
+    p.add_argument("--kv-heads", type=int, default=None)
+    p.add_argument("--head-dim", type=int, default=128)
+    p.add_argument("--batch", type=int, default=1)
+    p.add_argument("--dtype", default="bf16")
+    p.add_argument("--backend", default="fused")
+    p.add_argument("--no-extras", action="store_true", help="skip the NCCL-comparator / full-forward extras")
+    p.add_argument("--graph", action=argparse.BooleanOptionalAction, default=True,
+                   help="replay the step from a CUDA graph (launch-bound at 8 GPUs)")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampler (the profiling recipe's clocks line) running while the timed region executes."""
+
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int, period_ms: int = 50):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+        self.t_start = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-i", str(gpu_index),
+                 "-lms", str(period_ms)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0: float, t1: float) -> dict:
+        sm, mx, reasons, power = [], [], set(), []
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.06:
+                continue
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 10:
+                continue
+            try:
+                sm.append(float(parts[2])); mx.append(float(parts[3])); power.append(float(parts[4]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[6:10]):
+                if val.lower() == "active":
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+# ------------------------------------------------------------------------------------------------
+def emit(d: dict):
+    print(json.dumps(d), flush=True)
+
+
+def reexec_with_torchrun(args):
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    os.execv(sys.executable, cmd)
+
+
+def main():
+    args = parse_args()
+    n = args.gpus
+    if n > 1 and "RANK" not in os.environ:
+        reexec_with_torchrun(args)
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if not torch.cuda.is_available():
+        if rank == 0:
+            emit({"impl": args.impl, "unavailable": "no CUDA device visible"} if args.impl == "reference" else
+                 {"metric": "attention fwd tokens/sec", "value": None, "error": "no CUDA device visible"})
+        return 0
+    if world != n:
+        n = world
+    dtype = {"bf16": torch.bfloat16, "fp16": torch.float16}[args.dtype]
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+
+    import tree_attention_b200 as ta
+    from tree_attention_b200.ops import reference as ref
+
+    ta.setup(rank, world, local_rank=local_rank)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    B, Hq, D, S = args.batch, args.heads, args.head_dim, args.seq
+    Hkv = args.kv_heads or Hq
+    assert S % world == 0
+    s_local = S // world
+    scale = D ** -0.5
+    kv_bytes_rank = 2 * B * Hkv * s_local * D * 2
+    nbuf = max(1, -(-4 * L2_BYTES // kv_bytes_rank))  # working set > 4 x L2
+    nbuf = min(nbuf, 8)
+    gq = torch.Generator(device=dev).manual_seed(1234)
+    q = torch.randn(B, Hq, 1, D, device=dev, generator=gq).to(dtype)  # same seed on every rank: replicated Q
+    kvs = []
+    for i in range(nbuf):
+        _, k, v = ta.make_data((B, Hq, s_local, D), rank, dev, dtype=dtype, num_kv_heads=Hkv, seed=100 + i, log=False)
+        kvs.append((k, v))
+    config = {
+        "model": "tree-attention decode forward (Sq=1), KV sharded over GPUs", "global_batch": B, "seq_len": S,
+        "heads": Hq, "kv_heads": Hkv, "head_dim": D, "kv_tokens_per_rank": s_local,
+        "parallelism": f"sp{world}" if world > 1 else "single",
+        "l2": f"inputs larger than L2: {nbuf} KV buffer(s) x {kv_bytes_rank / 2**20:.0f} MiB/rank rotated per step "
+              f"(> 4 x 126 MiB L2), no flush",
+    }
+    metric = "attention fwd tokens/sec (decode step Sq=1: KV tokens attended per second, whole box, device-timed, max over ranks) at seq=128K"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        ref_path = os.path.join(ROOT, "baseline", "_ref", "model.py")
+        if not os.path.exists(ref_path):
+            if rank == 0:
+                emit({"impl": "reference", "unavailable": "baseline/_ref/model.py missing (run baseline/install_ref.sh)"})
+            ta.cleanup()
+            return 0
+        spec = importlib.util.spec_from_file_location("ref_model", ref_path)
+        rm = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(rm)
+        try:
+            rm.logger.remove()  # keep its per-call log lines off the terminal; the calls themselves still run
+        except Exception:
+            pass
+        # The reference's own public API: tree_decode(q, k, v, rank, world_size, device) on the layout its
+        # flash_res_lse documents (B, nh, 1, C) / (B, nh, T, C) (model.py:65-67).  Stock code path, default
+        # softmax_scale=1.0 (model.py:60,100).
+        def ref_step(i):
+            k, v = kvs[i % nbuf]
+            return rm.tree_decode(q, k, v, rank, world, dev)
+        try:
+            for i in range(warmup):
+                ref_step(i)
+            torch.cuda.synchronize()
+        except Exception as e:  # world_size > 1: RuntimeError at model.py:111, always
+            msg = f"unmodified reference tree_decode raises at world_size={world}: {type(e).__name__}: {str(e)[:160]}"
+            if rank == 0:
+                emit({"impl": "reference", "unavailable": msg, "n_gpus": world})
+            ta.cleanup()
+            return 0
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        barrier()
+        t0w = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            ref_step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t1w = time.time()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # e2e: pinned q -> device, step, result -> pinned host, every step
+        qh = q.cpu().pin_memory()
+        oh = torch.empty((B, Hq, 1, D), dtype=dtype).pin_memory()
+        qd = torch.empty_like(q)
+        barrier()
+        te0 = time.perf_counter()
+        for i in range(steps):
+            qd.copy_(qh, non_blocking=True)
+            k, v = kvs[i % nbuf]
+            o = rm.tree_decode(qd, k, v, rank, world, dev)
+            oh.copy_(o, non_blocking=True)
+            torch.cuda.synchronize()
+        te1 = time.perf_counter()
+        e2e_ms = (te1 - te0) * 1e3
+        clocks = None
+        if sampler is not None:
+            sampler.stop()
+            clocks = sampler.summary(t0w, t1w)
+        if rank == 0:
+            lat = ms / steps
+            emit({"impl": "reference", "metric": metric, "value": B * S / (lat * 1e-3), "unit": "tokens/s",
+                  "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": lat, "higher_is_better": True,
+                  "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                  "config": config, "clocks": clocks, "decode_tokens_per_s": B / (lat * 1e-3),
+                  "e2e": {"value": B * S / (e2e_ms / steps * 1e-3), "unit": "tokens/s",
+                          "h2d_bytes_per_step": qh.numel() * qh.element_size(),
+                          "d2h_bytes_per_step": oh.numel() * oh.element_size()},
+                  "gpu_launches": 0,
+                  "note": "unmodified /root/reference model.py tree_decode (local branch; stock torch ops; softmax_scale=1.0)"})
+        ta.cleanup()
+        return 0
+
+    # --------------------------------------------------------------------------------------------
+    # own arm
+    from tree_attention_b200 import _build
+
+    C = _build.load()
+    from tree_attention_b200.models.decoder import TreeDecodeSession
+
+    sess = TreeDecodeSession(kvs, softmax_scale=scale, backend=args.backend, use_graph=args.graph)
+    launches_per_step = sess.launches_per_step
+
+    # correctness gate before timing (never time a wrong kernel)
+    out = sess.step_device(q, 0)
+    o_p, l_p = ref.attention_partial_ref(q, kvs[0][0], kvs[0][1], scale, False, 0, 0, torch.float32, block=16384)
+    if world > 1:
+        packed = torch.cat([o_p, l_p[..., None]], -1).contiguous()
+        bufs = [torch.empty_like(packed) for _ in range(world)]
+        dist.all_gather(bufs, packed)
+        o_ref, _ = ref.merge_many([b[..., :-1] for b in bufs], [b[..., -1] for b in bufs])
+    else:
+        o_ref = o_p
+    err = float((out.float() - o_ref).abs().max())
+    if not err < 2e-2:
+        if rank == 0:
+            emit({"metric": metric, "value": None, "error": f"output mismatch vs oracle: {err}"})
+        ta.cleanup()
+        return 1
+
+    for i in range(warmup):
+        sess.step_device(q, i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t0w = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        sess.step_device(q, i)
+    e1.record()
+    torch.cuda.synchronize()
+    t1w = time.time()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    clock_source = "nvidia-smi during the timed region"
+    clocks = None
+    if sampler is not None:
+        clocks = sampler.summary(t0w, t1w)
+    need_probe = torch.tensor([1 if (clocks is not None and clocks["samples"] < 3) else 0], device=dev)
+    if world > 1:
+        dist.broadcast(need_probe, 0)
+    if int(need_probe.item()):
+        # timed region too short for a 50 ms sampler: repeat the identical loop for ~1.5 s and sample that
+        reps = max(steps, int(1.5e3 / max(ms / steps, 1e-3)))
+        barrier()
+        p0 = time.time()
+        for i in range(reps):
+            sess.step_device(q, i)
+        torch.cuda.synchronize()
+        p1 = time.time()
+        if sampler is not None:
+            clocks = sampler.summary(p0, p1)
+            clock_source = f"nvidia-smi during an identical {reps}-step loop run right after the timed region (too short to sample)"
+    if sampler is not None:
+        sampler.stop()
+        clocks["source"] = clock_source
+
+    # end-to-end through the public API: pinned host q -> device, step, result -> pinned host, every step
+    e2e = sess.run_e2e(q, steps, barrier)
+    e2e_ms = torch.tensor([e2e["ms"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_lat = float(e2e_ms.item()) / steps
+
+    extras = {}
+    if not args.no_extras:
+        extras = run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier)
+
+    if rank == 0:
+        lat = ms / steps
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        gbs = kv_bytes_rank / (lat * 1e-3) / 1e9
+        emit({
+            "metric": metric, "value": B * S / (lat * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": lat, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": B * S / (e2e_lat * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_lat,
+                    "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]},
+            "gpu_launches": launches_per_step * steps,
+            "decode_tokens_per_s": B / (lat * 1e-3),
+            "hbm_gbs_per_gpu": gbs, "hbm_frac_of_measured": gbs / hbm,
+            "max_abs_err_vs_oracle": err, "backend": args.backend, "cuda_graph": bool(sess.graphs),
+            **extras,
+        })
+    ta.cleanup()
+    return 0
+
+
+def run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier):
+    """Numbers that explain the headline: un-graphed launch path, NCCL-structured comparator."""
+    import torch
+    import torch.distributed as dist
+
+    out = {}
+    nb = len(kvs)
+
+    def timeit(fn, steps=50, warmup=5):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    try:
+        out["eager_launch_ms_per_step"] = timeit(
+            lambda i: ta.tree_attention(q, kvs[i % nb][0], kvs[i % nb][1], softmax_scale=scale, backend=args.backend))
+        if world > 1:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import nccl_minfix
+
+            out["nccl_minfix_ms_per_step"] = timeit(
+                lambda i: nccl_minfix.tree_decode_minfix(q, kvs[i % nb][0], kvs[i % nb][1], scale))
+            out["own_kernel_plus_nccl_allreduce3_ms_per_step"] = timeit(
+                lambda i: ta.tree_attention(q, kvs[i % nb][0], kvs[i % nb][1], softmax_scale=scale, backend="nccl",
+                                            schedule="allreduce3"))
+    except Exception as e:  # extras must never take the headline down
+        out["extras_error"] = f"{type(e).__name__}: {e}"[:200]
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

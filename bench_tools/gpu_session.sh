@@ -1,0 +1,56 @@
+#!/usr/bin/env bash
+# One gpurun call = one pass over: smoke, GPU tests, both bench arms, verbatim reference, ncu captures.
+# Every step has its own timeout and the script keeps going; everything lands in gpurun_out/.
+# usage: bench_tools/gpu_session.sh [tag] [steps...]   steps in: smoke tests bench ref ncu_list ncu_full
+set -u
+cd "$(dirname "$0")/.."
+TAG=${1:-s1}; shift || true
+STEPS=${*:-"probe smoke tests bench ref ncu_list ncu_full"}
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+export TREE_ATTN_NO_REBUILD=1 PYTHONUNBUFFERED=1
+nvidia-smi -L > "$OUT/gpus.txt" 2>&1
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,clocks.mem,power.draw,clocks_event_reasons.active --format=csv >> "$OUT/gpus.txt" 2>&1
+NG=$(nvidia-smi -L | wc -l)
+for st in $STEPS; do
+  echo "=== $st ($(date +%T))"
+  case $st in
+    probe)
+      timeout 900 python bench_tools/probe_all.py > "$OUT/probe.log" 2>&1; echo "rc=$?" >> "$OUT/probe.log"; cat "$OUT/probe.log" | tail -n 40;;
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; echo "rc=$?" >> "$OUT/smoke.log"; tail -n 3 "$OUT/smoke.log";;
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:cacheprovider > "$OUT/pytest_gpu.log" 2>&1; echo "rc=$?" >> "$OUT/pytest_gpu.log"; tail -n 15 "$OUT/pytest_gpu.log";;
+    bench)
+      timeout 600 python bench.py --gpus 1 > "$OUT/bench_own_1.json" 2> "$OUT/bench_own_1.err"; echo "rc=$?"; tail -n 2 "$OUT/bench_own_1.json"; tail -n 3 "$OUT/bench_own_1.err"
+      timeout 600 python bench.py --gpus 1 --impl reference > "$OUT/bench_ref_1.json" 2> "$OUT/bench_ref_1.err"; echo "rc=$?"; tail -n 2 "$OUT/bench_ref_1.json"; tail -n 3 "$OUT/bench_ref_1.err";;
+    benchN)
+      for n in 2 4 8; do
+        [ "$n" -le "$NG" ] || continue
+        timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n > "$OUT/bench_own_$n.json" 2> "$OUT/bench_own_$n.err"; echo "own n=$n rc=$?"; tail -n 1 "$OUT/bench_own_$n.json"; tail -n 3 "$OUT/bench_own_$n.err"
+        timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29700+n)) bench.py --gpus $n --impl reference --steps 20 > "$OUT/bench_ref_$n.json" 2> "$OUT/bench_ref_$n.err"; echo "ref n=$n rc=$?"; tail -n 1 "$OUT/bench_ref_$n.json"
+      done;;
+    ref)
+      mkdir -p "$OUT/ref_verbatim"
+      ( cd "$OUT/ref_verbatim" && CUDA_VISIBLE_DEVICES=0 timeout 180 python3 /root/reference/model.py > run_1gpu.log 2>&1; echo "rc=$?" >> run_1gpu.log
+        if [ "$NG" -ge 2 ]; then CUDA_VISIBLE_DEVICES=0,1 timeout 180 python3 /root/reference/model.py > run_2gpu.log 2>&1; echo "rc=$?" >> run_2gpu.log; fi )
+      tail -n 3 "$OUT"/ref_verbatim/*.log;;
+    ncu_list)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file "$OUT/launches.csv" \
+        python bench.py --gpus 1 --steps 5 --warmup 3 --no-extras --no-graph > "$OUT/ncu_list.log" 2>&1; echo "rc=$?"; tail -n 5 "$OUT/launches.csv";;
+    ncu_full)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:decode_simt -s 4 -c 1 -f -o "$OUT/prof_decode" \
+        python bench.py --gpus 1 --steps 3 --warmup 3 --no-extras --no-graph > "$OUT/ncu_full.log" 2>&1; echo "rc=$?"; ls -la "$OUT" | grep ncu-rep;;
+    ncu_fwd)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_fwd -s 2 -c 1 -f -o "$OUT/prof_fwd" \
+        python bench_tools/bench_fwd.py --seq 16384 --steps 2 --warmup 1 > "$OUT/ncu_fwd.log" 2>&1; echo "rc=$?"; ls -la "$OUT" | grep ncu-rep;;
+    fwd)
+      timeout 900 python bench_tools/bench_fwd.py > "$OUT/bench_fwd.log" 2>&1; echo "rc=$?"; tail -n 30 "$OUT/bench_fwd.log";;
+    sweep)
+      timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29811 bench_tools/sweep.py --out "$OUT/sweep_$NG.jsonl" > "$OUT/sweep_$NG.log" 2>&1; echo "rc=$?"; tail -n 20 "$OUT/sweep_$NG.log";;
+    tests_multi)
+      timeout 1500 python -m pytest tests/test_gpu_multi.py -q --timeout 600 -p no:cacheprovider > "$OUT/pytest_multi.log" 2>&1; echo "rc=$?" >> "$OUT/pytest_multi.log"; tail -n 15 "$OUT/pytest_multi.log";;
+    *) echo "unknown step $st";;
+  esac
+done
+echo "=== done ($(date +%T))"

@@ -1,0 +1,110 @@
+"""Streaming decode kernel (csrc/decode_simt.cu) vs the fp32 PyTorch oracle of the same op."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import tree_attention_b200 as ta
+from tree_attention_b200.ops import local as L
+from tree_attention_b200.ops import reference as ref
+
+
+def _mk(b, hq, hkv, sq, s, d, dtype, seed=0, bshd=False):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    if bshd:
+        q = torch.randn(b, sq, hq, d, device="cuda", generator=g).to(dtype).transpose(1, 2)
+        k = torch.randn(b, s, hkv, d, device="cuda", generator=g).to(dtype).transpose(1, 2)
+        v = torch.randn(b, s, hkv, d, device="cuda", generator=g).to(dtype).transpose(1, 2)
+    else:
+        q = torch.randn(b, hq, sq, d, device="cuda", generator=g).to(dtype)
+        k = torch.randn(b, hkv, s, d, device="cuda", generator=g).to(dtype)
+        v = torch.randn(b, hkv, s, d, device="cuda", generator=g).to(dtype)
+    return q, k, v
+
+
+CASES = [
+    # b, hq, hkv, sq, s, d, dtype, causal, bshd
+    (1, 1, 1, 1, 1024, 128, torch.bfloat16, False, False),   # BASELINE config #1 shape class (single head)
+    (1, 16, 16, 1, 300, 128, torch.float16, False, False),    # ragged tail, reference dtype
+    (2, 8, 8, 1, 4096, 128, torch.bfloat16, False, False),
+    (1, 32, 32, 1, 16384, 128, torch.bfloat16, False, False),  # north-star per-rank shard at W=8
+    (1, 32, 8, 1, 8192, 128, torch.bfloat16, False, False),   # GQA 32q/8kv -> 4 rows
+    (2, 8, 2, 2, 2000, 128, torch.bfloat16, True, False),     # 8 rows -> two passes, causal
+    (1, 12, 4, 3, 777, 64, torch.float16, True, False),       # head_dim 64, 9 rows -> 3 passes
+    (1, 4, 4, 1, 5000, 64, torch.bfloat16, False, False),
+    (2, 8, 4, 1, 3000, 128, torch.bfloat16, False, True),     # BSHD-strided inputs
+    (1, 2, 2, 1, 100000, 128, torch.bfloat16, False, False),  # few heads, many splits per head
+    (3, 5, 5, 1, 129, 128, torch.bfloat16, True, False),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_decode_matches_oracle(case):
+    b, hq, hkv, sq, s, d, dtype, causal, bshd = case
+    q, k, v = _mk(b, hq, hkv, sq, s, d, dtype, bshd=bshd)
+    scale = d ** -0.5
+    q_pos0 = s - sq
+    out, lse = L.decode_attention(q, k, v, scale, causal, q_pos0, 0)
+    o_ref, l_ref = ref.attention_partial_ref(q, k, v, scale, causal, q_pos0, 0, torch.float32, block=16384)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 4e-3
+    assert (out.float() - o_ref).abs().max().item() < tol
+    assert (lse - l_ref).abs().max().item() < 2e-3
+
+
+def test_causal_offsets_and_fully_masked_shard():
+    q, k, v = _mk(1, 4, 4, 1, 1000, 128, torch.bfloat16, seed=3)
+    # shard starts AFTER the query position: every key masked -> identity (0, -inf), no NaN
+    out, lse = L.decode_attention(q, k, v, 0.1, True, q_pos0=10, kv_pos0=500)
+    assert torch.all(out == 0) and torch.all(torch.isinf(lse) & (lse < 0))
+    # partially visible shard
+    out, lse = L.decode_attention(q, k, v, 0.1, True, q_pos0=700, kv_pos0=500)
+    o_ref, l_ref = ref.attention_partial_ref(q, k, v, 0.1, True, 700, 500)
+    assert (out.float() - o_ref).abs().max().item() < 1.5e-2 and (lse - l_ref).abs().max().item() < 2e-3
+
+
+def test_public_api_dispatches_to_kernel_and_matches():
+    q, k, v = ta.make_data((1, 16, 64000, 128), 0, "cuda", dtype=torch.float16, log=False)  # model.py:140-145
+    out = ta.tree_decode(q, k, v, 0, 1, torch.device("cuda"))       # reference shim: scale 1.0
+    o_ref, _ = ref.attention_partial_ref(q, k, v, 1.0, block=16384)
+    assert (out.float() - o_ref).abs().max().item() < 1e-2
+    res, lse = ta.flash_res_lse(q, k, v)
+    assert res.shape == (1, 16, 1, 128) and lse.shape == (1, 16, 1) and lse.dtype == torch.float32
+
+
+def test_repeated_calls_are_deterministic_and_reset_tickets():
+    q, k, v = _mk(2, 8, 8, 1, 6000, 128, torch.bfloat16, seed=5)
+    first, _ = L.decode_attention(q, k, v, 0.088, False)
+    first = first.clone()
+    for _ in range(200):
+        out, _ = L.decode_attention(q, k, v, 0.088, False)
+    torch.cuda.synchronize()
+    assert torch.equal(out, first)
+
+
+def test_cuda_graph_replay():
+    q, k, v = _mk(1, 8, 8, 1, 4096, 128, torch.bfloat16, seed=7)
+    out = torch.empty_like(q)
+    lse = torch.empty(1, 8, 1, device="cuda", dtype=torch.float32)
+    L.decode_attention(q, k, v, 0.088, out=out, lse=lse)  # warm-up (workspace allocation)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g):
+            L.decode_attention(q, k, v, 0.088, out=out, lse=lse)
+    ref_out = out.clone()
+    for i in range(3):
+        q.copy_(torch.randn_like(q))
+        g.replay()
+        torch.cuda.synchronize()
+        exp, _ = ref.attention_partial_ref(q, k, v, 0.088)
+        assert (out.float() - exp).abs().max().item() < 1.5e-2
+    assert not torch.equal(out, ref_out)
+
+
+def test_missing_kernel_is_loud():
+    q, k, v = _mk(1, 2, 2, 1, 256, 32, torch.bfloat16)  # head_dim 32: no sm_100a kernel
+    with pytest.raises(RuntimeError):
+        ta.tree_attention(q, k, v)

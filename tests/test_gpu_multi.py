@@ -1,0 +1,141 @@
+"""Multi-GPU: fused in-kernel tree combine over symmetric memory vs the NCCL path vs the oracle.
+Needs >= 2 GPUs (skipped otherwise)."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from _dist_utils import run_distributed
+
+NGPU = torch.cuda.device_count() if torch.cuda.is_available() else 0
+need2 = pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
+WORLDS = [w for w in (2, 4, 8) if w <= NGPU]
+
+
+def _oracle(q, k, v, world, scale, causal):
+    import torch.distributed as dist
+    from tree_attention_b200.ops import reference as ref
+
+    ks = [torch.empty_like(k) for _ in range(world)]
+    vs = [torch.empty_like(v) for _ in range(world)]
+    dist.all_gather(ks, k.contiguous())
+    dist.all_gather(vs, v.contiguous())
+    return ref.attention_partial_ref(q, torch.cat(ks, 2), torch.cat(vs, 2), scale, causal,
+                                     world * k.shape[2] - q.shape[2], 0, torch.float32, block=16384)
+
+
+def _worker_fused(rank, world):
+    import torch.distributed as dist
+    import tree_attention_b200 as ta
+
+    dev = torch.device("cuda", rank)
+    for (b, hq, hkv, sq, s, d, dtype, causal) in [
+        (1, 32, 32, 1, 4096, 128, torch.bfloat16, False),
+        (2, 8, 2, 1, 1500, 128, torch.bfloat16, True),
+        (1, 16, 16, 1, 64000 // 8, 128, torch.float16, False),
+        (1, 8, 4, 3, 999, 64, torch.bfloat16, True),
+    ]:
+        q, k, v = ta.make_data((b, hq, s, d), rank, dev, dtype=dtype, sq=sq, num_kv_heads=hkv, log=False)
+        scale = d ** -0.5
+        o_ref, l_ref = _oracle(q, k, v, world, scale, causal)
+        results = {}
+        for backend, sched in [("fused", "oneshot"), ("symm", "oneshot"), ("symm", "butterfly"),
+                               ("nccl", "allreduce3"), ("nccl", "allgather"), ("nccl", "butterfly")]:
+            out, lse = ta.tree_attention(q, k, v, causal=causal, return_lse=True, backend=backend, schedule=sched)
+            torch.cuda.synchronize()
+            err = (out.float() - o_ref).abs().max().item()
+            assert err < 2e-2, (backend, sched, err)
+            assert (lse - l_ref).abs().max().item() < 3e-3, (backend, sched)
+            results[(backend, sched)] = out
+            if backend in ("fused", "symm"):
+                outs = [torch.empty_like(out) for _ in range(world)]
+                dist.all_gather(outs, out.contiguous())
+                for o in outs:
+                    assert torch.equal(o, outs[0]), f"{backend}/{sched}: ranks disagree bitwise"
+
+
+@need2
+@pytest.mark.parametrize("world", WORLDS)
+def test_fused_tree_attention(world, port):
+    run_distributed(_worker_fused, world, port)
+
+
+def _worker_stress(rank, world):
+    """>= 1000 back-to-back fused steps: epoch/parity reuse must never serve stale partials."""
+    import tree_attention_b200 as ta
+    from tree_attention_b200.parallel import symm
+
+    dev = torch.device("cuda", rank)
+    q, k, v = ta.make_data((1, 8, 2048, 128), rank, dev, dtype=torch.bfloat16, log=False)
+    o_ref, _ = _oracle(q, k, v, world, 0.088, False)
+    qs = [torch.randn_like(q) for _ in range(4)]
+    refs = [_oracle(qq, k, v, world, 0.088, False)[0] for qq in qs]
+    for it in range(1200):
+        out = ta.tree_attention(qs[it % 4], k, v, softmax_scale=0.088, backend="fused")
+        if it % 97 == 0 or it > 1190:
+            assert (out.float() - refs[it % 4]).abs().max().item() < 2e-2, it
+    torch.cuda.synchronize()
+    reg = symm.regions()[("decode", 0)]
+    reg.check()
+    assert reg.epoch() >= 1200
+
+
+@need2
+def test_epoch_reuse_stress(port):
+    run_distributed(_worker_stress, 2, port)
+
+
+def _worker_graph(rank, world):
+    import tree_attention_b200 as ta
+
+    dev = torch.device("cuda", rank)
+    q, k, v = ta.make_data((1, 8, 4096, 128), rank, dev, dtype=torch.bfloat16, log=False)
+    ta.tree_attention(q, k, v, backend="fused")  # allocate workspaces + symmetric region
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g):
+            out = ta.tree_attention(q, k, v, backend="fused")
+    for i in range(5):
+        q.copy_(torch.randn_like(q))
+        import torch.distributed as dist
+        dist.broadcast(q, 0)
+        g.replay()
+        torch.cuda.synchronize()
+        o_ref, _ = _oracle(q, k, v, world, 128 ** -0.5, False)
+        assert (out.float() - o_ref).abs().max().item() < 2e-2, i
+
+
+@need2
+def test_fused_cuda_graph_replay(port):
+    run_distributed(_worker_graph, 2, port)
+
+
+def _worker_fault(rank, world):
+    """Fault injection: rank 1 never publishes -> rank 0's bounded spin reports it instead of hanging."""
+    import tree_attention_b200 as ta
+    from tree_attention_b200.parallel import symm
+
+    dev = torch.device("cuda", rank)
+    q, k, v = ta.make_data((1, 4, 1024, 128), rank, dev, dtype=torch.bfloat16, log=False)
+    ta.tree_attention(q, k, v, backend="fused")
+    torch.cuda.synchronize()
+    reg = symm.regions()[("decode", 0)]
+    reg.comm.timeout_s = 0.2
+    if rank == 1:
+        reg.comm.skip_publish = 1
+    out = ta.tree_attention(q, k, v, backend="fused")
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="never arrived"):
+        reg.check()
+    assert torch.isnan(out.float()).any()  # a failed combine can never be consumed silently
+    code, item, src, ep = reg.status()
+    assert src == 1
+
+
+@need2
+def test_failure_detection_bounded_spin(port):
+    run_distributed(_worker_fault, 2, port)

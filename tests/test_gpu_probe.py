@@ -1,0 +1,25 @@
+"""tcgen05 layout conventions, pinned down on hardware with a one-CTA GEMM (csrc/umma_probe.cu)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tree_attention_b200 import _build
+
+
+@pytest.mark.parametrize("a_from_tmem", [False, True])
+@pytest.mark.parametrize("b_mn_major", [False, True])
+@pytest.mark.parametrize("n,k", [(128, 64), (128, 128), (64, 128), (256, 128), (128, 256), (16, 128), (32, 64)])
+def test_umma_probe(n, k, b_mn_major, a_from_tmem):
+    if b_mn_major and n % 64:
+        pytest.skip("MN-major B needs N % 64 == 0")
+    C = _build.load()
+    g = torch.Generator(device="cuda").manual_seed(n * 1000 + k)
+    a = torch.randn(128, k, device="cuda", generator=g).bfloat16()
+    b = torch.randn((k, n) if b_mn_major else (n, k), device="cuda", generator=g).bfloat16()
+    c = torch.zeros(128, n, device="cuda", dtype=torch.float32)
+    C.umma_probe(a, b, c, b_mn_major, a_from_tmem)
+    torch.cuda.synchronize()
+    exp = a.float() @ (b.float() if b_mn_major else b.float().t())
+    err = (c - exp).abs().max().item()
+    assert err < 1e-2 * max(1.0, exp.abs().max().item() / 16), f"max err {err}"

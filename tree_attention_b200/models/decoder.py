@@ -1,0 +1,119 @@
+"""Decode-time serving objects built on ``tree_attention``.
+
+``TreeDecodeSession`` is the user-facing wrapper for the reference's one use case -- a decode step over a
+sequence-sharded KV cache (``/root/reference/model.py:129-155`` runs exactly one such step) -- extended to
+what a server needs: several KV caches ("layers") resident in HBM, a step captured once per layer in a
+CUDA graph (the step is a single fused kernel; at 8 GPUs it is shorter than a Python launch), pinned-host
+I/O for the query / result, and a KV-append for the owning rank.
+"""
+from __future__ import annotations
+
+import time
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ..ops import local as local_ops
+from ..parallel.tree import tree_attention
+
+
+class TreeDecodeSession:
+    def __init__(
+        self,
+        kv_layers: Sequence[Tuple[torch.Tensor, torch.Tensor]],
+        softmax_scale: Optional[float] = None,
+        causal: bool = False,
+        backend: str = "fused",
+        schedule: str = "oneshot",
+        use_graph: bool = True,
+        group=None,
+        q_shape: Optional[Tuple[int, int, int, int]] = None,
+    ):
+        self.kv = list(kv_layers)
+        k0 = self.kv[0][0]
+        self.device = k0.device
+        self.dtype = k0.dtype
+        self.scale = softmax_scale
+        self.causal = causal
+        self.backend = backend
+        self.schedule = schedule
+        self.group = group
+        b, hkv, s, d = k0.shape
+        self.q_shape = tuple(q_shape) if q_shape is not None else (b, hkv, 1, d)
+        self.q_static = torch.zeros(self.q_shape, dtype=self.dtype, device=self.device)
+        self.out_static: List[Optional[torch.Tensor]] = [None] * len(self.kv)
+        self.graphs: List[torch.cuda.CUDAGraph] = []
+        g = self.q_shape[1] // hkv
+        rows = g * self.q_shape[2]
+        self.launches_per_step = max(1, -(-rows // 4)) if local_ops.decode_eligible(self.q_static, k0) else 1
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        graphable = self.device.type == "cuda" and (world == 1 or backend in ("fused", "symm", "auto"))
+        self._use_graph = bool(use_graph and graphable)
+        self._prepared = False
+
+    # -- internals ---------------------------------------------------------------------------------
+    def _eager(self, q: torch.Tensor, layer: int) -> torch.Tensor:
+        k, v = self.kv[layer]
+        return tree_attention(q, k, v, group=self.group, causal=self.causal, softmax_scale=self.scale,
+                              backend=self.backend, schedule=self.schedule)
+
+    def _prepare(self) -> None:
+        if self._prepared:
+            return
+        for i in range(len(self.kv)):  # allocates workspaces and (collectively) the symmetric region
+            self.out_static[i] = self._eager(self.q_static, i)
+        torch.cuda.synchronize()
+        if self._use_graph:
+            side = torch.cuda.Stream()
+            for i in range(len(self.kv)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g):
+                        self.out_static[i] = self._eager(self.q_static, i)
+                self.graphs.append(g)
+            torch.cuda.synchronize()
+        self._prepared = True
+
+    # -- API ---------------------------------------------------------------------------------------
+    def step_device(self, q: Optional[torch.Tensor], layer: int) -> torch.Tensor:
+        """One decode-attention step for ``layer`` with the query already on the device.
+        ``q=None`` reuses whatever is in ``q_static``."""
+        layer %= len(self.kv)
+        self._prepare()
+        if q is not None and q.data_ptr() != self.q_static.data_ptr():
+            self.q_static.copy_(q, non_blocking=True)
+        if self.graphs:
+            self.graphs[layer].replay()
+            return self.out_static[layer]
+        self.out_static[layer] = self._eager(self.q_static, layer)
+        return self.out_static[layer]
+
+    def step(self, q_host: torch.Tensor, out_host: torch.Tensor, layer: int) -> torch.Tensor:
+        """End-to-end step: pinned host query -> device, attention, result -> pinned host, synchronised."""
+        self.q_static.copy_(q_host, non_blocking=True)
+        out = self.step_device(None, layer)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out_host
+
+    def append_kv(self, layer: int, k_new: torch.Tensor, v_new: torch.Tensor, position: int) -> None:
+        """Write one new token's K/V at local row ``position`` of this rank's shard (the owner of the
+        global position calls this; shards are preallocated)."""
+        k, v = self.kv[layer]
+        k[:, :, position : position + k_new.shape[2]].copy_(k_new, non_blocking=True)
+        v[:, :, position : position + v_new.shape[2]].copy_(v_new, non_blocking=True)
+
+    def run_e2e(self, q: torch.Tensor, steps: int, barrier) -> dict:
+        self._prepare()
+        qh = q.detach().cpu().pin_memory()
+        oh = torch.empty(self.q_shape, dtype=self.dtype).pin_memory()
+        for i in range(3):
+            self.step(qh, oh, i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            self.step(qh, oh, i)
+        t1 = time.perf_counter()
+        barrier()
+        return {"ms": (t1 - t0) * 1e3, "h2d": qh.numel() * qh.element_size(), "d2h": oh.numel() * oh.element_size()}
