@@ -32,8 +32,8 @@ for st in $STEPS; do
       done;;
     ref)
       mkdir -p "$OUT/ref_verbatim"
-      ( cd "$OUT/ref_verbatim" && CUDA_VISIBLE_DEVICES=0 timeout 180 python3 /root/reference/model.py > run_1gpu.log 2>&1; echo "rc=$?" >> run_1gpu.log
-        if [ "$NG" -ge 2 ]; then CUDA_VISIBLE_DEVICES=0,1 timeout 180 python3 /root/reference/model.py > run_2gpu.log 2>&1; echo "rc=$?" >> run_2gpu.log; fi )
+      ( REPO=$PWD; cd "$OUT/ref_verbatim" && CUDA_VISIBLE_DEVICES=0 timeout 180 python3 "$REPO/baseline/_ref/model.py" > run_1gpu.log 2>&1; echo "rc=$?" >> run_1gpu.log
+        if [ "$NG" -ge 2 ]; then CUDA_VISIBLE_DEVICES=0,1 timeout 180 python3 "$REPO/baseline/_ref/model.py" > run_2gpu.log 2>&1; echo "rc=$?" >> run_2gpu.log; fi )
       tail -n 3 "$OUT"/ref_verbatim/*.log;;
     ncu_list)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file "$OUT/launches.csv" \

@@ -70,7 +70,11 @@ def _worker_stress(rank, world):
     dev = torch.device("cuda", rank)
     q, k, v = ta.make_data((1, 8, 2048, 128), rank, dev, dtype=torch.bfloat16, log=False)
     o_ref, _ = _oracle(q, k, v, world, 0.088, False)
+    import torch.distributed as dist
+
     qs = [torch.randn_like(q) for _ in range(4)]
+    for t in qs:  # Q is replicated: every rank must attend with the same query
+        dist.broadcast(t, 0)
     refs = [_oracle(qq, k, v, world, 0.088, False)[0] for qq in qs]
     for it in range(1200):
         out = ta.tree_attention(qs[it % 4], k, v, softmax_scale=0.088, backend="fused")

@@ -1,0 +1,352 @@
+// attn_partial_fwd -- flash-attention forward for sm_100a on the 5th-generation tensor cores.
+//
+// Replaces the reference's local attention (/root/reference/model.py:74-80: matmul -> softmax -> matmul
+// with the full score row materialised in HBM) for Sq >= 1 with GQA, causal masks
+// over GLOBAL positions, and the (o, lse) contract the tree combine needs.
+//
+// One CTA = one 128-row query tile of one (batch, q-head); 6 warps, warp-specialised:
+//   warps 0-3  softmax: tcgen05.ld S (one row per thread) -> online softmax with lazy rescale ->
+//              P (bf16/fp16) written back to TMEM over S -> epilogue O/l, lse, swizzled smem, TMA store
+//   warp  4    TMA producer: Q once, then K and V tiles through two 3-stage mbarrier rings
+//   warp  5    MMA issuer (one elected lane): S = Q K^T (SS form, K-major operands),
+//              O += P V (TS form: A = P from TMEM, B = V MN-major from smem); owns the TMEM allocation
+// TMEM (512 columns): S0 [0,128) | S1 [128,256) | O [256,256+D).  S is double-buffered so that
+// QK^T of tile j+1 and PV of tile j-1 run on the tensor pipe while the softmax of tile j runs on the
+// SIMT pipes; P_j aliases the first 64 columns of S_j.
+// All layout conventions used here are verified on hardware by csrc/umma_probe.cu (tests/test_gpu_probe.py).
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace ta {
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockN = 128;
+constexpr int kSoftmaxThreads = 128;
+constexpr int kFwdThreads = 192;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units: P stays <= 2^8 before the max is refreshed
+
+struct FwdParams {
+  float* lse;        // (B, Hq, Sq) natural log
+  void* out;         // used only by the "no visible keys" path (plain stores)
+  long long o_sb, o_sh, o_ss;
+  int B, Hq, Hkv, G, Sq, S;
+  float scale_log2;
+  int causal;
+  long long q_pos0, kv_pos0;
+  int num_m_tiles;
+};
+
+template <int D>
+struct FwdSmem {
+  static constexpr int kStages = 3;
+  static constexpr int kAtoms = D / 64;
+  static constexpr int kQBytes = kBlockM * D * 2;
+  static constexpr int kKVBytes = kBlockN * D * 2;
+  static constexpr int kAtomBytes = 128 * 128;  // 128 rows x 128 B
+  static constexpr size_t kTotal = 1024 + size_t(kQBytes) + size_t(2 * kStages) * kKVBytes + 256;
+};
+
+__device__ __forceinline__ float neg_inf_f() { return __int_as_float(0xff800000); }
+
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if constexpr (BF16) return pack_bf16x2(lo, hi);
+  else return pack_f16x2(lo, hi);
+}
+
+template <int D, bool BF16>
+__global__ void __launch_bounds__(kFwdThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap omap,
+                const FwdParams p) {
+  using SM = FwdSmem<D>;
+  constexpr int NS = SM::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + SM::kQBytes;
+  uint8_t* v_s = k_s + NS * SM::kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + NS * SM::kKVBytes);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // NS
+  uint64_t* k_empty = k_full + NS;    // NS
+  uint64_t* v_full = k_empty + NS;    // NS
+  uint64_t* v_empty = v_full + NS;    // NS
+  uint64_t* s_full = v_empty + NS;    // 2
+  uint64_t* p_full = s_full + 2;      // 2
+  uint64_t* pv_done = p_full + 2;     // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int m_tile = p.num_m_tiles - 1 - (int)blockIdx.x;  // heaviest (causal) tiles first
+  const int hq = blockIdx.y, b = blockIdx.z;
+  const int hkv = hq / p.G;
+  const int m0 = m_tile * kBlockM;
+
+  // number of KV tiles this query tile can see
+  int n_end = p.S;
+  if (p.causal) {
+    const long long last_q = p.q_pos0 + min(m0 + kBlockM - 1, p.Sq - 1);
+    const long long lim = last_q - p.kv_pos0 + 1;
+    n_end = (int)max(0LL, min((long long)p.S, lim));
+  }
+  const int n_tiles = (n_end + kBlockN - 1) / kBlockN;
+
+  if (n_tiles == 0) {
+    // nothing visible: the monoid identity (0, -inf)
+    if (warp < 4) {
+      const int row = m0 + tid;
+      if (row < p.Sq) {
+        uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)b * p.o_sb + (long long)hq * p.o_sh + (long long)row * p.o_ss;
+        for (int d = 0; d < D; d += 8) *reinterpret_cast<uint4*>(op + d) = make_uint4(0, 0, 0, 0);
+        p.lse[((long long)b * p.Hq + hq) * p.Sq + row] = neg_inf_f();
+      }
+    }
+    return;
+  }
+
+  if (tid == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&qmap); tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); tma_prefetch_desc(&omap);
+  }
+  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_o = tmem + 256;
+
+  if (warp == 4) {
+    // =============================== TMA producer ===============================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, SM::kQBytes);
+#pragma unroll
+      for (int a = 0; a < SM::kAtoms; ++a) tma_load_4d(q_s + a * SM::kAtomBytes, &qmap, q_full, a * 64, m0, hq, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % NS;
+        const uint32_t ph = (j / NS) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], SM::kKVBytes);
+#pragma unroll
+        for (int a = 0; a < SM::kAtoms; ++a)
+          tma_load_4d(k_s + st * SM::kKVBytes + a * SM::kAtomBytes, &kmap, &k_full[st], a * 64, j * kBlockN, hkv, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], SM::kKVBytes);
+#pragma unroll
+        for (int a = 0; a < SM::kAtoms; ++a)
+          tma_load_4d(v_s + st * SM::kKVBytes + a * SM::kAtomBytes, &vmap, &v_full[st], a * 64, j * kBlockN, hkv, b);
+      }
+    }
+  } else if (warp == 5) {
+    // =============================== MMA issuer =================================================
+    if (lane == 0) {
+      constexpr uint32_t fmt = BF16 ? 1u : 0u;
+      constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kBlockM, kBlockN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc(fmt, fmt, kBlockM, D, 0, 1);
+      const uint32_t q_addr = smem_u32(q_s);
+      auto issue_qk = [&](int j) {
+        const int st = j % NS;
+        mbar_wait(&k_full[st], (j / NS) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(k_s + st * SM::kKVBytes);
+        const uint32_t d_tmem = tmem + (j & 1) * 128;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * SM::kAtomBytes + (kk % 4) * 32;
+          umma_ss_f16(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
+                      idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        const int st = j % NS;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        mbar_wait(&v_full[st], (j / NS) & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(v_s + st * SM::kKVBytes);
+        const uint32_t p_tmem = tmem + (j & 1) * 128;
+#pragma unroll
+        for (int kk = 0; kk < kBlockN / 16; ++kk) {
+          umma_ts_f16(tmem_o, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * 2048, kBlockN * 128, 1024), idesc_pv,
+                      (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(&pv_done[j & 1]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== softmax warps ==============================================
+    const int row = tid;                                   // row of the tile == TMEM lane
+    const uint32_t lane_addr = uint32_t(warp * 32) << 16;  // this warp's lane quarter
+    const long long q_pos = p.q_pos0 + m0 + row;
+    float m_used = neg_inf_f();  // running (stale) max, scaled log2 domain
+    float l_sum = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int n0 = j * kBlockN;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_tmem = tmem + (j & 1) * 128 + lane_addr;
+      uint32_t sr[128];
+      tmem_ld_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+      tmem_ld_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+      tmem_ld_32x32b_x32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
+      tmem_ld_32x32b_x32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
+      tmem_ld_wait();
+      // mask (diagonal tiles and the ragged last tile only)
+      const bool need_mask = (n0 + kBlockN > p.S) || (p.causal && (p.kv_pos0 + n0 + kBlockN - 1 > p.q_pos0 + m0));
+      if (need_mask) {
+        long long lim = (long long)p.S - n0 - 1;
+        if (p.causal) lim = min(lim, q_pos - p.kv_pos0 - n0);
+        const int limc = (int)max(-1LL, min(lim, 127LL));
+#pragma unroll
+        for (int c = 0; c < 128; ++c)
+          if (c > limc) sr[c] = 0xff800000u;
+      }
+      float mx = neg_inf_f();
+#pragma unroll
+      for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
+      const float m_new = fmaxf(m_used, mx * p.scale_log2);
+      // lazy rescale: refresh the reference max only when it moved by more than the threshold
+      const bool refresh = (m_new - m_used > kRescaleThreshold) || (m_used == neg_inf_f() && m_new != neg_inf_f());
+      if (__any_sync(0xffffffffu, refresh) ) {
+        const float alpha = refresh ? fast_exp2(m_used - m_new) : 1.f;  // m_used=-inf -> 0
+        if (refresh) { l_sum *= alpha; m_used = m_new; }
+        if (j > 0) {
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t orow[32];
+            tmem_ld_32x32b_x32(tmem_o + lane_addr + c0, orow);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_o + lane_addr + c0, orow);
+          }
+        }
+      }
+      const float m_sub = (m_used == neg_inf_f()) ? 0.f : m_used;
+      const float neg_m = -m_sub;
+      float ls0 = 0.f, ls1 = 0.f;
+      uint32_t pk[64];
+#pragma unroll
+      for (int c = 0; c < 128; c += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c]), p.scale_log2, neg_m));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, neg_m));
+        ls0 += p0; ls1 += p1;
+        pk[c >> 1] = pack2<BF16>(p0, p1);
+      }
+      l_sum += ls0 + ls1;
+      tmem_st_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+      tmem_st_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+    }
+    // ------------------------------- epilogue --------------------------------------------------
+    const int jl = n_tiles - 1;
+    mbar_wait(&pv_done[jl & 1], (jl >> 1) & 1);
+    tc_fence_after();
+    const float inv_l = l_sum > 0.f ? 1.f / l_sum : 0.f;
+    // all QK^T MMAs are complete -> the Q tile buffer is free: stage O there in the TMA/UMMA 128B swizzle
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t orow[32];
+      tmem_ld_32x32b_x32(tmem_o + lane_addr + c0, orow);
+      tmem_ld_wait();
+      const int atom = c0 >> 6;
+      uint8_t* base = q_s + atom * SM::kAtomBytes + row * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {  // 4 chunks of 8 elements (16 B)
+        uint4 w;
+        w.x = pack2<BF16>(__uint_as_float(orow[g * 8 + 0]) * inv_l, __uint_as_float(orow[g * 8 + 1]) * inv_l);
+        w.y = pack2<BF16>(__uint_as_float(orow[g * 8 + 2]) * inv_l, __uint_as_float(orow[g * 8 + 3]) * inv_l);
+        w.z = pack2<BF16>(__uint_as_float(orow[g * 8 + 4]) * inv_l, __uint_as_float(orow[g * 8 + 5]) * inv_l);
+        w.w = pack2<BF16>(__uint_as_float(orow[g * 8 + 6]) * inv_l, __uint_as_float(orow[g * 8 + 7]) * inv_l);
+        const int chunk = ((c0 & 63) >> 3) + g;
+        *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = w;
+      }
+    }
+    if (m0 + row < p.Sq)
+      p.lse[((long long)b * p.Hq + hq) * p.Sq + m0 + row] =
+          l_sum > 0.f ? (m_used + fast_log2(l_sum)) * 0.6931471805599453f : neg_inf_f();
+    fence_proxy_async_smem();
+    tc_fence_before();
+    named_bar_sync(1, kSoftmaxThreads);
+    if (tid == 0) {
+#pragma unroll
+      for (int a = 0; a < SM::kAtoms; ++a) tma_store_4d(&omap, q_s + a * SM::kAtomBytes, a * 64, m0, hq, b);
+      tma_store_commit();
+      tma_store_wait<0>();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+}
+
+template <int D, bool BF16>
+void launch_fwd(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                cudaStream_t stream) {
+  using SM = FwdSmem<D>;
+  CUtensorMap qmap = make_tmap_bhsd(q, 2, s.B, s.Hq, s.Sq, D, s.q_sb, s.q_sh, s.q_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, D, s.k_sb, s.k_sh, s.k_ss, 64, kBlockN, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap vmap = make_tmap_bhsd(v, 2, s.B, s.Hkv, s.S, D, s.v_sb, s.v_sh, s.v_ss, 64, kBlockN, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap omap = make_tmap_bhsd(out, 2, s.B, s.Hq, s.Sq, D, s.o_sb, s.o_sh, s.o_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+  FwdParams p;
+  p.lse = lse; p.out = out; p.o_sb = s.o_sb; p.o_sh = s.o_sh; p.o_ss = s.o_ss;
+  p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = s.Hq / s.Hkv; p.Sq = s.Sq; p.S = s.S;
+  p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
+  p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;
+  p.num_m_tiles = (s.Sq + kBlockM - 1) / kBlockM;
+  auto kern = attn_fwd_kernel<D, BF16>;
+  static bool configured = false;
+  if (!configured) {
+    TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kTotal));
+    configured = true;
+  }
+  dim3 grid(p.num_m_tiles, s.Hq, s.B);
+  kern<<<grid, kFwdThreads, SM::kTotal, stream>>>(qmap, kmap, vmap, omap, p);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                     cudaStream_t stream) {
+  if (s.D != 64 && s.D != 128) throw std::runtime_error("attn_fwd: head_dim must be 64 or 128");
+  if (s.Hq % s.Hkv != 0) throw std::runtime_error("attn_fwd: Hq must be a multiple of Hkv");
+  if (s.S <= 0 || s.Sq <= 0) throw std::runtime_error("attn_fwd: empty problem");
+  if (s.D == 128) {
+    if (s.is_bf16) launch_fwd<128, true>(s, q, k, v, out, lse, stream);
+    else launch_fwd<128, false>(s, q, k, v, out, lse, stream);
+  } else {
+    if (s.is_bf16) launch_fwd<64, true>(s, q, k, v, out, lse, stream);
+    else launch_fwd<64, false>(s, q, k, v, out, lse, stream);
+  }
+}
+
+}  // namespace ta

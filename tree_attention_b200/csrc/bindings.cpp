@@ -129,6 +129,16 @@ void decode_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, a
                          at::cuda::getCurrentCUDAStream());
 }
 
+void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out, at::Tensor& lse,
+              double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
+  c10::cuda::CUDAGuard guard(q.device());
+  AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == (int64_t)s.B * s.Hq * s.Sq,
+              "lse must be contiguous fp32 (B, Hq, Sq)");
+  ta::attn_fwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(),
+                      at::cuda::getCurrentCUDAStream());
+}
+
 void combine(const at::Tensor& o_part, const at::Tensor& lse_part, at::Tensor& out, c10::optional<at::Tensor> lse_out,
              Comm& comm, int mode) {
   c10::cuda::CUDAGuard guard(o_part.device());
@@ -181,6 +191,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_property_readonly("world", [](Comm& c) { return c.h.world; });
   m.def("decode_plan", &decode_plan);
   m.def("decode_fwd", &decode_fwd);
+  m.def("attn_fwd", &attn_fwd);
   m.def("combine", &combine);
   m.def("umma_probe", &umma_probe);
   m.def("num_sms", []() { return ta::num_sms(); });

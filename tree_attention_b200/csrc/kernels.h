@@ -57,4 +57,8 @@ void combine_launch(const float* o_part, const float* lse_part, void* out, int o
 void umma_probe_launch(const void* a, const void* b, float* c, int N, int K, int b_mn_major, int a_from_tmem,
                        cudaStream_t stream);
 
+// ---- tcgen05 flash-attention forward: shard-local partial (o normalised, lse natural log) ----
+void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                     cudaStream_t stream);
+
 }  // namespace ta
