@@ -62,6 +62,47 @@ def test_fused_tree_attention(world, port):
     run_distributed(_worker_fused, world, port)
 
 
+def _worker_prefill(rank, world):
+    """tcgen05 forward with the fused in-kernel combine (compute + merge CTAs in one launch)."""
+    import torch.distributed as dist
+    import tree_attention_b200 as ta
+
+    dev = torch.device("cuda", rank)
+    for (b, hq, hkv, sq, s, d, dtype, causal) in [
+        (1, 4, 4, 256, 512, 128, torch.bfloat16, False),
+        (2, 8, 2, 300, 777, 128, torch.bfloat16, True),      # ragged, GQA, some (tile, rank) pairs fully masked
+        (1, 4, 4, 1024, 1024, 64, torch.float16, True),
+        (1, 32, 8, 2048, 2048, 128, torch.bfloat16, True),   # many more items than SMs: merge CTAs interleave
+    ]:
+        q, k, v = ta.make_data((b, hq, s, d), rank, dev, dtype=dtype, sq=sq, num_kv_heads=hkv, log=False)
+        scale = d ** -0.5
+        o_ref, l_ref = _oracle(q, k, v, world, scale, causal)
+        for backend in ("fused", "symm", "nccl"):
+            out, lse = ta.tree_attention(q, k, v, causal=causal, return_lse=True, backend=backend,
+                                         schedule="allgather" if backend == "nccl" else "oneshot")
+            torch.cuda.synchronize()
+            err = (out.float() - o_ref).abs().max().item()
+            assert err < 3e-2, (backend, err)
+            dead = torch.isinf(l_ref)
+            assert (lse[~dead] - l_ref[~dead]).abs().max().item() < 5e-3, backend
+            if backend == "fused":
+                outs = [torch.empty_like(out) for _ in range(world)]
+                dist.all_gather(outs, out.contiguous())
+                for o in outs:
+                    assert torch.equal(o, outs[0]), "fused prefill: ranks disagree bitwise"
+    # repeated launches: parity / epoch reuse
+    for it in range(50):
+        out = ta.tree_attention(q, k, v, causal=True, backend="fused")
+    torch.cuda.synchronize()
+    assert (out.float() - o_ref).abs().max().item() < 3e-2
+
+
+@need2
+@pytest.mark.parametrize("world", WORLDS)
+def test_fused_prefill_tcgen05(world, port):
+    run_distributed(_worker_prefill, world, port)
+
+
 def _worker_stress(rank, world):
     """>= 1000 back-to-back fused steps: epoch/parity reuse must never serve stale partials."""
     import tree_attention_b200 as ta

@@ -36,6 +36,9 @@ struct FwdParams {
   int causal;
   long long q_pos0, kv_pos0;
   int num_m_tiles;
+  int n_items;   // B * Hq * num_m_tiles
+  int lag;       // merge CTA of item i is dispatched about `lag` compute CTAs after item i
+  CommCtx comm;  // world == 1: unused
 };
 
 template <int D>
@@ -56,7 +59,99 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   else return pack_f16x2(lo, hi);
 }
 
+// Merge CTA (fused multi-GPU mode): all W partial tiles of `item` have been pushed into THIS rank's
+// symmetric buffer by the compute CTAs of every rank; merge them in rank order and write the final tile.
 template <int D, bool BF16>
+__device__ __forceinline__ void merge_item(const FwdParams& p, int item, uint32_t epoch, uint8_t* smem) {
+  constexpr int kSlotBytes = kBlockM * D * 2 + kBlockM * 4;
+  constexpr int CPR = D / 8;  // 16-byte chunks per row
+  const int tid = threadIdx.x;
+  const int world = p.comm.world;
+  const int parity = epoch & 1;
+  const int mi = item % p.num_m_tiles;
+  const int bh = item / p.num_m_tiles;
+  const int hq = bh % p.Hq, b = bh / p.Hq;
+  const int m0 = (p.num_m_tiles - 1 - mi) * kBlockM;
+  float* w_s = reinterpret_cast<float*>(smem);           // [128][world]
+  int* ok_s = reinterpret_cast<int*>(w_s + kBlockM * kMaxWorld);
+  if (tid == 0) *ok_s = 1;
+  __syncthreads();
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(p.comm.data[p.comm.rank]);
+  if (tid < world) {
+    const uint32_t* f = p.comm.flags[p.comm.rank] + ((size_t)(parity * world + tid) * p.n_items + item);
+    if (!spin_flag_acquire(f, epoch, p.comm.timeout_ns)) {
+      p.comm.status[0] = kCommTimeout; p.comm.status[1] = item; p.comm.status[2] = tid; p.comm.status[3] = epoch;
+      *ok_s = 0;
+    }
+  }
+  __syncthreads();
+  const bool ok = *ok_s != 0;
+  if (tid < kBlockM) {
+    const int row = tid;
+    float mx = neg_inf_f();
+    for (int s = 0; s < world; ++s) {
+      const float* lp = reinterpret_cast<const float*>(base + ((size_t)(parity * world + s) * p.n_items + item) * kSlotBytes + kBlockM * D * 2);
+      mx = fmaxf(mx, ld_relaxed_sys_f(lp + row));
+    }
+    const float ms = mx == neg_inf_f() ? 0.f : mx;
+    float den = 0.f;
+    for (int s = 0; s < world; ++s) {
+      const float* lp = reinterpret_cast<const float*>(base + ((size_t)(parity * world + s) * p.n_items + item) * kSlotBytes + kBlockM * D * 2);
+      const float w = fast_exp2((ld_relaxed_sys_f(lp + row) - ms) * 1.4426950408889634f);
+      w_s[row * kMaxWorld + s] = w;
+      den += w;
+    }
+    const float inv = den > 0.f ? 1.f / den : 0.f;
+    for (int s = 0; s < world; ++s) w_s[row * kMaxWorld + s] *= inv;
+    if (m0 + row < p.Sq) {
+      float l = den > 0.f ? ms + fast_log2(den) * 0.6931471805599453f : neg_inf_f();
+      if (!ok) l = __int_as_float(0x7fc00000);
+      p.lse[((long long)b * p.Hq + hq) * p.Sq + m0 + row] = l;
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < kBlockM * CPR; c += kFwdThreads) {
+    const int row = c / CPR, ch = c - row * CPR;
+    if (m0 + row >= p.Sq) continue;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < world; ++s) {
+      const uint8_t* sp = base + ((size_t)(parity * world + s) * p.n_items + item) * kSlotBytes + (size_t)row * D * 2 + ch * 16;
+      const float4 raw = ld_relaxed_sys_f4(reinterpret_cast<const float4*>(sp));
+      const uint32_t w4[4] = {__float_as_uint(raw.x), __float_as_uint(raw.y), __float_as_uint(raw.z), __float_as_uint(raw.w)};
+      const float w = w_s[row * kMaxWorld + s];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float lo, hi;
+        if constexpr (BF16) { lo = bf16lo(w4[i]); hi = bf16hi(w4[i]); } else { lo = f16lo(w4[i]); hi = f16hi(w4[i]); }
+        acc[2 * i] = fmaf(w, lo, acc[2 * i]);
+        acc[2 * i + 1] = fmaf(w, hi, acc[2 * i + 1]);
+      }
+    }
+    if (!ok) { for (int i = 0; i < 8; ++i) acc[i] = __int_as_float(0x7fc00000); }
+    uint4 o;
+    o.x = pack2<BF16>(acc[0], acc[1]); o.y = pack2<BF16>(acc[2], acc[3]);
+    o.z = pack2<BF16>(acc[4], acc[5]); o.w = pack2<BF16>(acc[6], acc[7]);
+    uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)b * p.o_sb + (long long)hq * p.o_sh +
+                   (long long)(m0 + row) * p.o_ss + ch * 8;
+    *reinterpret_cast<uint4*>(op) = o;
+  }
+}
+
+// end-of-kernel arrival; the last CTA bumps the device-resident epoch for the next launch
+__device__ __forceinline__ void comm_kernel_exit(const FwdParams& p, uint32_t epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t done = atomicAdd(p.comm.status + 8, 1u);
+    if (done == gridDim.x - 1) {
+      p.comm.status[8] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(p.comm.epoch) = epoch;
+    }
+  }
+}
+
+template <int D, bool BF16, bool kComm>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                 const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap omap,
@@ -82,10 +177,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int m_tile = p.num_m_tiles - 1 - (int)blockIdx.x;  // heaviest (causal) tiles first
-  const int hq = blockIdx.y, b = blockIdx.z;
+  // ---- work decode.  Single GPU: block x computes item x.  Fused multi-GPU: compute CTAs and merge CTAs
+  // share the launch, merges trail their item by `lag` compute CTAs:
+  //   x < L: compute x | L <= x < 2N-L: even -> compute, odd -> merge | x >= 2N-L: merge
+  int item = blockIdx.x;
+  uint32_t epoch = 0;
+  if constexpr (kComm) {
+    epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
+    const int N = p.n_items, L = p.lag, x = blockIdx.x;
+    bool is_merge = false;
+    if (x < L) item = x;
+    else if (x < 2 * N - L) { const int k = x - L; if (k & 1) { is_merge = true; item = k >> 1; } else item = L + (k >> 1); }
+    else { is_merge = true; item = (N - L) + (x - (2 * N - L)); }
+    if (is_merge) {
+      merge_item<D, BF16>(p, item, epoch, smem);
+      comm_kernel_exit(p, epoch);
+      return;
+    }
+  }
+  const int m_tile = p.num_m_tiles - 1 - (item % p.num_m_tiles);  // heaviest (causal) tiles first
+  const int bh = item / p.num_m_tiles;
+  const int hq = bh % p.Hq, b = bh / p.Hq;
   const int hkv = hq / p.G;
   const int m0 = m_tile * kBlockM;
+  constexpr int kSlotBytes = kBlockM * D * 2 + kBlockM * 4;
+  const size_t slot_off = kComm ? ((size_t)((epoch & 1) * p.comm.world + p.comm.rank) * p.n_items + item) * kSlotBytes : 0;
+  const size_t flag_off = kComm ? ((size_t)((epoch & 1) * p.comm.world + p.comm.rank) * p.n_items + item) : 0;
 
   // number of KV tiles this query tile can see
   int n_end = p.S;
@@ -98,7 +215,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
   if (n_tiles == 0) {
     // nothing visible: the monoid identity (0, -inf)
-    if (warp < 4) {
+    if constexpr (kComm) {
+      if (!p.comm.skip_publish) {
+        for (int dst = 0; dst < p.comm.world; ++dst) {
+          uint8_t* slot = reinterpret_cast<uint8_t*>(p.comm.data[dst]) + slot_off;
+          for (int c = tid; c < kBlockM * (D / 8); c += kFwdThreads) reinterpret_cast<uint4*>(slot)[c] = make_uint4(0, 0, 0, 0);
+          if (tid < kBlockM) reinterpret_cast<float*>(slot + kBlockM * D * 2)[tid] = neg_inf_f();
+        }
+        __syncthreads();
+        if (tid < p.comm.world) { fence_acq_rel_sys(); st_release_sys_u32(p.comm.flags[tid] + flag_off, epoch); }
+      }
+      comm_kernel_exit(p, epoch);
+    } else if (warp < 4) {
       const int row = m0 + tid;
       if (row < p.Sq) {
         uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)b * p.o_sb + (long long)hq * p.o_sh + (long long)row * p.o_ss;
@@ -221,9 +349,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         for (int c = 0; c < 128; ++c)
           if (c > limc) sr[c] = 0xff800000u;
       }
-      float mx = neg_inf_f();
+      float mx8[8];
 #pragma unroll
-      for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
+      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
+#pragma unroll
+      for (int c = 8; c < 128; c += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(mx8[i], __uint_as_float(sr[c + i]));
+      }
+      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       const float m_new = fmaxf(m_used, mx * p.scale_log2);
       // lazy rescale: refresh the reference max only when it moved by more than the threshold
       const bool refresh = (m_new - m_used > kRescaleThreshold) || (m_used == neg_inf_f() && m_new != neg_inf_f());
@@ -246,16 +380,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       }
       const float m_sub = (m_used == neg_inf_f()) ? 0.f : m_used;
       const float neg_m = -m_sub;
-      float ls0 = 0.f, ls1 = 0.f;
+      float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       uint32_t pk[64];
 #pragma unroll
-      for (int c = 0; c < 128; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c]), p.scale_log2, neg_m));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + 1]), p.scale_log2, neg_m));
-        ls0 += p0; ls1 += p1;
-        pk[c >> 1] = pack2<BF16>(p0, p1);
+      for (int c = 0; c < 128; c += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c + i]), p.scale_log2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + i + 1]), p.scale_log2, neg_m));
+          ls[i] += p0; ls[i + 1] += p1;
+          pk[(c + i) >> 1] = pack2<BF16>(p0, p1);
+        }
       }
-      l_sum += ls0 + ls1;
+      l_sum += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
       tmem_st_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
       tmem_st_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       tmem_st_wait();
@@ -287,17 +424,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = w;
       }
     }
-    if (m0 + row < p.Sq)
-      p.lse[((long long)b * p.Hq + hq) * p.Sq + m0 + row] =
-          l_sum > 0.f ? (m_used + fast_log2(l_sum)) * 0.6931471805599453f : neg_inf_f();
-    fence_proxy_async_smem();
-    tc_fence_before();
-    named_bar_sync(1, kSoftmaxThreads);
-    if (tid == 0) {
+    const float lse_row = l_sum > 0.f ? (m_used + fast_log2(l_sum)) * 0.6931471805599453f : neg_inf_f();
+    if constexpr (!kComm) {
+      if (m0 + row < p.Sq) p.lse[((long long)b * p.Hq + hq) * p.Sq + m0 + row] = lse_row;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(1, kSoftmaxThreads);
+      if (tid == 0) {
 #pragma unroll
-      for (int a = 0; a < SM::kAtoms; ++a) tma_store_4d(&omap, q_s + a * SM::kAtomBytes, a * 64, m0, hq, b);
-      tma_store_commit();
-      tma_store_wait<0>();
+        for (int a = 0; a < SM::kAtoms; ++a) tma_store_4d(&omap, q_s + a * SM::kAtomBytes, a * 64, m0, hq, b);
+        tma_store_commit();
+        tma_store_wait<0>();
+      }
+    } else {
+      // fused tree combine, step 1: push this rank's partial tile (o in the I/O dtype, lse fp32) into slot
+      // [parity][my rank][item] of EVERY rank's symmetric buffer with coalesced 16-byte P2P stores, then
+      // release one epoch flag per destination.
+      tc_fence_before();
+      named_bar_sync(1, kSoftmaxThreads);
+      if (!p.comm.skip_publish) {
+        constexpr int CPR = D / 8;
+        for (int dst = 0; dst < p.comm.world; ++dst) {
+          uint8_t* slot = reinterpret_cast<uint8_t*>(p.comm.data[dst]) + slot_off;
+#pragma unroll 4
+          for (int c = tid; c < kBlockM * CPR; c += kSoftmaxThreads) {
+            const int r = c / CPR, ch = c - r * CPR;
+            const uint4 w = *reinterpret_cast<const uint4*>(q_s + (ch >> 3) * SM::kAtomBytes + r * 128 + (((ch & 7) ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(slot + (size_t)r * D * 2 + ch * 16) = w;
+          }
+          reinterpret_cast<float*>(slot + kBlockM * D * 2)[row] = lse_row;
+        }
+        named_bar_sync(1, kSoftmaxThreads);
+        if (tid < p.comm.world) { fence_acq_rel_sys(); st_release_sys_u32(p.comm.flags[tid] + flag_off, epoch); }
+      }
     }
   }
   tc_fence_before();
@@ -306,11 +465,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     tc_fence_after();
     tmem_dealloc<512>(tmem);
   }
+  if constexpr (kComm) comm_kernel_exit(p, epoch);
 }
 
-template <int D, bool BF16>
+inline CommCtx to_device_ctx(const CommCtxHost& h) {
+  CommCtx c;
+  c.rank = h.rank;
+  c.world = h.world;
+  for (int i = 0; i < kMaxWorld; ++i) {
+    c.data[i] = reinterpret_cast<float*>(h.data[i]);
+    c.flags[i] = reinterpret_cast<uint32_t*>(h.flags[i]);
+  }
+  c.epoch = reinterpret_cast<uint32_t*>(h.epoch);
+  c.status = reinterpret_cast<uint32_t*>(h.status);
+  c.timeout_ns = h.timeout_ns;
+  c.skip_publish = h.skip_publish;
+  return c;
+}
+
+template <int D, bool BF16, bool kComm>
 void launch_fwd(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                cudaStream_t stream) {
+                const CommCtxHost& comm, cudaStream_t stream) {
   using SM = FwdSmem<D>;
   CUtensorMap qmap = make_tmap_bhsd(q, 2, s.B, s.Hq, s.Sq, D, s.q_sb, s.q_sh, s.q_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, D, s.k_sb, s.k_sh, s.k_ss, 64, kBlockN, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -322,31 +497,50 @@ void launch_fwd(const AttnShape& s, const void* q, const void* k, const void* v,
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
   p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;
   p.num_m_tiles = (s.Sq + kBlockM - 1) / kBlockM;
-  auto kern = attn_fwd_kernel<D, BF16>;
+  p.n_items = p.num_m_tiles * s.Hq * s.B;
+  p.lag = std::min(p.n_items, 2 * num_sms());
+  p.comm = to_device_ctx(comm);
+  if (kComm) {
+    const size_t slot = (size_t)kBlockM * D * 2 + kBlockM * 4;
+    if ((size_t)2 * comm.world * p.n_items * slot > comm.data_bytes ||
+        (size_t)2 * comm.world * p.n_items * 4 > comm.flag_bytes)
+      throw std::runtime_error("attn_fwd(fused): symmetric buffer too small");
+  }
+  auto kern = attn_fwd_kernel<D, BF16, kComm>;
   static bool configured = false;
   if (!configured) {
     TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kTotal));
     configured = true;
   }
-  dim3 grid(p.num_m_tiles, s.Hq, s.B);
+  dim3 grid(kComm ? 2 * p.n_items : p.n_items);
   kern<<<grid, kFwdThreads, SM::kTotal, stream>>>(qmap, kmap, vmap, omap, p);
   TA_CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace
 
+size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes) {
+  const size_t n_items = (size_t)((s.Sq + kBlockM - 1) / kBlockM) * s.Hq * s.B;
+  const size_t slot = (size_t)kBlockM * s.D * 2 + kBlockM * 4;
+  *flag_bytes = (size_t)2 * world * n_items * 4;
+  return (size_t)2 * world * n_items * slot;
+}
+
 void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                     cudaStream_t stream) {
+                     const CommCtxHost& comm, cudaStream_t stream) {
   if (s.D != 64 && s.D != 128) throw std::runtime_error("attn_fwd: head_dim must be 64 or 128");
   if (s.Hq % s.Hkv != 0) throw std::runtime_error("attn_fwd: Hq must be a multiple of Hkv");
   if (s.S <= 0 || s.Sq <= 0) throw std::runtime_error("attn_fwd: empty problem");
+  const bool fused = comm.world > 1;
+#define TA_FWD(DD, BB)                                                               \
+  if (fused) launch_fwd<DD, BB, true>(s, q, k, v, out, lse, comm, stream);           \
+  else launch_fwd<DD, BB, false>(s, q, k, v, out, lse, comm, stream);
   if (s.D == 128) {
-    if (s.is_bf16) launch_fwd<128, true>(s, q, k, v, out, lse, stream);
-    else launch_fwd<128, false>(s, q, k, v, out, lse, stream);
+    if (s.is_bf16) { TA_FWD(128, true) } else { TA_FWD(128, false) }
   } else {
-    if (s.is_bf16) launch_fwd<64, true>(s, q, k, v, out, lse, stream);
-    else launch_fwd<64, false>(s, q, k, v, out, lse, stream);
+    if (s.is_bf16) { TA_FWD(64, true) } else { TA_FWD(64, false) }
   }
+#undef TA_FWD
 }
 
 }  // namespace ta

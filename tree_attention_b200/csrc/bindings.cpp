@@ -129,14 +129,43 @@ void decode_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, a
                          at::cuda::getCurrentCUDAStream());
 }
 
+py::tuple attn_fwd_comm_bytes(int B, int Hq, int Sq, int D, int world) {
+  AttnShape s;
+  s.B = B; s.Hq = Hq; s.Sq = Sq; s.D = D;
+  size_t fb = 0;
+  size_t db = ta::attn_fwd_comm_bytes(s, world, &fb);
+  return py::make_tuple((int64_t)db, (int64_t)fb);
+}
+
 void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out, at::Tensor& lse,
-              double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
+              double scale, bool causal, int64_t q_pos0, int64_t kv_pos0, py::object comm) {
   c10::cuda::CUDAGuard guard(q.device());
   AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
   TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == (int64_t)s.B * s.Hq * s.Sq,
               "lse must be contiguous fp32 (B, Hq, Sq)");
-  ta::attn_fwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(),
+  CommCtxHost c;
+  if (!comm.is_none()) c = comm.cast<Comm&>().h;
+  ta::attn_fwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
                       at::cuda::getCurrentCUDAStream());
+}
+
+void attn_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& o, const at::Tensor& dout,
+              const at::Tensor& lse, at::Tensor& dq, at::Tensor& dk, at::Tensor& dv, at::Tensor& delta, at::Tensor& lse2,
+              double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
+  c10::cuda::CUDAGuard guard(q.device());
+  AttnShape s = make_shape(q, k, v, o, scale, causal, q_pos0, kv_pos0);
+  TORCH_CHECK(dout.sizes() == q.sizes() && dout.scalar_type() == q.scalar_type() && dout.stride(3) == 1, "bad dout");
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == (int64_t)s.B * s.Hq * s.Sq, "bad lse");
+  TORCH_CHECK(dq.scalar_type() == at::kFloat && dq.is_contiguous() && dq.numel() == q.numel(), "dq must be contiguous fp32");
+  TORCH_CHECK(dk.is_contiguous() && dv.is_contiguous() && dk.numel() == k.numel() && dv.numel() == v.numel() &&
+                  dk.scalar_type() == q.scalar_type() && dv.scalar_type() == q.scalar_type(), "bad dk/dv");
+  const int64_t sq_pad = (s.Sq + 63) / 64 * 64;
+  TORCH_CHECK(delta.scalar_type() == at::kFloat && lse2.scalar_type() == at::kFloat && delta.is_contiguous() &&
+                  lse2.is_contiguous() && delta.numel() >= (int64_t)s.B * s.Hq * sq_pad && lse2.numel() >= (int64_t)s.B * s.Hq * sq_pad,
+              "delta / lse2 scratch too small");
+  ta::attn_bwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), dout.data_ptr(), lse.data_ptr<float>(),
+                      dq.data_ptr<float>(), dk.data_ptr(), dv.data_ptr(), delta.data_ptr<float>(), lse2.data_ptr<float>(),
+                      dout.stride(0), dout.stride(1), dout.stride(2), at::cuda::getCurrentCUDAStream());
 }
 
 void combine(const at::Tensor& o_part, const at::Tensor& lse_part, at::Tensor& out, c10::optional<at::Tensor> lse_out,
@@ -192,6 +221,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_plan", &decode_plan);
   m.def("decode_fwd", &decode_fwd);
   m.def("attn_fwd", &attn_fwd);
+  m.def("attn_fwd_comm_bytes", &attn_fwd_comm_bytes);
+  m.def("attn_bwd", &attn_bwd);
   m.def("combine", &combine);
   m.def("umma_probe", &umma_probe);
   m.def("num_sms", []() { return ta::num_sms(); });

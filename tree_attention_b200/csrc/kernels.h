@@ -58,7 +58,17 @@ void umma_probe_launch(const void* a, const void* b, float* c, int N, int K, int
                        cudaStream_t stream);
 
 // ---- tcgen05 flash-attention forward: shard-local partial (o normalised, lse natural log) ----
+// comm.world > 1: fused mode -- compute CTAs push their partial tiles to every peer, merge CTAs in the same
+// launch produce the final (replicated) output; no NCCL.
 void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                     cudaStream_t stream);
+                     const CommCtxHost& comm, cudaStream_t stream);
+size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
+
+// ---- tcgen05 flash-attention backward over one KV shard with the GLOBAL o / lse ----
+// dq: fp32 (B, Hq, Sq, D) contiguous (this shard's partial); dk, dv: (B, Hkv, S, D) contiguous, I/O dtype;
+// delta, lse2: fp32 scratch (B, Hq, ceil64(Sq)).
+void attn_bwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, const void* o, const void* dout,
+                     const float* lse, float* dq, void* dk, void* dv, float* delta, float* lse2, int64_t do_sb,
+                     int64_t do_sh, int64_t do_ss, cudaStream_t stream);
 
 }  // namespace ta

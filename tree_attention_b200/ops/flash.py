@@ -39,7 +39,10 @@ def attention_fwd(
     q_pos0: int = 0,
     kv_pos0: int = 0,
     out: Optional[torch.Tensor] = None,
+    comm=None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Shard-local partial ``(o, lse)``; with ``comm`` (a ``_C.Comm`` of the ``fwd`` family) the SAME launch
+    also performs the cross-GPU combine and ``(o, lse)`` are the global, replicated results."""
     C = _build.load()
     q = q if q.stride(-1) == 1 else q.contiguous()
     k = k if k.stride(-1) == 1 else k.contiguous()
@@ -48,8 +51,38 @@ def attention_fwd(
     if out is None:
         out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
     lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
-    C.attn_fwd(q, k, v, out, lse, float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0))
+    C.attn_fwd(q, k, v, out, lse, float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0), comm)
     return out, lse
+
+
+def bwd_eligible(q: torch.Tensor, k: torch.Tensor) -> bool:
+    try:
+        has = hasattr(_build.load(), "attn_bwd")
+    except Exception:
+        has = False
+    return has and q.is_cuda and q.dtype in (torch.bfloat16, torch.float16) and q.shape[-1] in (64, 128)
+
+
+def attention_bwd(q, k, v, o, lse, do, softmax_scale, causal=False, q_pos0=0, kv_pos0=0):
+    """tcgen05 backward over THIS rank's KV shard with the global ``o``/``lse``.
+    Returns ``(dq_partial fp32, dk, dv)``; ``dq_partial`` must be summed over ranks."""
+    C = _build.load()
+    q = q if q.stride(-1) == 1 else q.contiguous()
+    k = k if k.stride(-1) == 1 else k.contiguous()
+    v = v if v.stride(-1) == 1 else v.contiguous()
+    o = o if o.stride(-1) == 1 else o.contiguous()
+    do = do if do.stride(-1) == 1 else do.contiguous()
+    b, hq, sq, d = q.shape
+    hkv, s = k.shape[1], k.shape[2]
+    sq_pad = (sq + 63) // 64 * 64
+    dq = torch.empty((b, hq, sq, d), dtype=torch.float32, device=q.device)
+    dk = torch.empty((b, hkv, s, d), dtype=q.dtype, device=q.device)
+    dv = torch.empty((b, hkv, s, d), dtype=q.dtype, device=q.device)
+    delta = torch.empty((b, hq, sq_pad), dtype=torch.float32, device=q.device)
+    lse2 = torch.empty((b, hq, sq_pad), dtype=torch.float32, device=q.device)
+    C.attn_bwd(q, k, v, o, do, lse.contiguous(), dq, dk, dv, delta, lse2, float(softmax_scale), bool(causal),
+               int(q_pos0), int(kv_pos0))
+    return dq, dk, dv
 
 
 def attention_fwd_fused(
@@ -63,9 +96,33 @@ def attention_fwd_fused(
     group=None,
     return_lse: bool = True,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """Local tcgen05 forward + cross-GPU combine over symmetric memory (no NCCL)."""
-    from ..parallel.tree import combine_partials
+    """ONE launch per rank: tcgen05 attention over the local KV shard, partial tiles pushed to every peer
+    over NVLink from the epilogue, merge CTAs of the same launch write the replicated result.  No NCCL.
 
-    o_p, lse_p = attention_fwd(q, k, v, softmax_scale, causal, q_pos0, kv_pos0)
-    o, lse = combine_partials(o_p, lse_p, group, "symm", "oneshot", out_dtype=q.dtype)
-    return o, lse
+    Very long query blocks are processed in chunks so that the symmetric buffer (2 x W x |O| in the I/O
+    dtype) stays under ``TREE_ATTN_FWD_SYMM_CAP_GB`` (default 8)."""
+    import os
+
+    import torch.distributed as dist
+
+    from ..parallel import symm
+
+    C = _build.load()
+    world = dist.get_world_size(group)
+    b, hq, sq, d = q.shape
+    cap = int(float(os.environ.get("TREE_ATTN_FWD_SYMM_CAP_GB", "8")) * (1 << 30))
+    per_row = 2 * world * b * hq * (d * 2 + 4)
+    chunk = max(128, min(sq, (cap // per_row) // 128 * 128))
+    data, flags = C.attn_fwd_comm_bytes(b, hq, min(chunk, sq), d, world)
+    reg = symm.get_region("fwd", int(data), int(flags), group)
+    out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
+    lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
+    if chunk >= sq:
+        o_c, l_c = attention_fwd(q, k, v, softmax_scale, causal, q_pos0, kv_pos0, out=out, comm=reg.comm)
+        return o_c, l_c
+    for s0 in range(0, sq, chunk):
+        s1 = min(sq, s0 + chunk)
+        o_c, l_c = attention_fwd(q[:, :, s0:s1], k, v, softmax_scale, causal, q_pos0 + s0, kv_pos0,
+                                 out=out[:, :, s0:s1], comm=reg.comm)
+        lse[:, :, s0:s1] = l_c
+    return out, lse
