@@ -399,6 +399,23 @@ def run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier):
             out["own_kernel_plus_nccl_allreduce3_ms_per_step"] = timeit(
                 lambda i: ta.tree_attention(q, kvs[i % nb][0], kvs[i % nb][1], softmax_scale=scale, backend="nccl",
                                             schedule="allreduce3"))
+        if world > 1:
+            from tree_attention_b200.parallel import symm
+
+            reg = symm.regions().get(("decode", 0))
+            if reg is not None:
+                reg.combine_stamps(reset=True)
+                for i in range(200):
+                    sess.step_device(None, i)
+                torch.cuda.synchronize()
+                st = reg.combine_stamps(reset=True)
+                B_, Hq_, D_ = q.shape[0], q.shape[1], q.shape[3]
+                recv = (world - 1) * B_ * Hq_ * (D_ + 4) * 4
+                out["combine_step"] = {
+                    **st, "bytes_received_per_rank": recv,
+                    "nvlink_gbs_per_combine_step": recv / max(st["combine_step_ns"], 1),
+                    "note": "in-kernel globaltimer stamps, max over CTAs and 200 steps: publish -> merged output written",
+                }
     except Exception as e:  # extras must never take the headline down
         out["extras_error"] = f"{type(e).__name__}: {e}"[:200]
     return out

@@ -12,6 +12,8 @@ from _dist_utils import run_distributed
 NGPU = torch.cuda.device_count() if torch.cuda.is_available() else 0
 need2 = pytest.mark.skipif(NGPU < 2, reason="needs >= 2 GPUs")
 WORLDS = [w for w in (2, 4, 8) if w <= NGPU]
+if os.environ.get("TREE_ATTN_TEST_WORLDS"):
+    WORLDS = [int(w) for w in os.environ["TREE_ATTN_TEST_WORLDS"].split(",") if int(w) <= NGPU]
 
 
 def _oracle(q, k, v, world, scale, causal):

@@ -140,6 +140,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   // bump happens after ALL CTAs passed their end-of-kernel arrival).
   uint32_t epoch = 0;
   if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
+  const uint64_t t_cta0 = globaltimer_ns();
   const int parity = epoch & 1;
   const int BH = p.B * p.Hkv;
   const long long q_pos_max = p.q_pos0 + p.Sq - 1;
@@ -227,6 +228,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   };
 
   // merge the W published partials of head x (all in LOCAL memory by now) in rank order
+  uint64_t t_publish = 0;
   auto combine_ranks = [&](int x) {
     if (tid < world) {
       bool ok = spin_flag_acquire(flag_ptr(p.comm.rank, tid, x), epoch, p.comm.timeout_ns);
@@ -236,6 +238,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       }
     }
     named_bar_sync(1, kConsumerThreads);
+    const uint64_t t_got = globaltimer_ns();
     const bool ok = s_misc[2] != 0;
     for (int idx = tid; idx < p.rows_valid * D; idx += kConsumerThreads) {
       const int r = idx / D, d = idx - r * D;
@@ -255,6 +258,12 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       store_out(x, r, d, o_norm, lse2);
     }
     named_bar_sync(1, kConsumerThreads);
+    if (tid == 0 && t_publish != 0) {  // in-kernel stamps of the combine step
+      const uint64_t t_done = globaltimer_ns();
+      atomicMax(p.comm.status + 10, (uint32_t)min((unsigned long long)(t_got - t_publish), 0xffffffffull));
+      atomicMax(p.comm.status + 11, (uint32_t)min((unsigned long long)(t_done - t_publish), 0xffffffffull));
+      atomicMax(p.comm.status + 12, (uint32_t)min((unsigned long long)(t_publish - t_cta0), 0xffffffffull));
+    }
   };
 
   // per-CTA partial of head x is complete: merge warps, write partial, take a ticket, maybe finish the head
@@ -340,6 +349,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         st_release_sys_u32(flag_ptr(tid, p.comm.rank, x), epoch);
       }
       if (tid == 0) {
+        t_publish = globaltimer_ns();
         const int n = s_misc[1];
         if (n < kMaxPending) { pending[n] = x; s_misc[1] = n + 1; }
         else s_misc[3] = x + 1;  // list full: combine inline below

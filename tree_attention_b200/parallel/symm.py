@@ -78,6 +78,17 @@ class SymmRegion:
                 f"(item {item}) -- peer dead, not launched, or publish skipped"
             )
 
+    def combine_stamps(self, reset: bool = True) -> dict:
+        """In-kernel globaltimer stamps of the fused combine (max over CTAs and calls since the last reset):
+        wait for peers, publish -> merged output written, CTA start -> local partial published (ns)."""
+        C = _build.load()
+        v = C.symm_read_u32(self.local_ptr + STATUS_OFFSET + 40, 3)
+        if reset:
+            torch.cuda.synchronize()
+            C.symm_memset(self.local_ptr + STATUS_OFFSET + 40, 0, 12)
+            torch.cuda.synchronize()
+        return {"wait_peers_ns": int(v[0]), "combine_step_ns": int(v[1]), "local_partial_ns": int(v[2])}
+
     def clear_status(self) -> None:
         C = _build.load()
         C.symm_memset(self.local_ptr + STATUS_OFFSET, 0, 16)
