@@ -220,41 +220,63 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       p.lse[((long long)b * p.Hq + (h * p.G + g)) * p.Sq + i] = lse2 * 0.6931471805599453f;
   };
 
-  auto slot_ptr = [&](int dst, int src, int x) -> float* {
-    return p.comm.data[dst] + ((size_t)(parity * world + src) * BH + x) * (size_t)(R * (D + 4));
+  // ---- cross-GPU transport: NCCL-LL style words {fp32 value, epoch tag} (8-byte atomic granules).  Every word
+  // validates itself, so there is no separate flag, no fence and no second NVLink round trip: the combine
+  // costs one one-way store latency.  Slots are double-buffered by epoch parity.
+  auto word_ptr = [&](int dst, int src, int x) -> uint2* {
+    return reinterpret_cast<uint2*>(p.comm.data[dst]) + ((size_t)(parity * world + src) * BH + x) * (size_t)(R * (D + 2));
   };
-  auto flag_ptr = [&](int dst, int src, int x) -> uint32_t* {
-    return p.comm.flags[dst] + ((size_t)(parity * world + src) * BH + x);
+  auto ll_store = [&](uint2* w, float v) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(w), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+  };
+  auto ll_wait = [&](const uint2* w, bool& ok) -> float {
+    uint32_t v, tag;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(w) : "memory");
+    if (tag != epoch) {
+      const uint64_t t0 = globaltimer_ns();
+      uint32_t it = 0;
+      do {
+        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(w) : "memory");
+        if (tag == epoch) break;
+        if ((++it & 0x3fu) == 0 && globaltimer_ns() - t0 > p.comm.timeout_ns) { ok = false; break; }
+      } while (true);
+    }
+    return __uint_as_float(v);
   };
 
-  // merge the W published partials of head x (all in LOCAL memory by now) in rank order
+  // merge the W published partials of head x in rank order (each word is polled until its tag is this epoch)
   uint64_t t_publish = 0;
   auto combine_ranks = [&](int x) {
-    if (tid < world) {
-      bool ok = spin_flag_acquire(flag_ptr(p.comm.rank, tid, x), epoch, p.comm.timeout_ns);
-      if (!ok) {
-        p.comm.status[0] = kCommTimeout; p.comm.status[1] = x; p.comm.status[2] = tid; p.comm.status[3] = epoch;
-        s_misc[2] = 0;
-      }
-    }
-    named_bar_sync(1, kConsumerThreads);
-    const uint64_t t_got = globaltimer_ns();
-    const bool ok = s_misc[2] != 0;
+    uint64_t t_got = 0;
     for (int idx = tid; idx < p.rows_valid * D; idx += kConsumerThreads) {
       const int r = idx / D, d = idx - r * D;
+      bool ok = true;
+      float lse_s[kMaxWorld];
       float mx = neg_inf();
-      for (int s = 0; s < world; ++s) mx = fmaxf(mx, ld_relaxed_sys_f(slot_ptr(p.comm.rank, s, x) + r * (D + 4) + D));
+      int bad_src = -1;
+      for (int s = 0; s < world; ++s) {
+        bool oks = true;
+        lse_s[s] = ll_wait(word_ptr(p.comm.rank, s, x) + r * (D + 2) + D, oks);
+        if (!oks) { ok = false; bad_src = s; }
+        mx = fmaxf(mx, lse_s[s]);
+      }
       const float ms = (mx == neg_inf()) ? 0.f : mx;
       float num = 0.f, den = 0.f;
       for (int s = 0; s < world; ++s) {
-        const float* sp = slot_ptr(p.comm.rank, s, x) + r * (D + 4);
-        const float w = fast_exp2(ld_relaxed_sys_f(sp + D) - ms);
-        num = fmaf(w, ld_relaxed_sys_f(sp + d), num);
+        bool oks = true;
+        const float val = ll_wait(word_ptr(p.comm.rank, s, x) + r * (D + 2) + d, oks);
+        if (!oks) { ok = false; bad_src = s; }
+        const float w = fast_exp2(lse_s[s] - ms);
+        num = fmaf(w, val, num);
         den += w;
       }
+      if (idx == 0) t_got = globaltimer_ns();
       float o_norm = den > 0.f ? num / den : 0.f;
       float lse2 = den > 0.f ? ms + fast_log2(den) : neg_inf();
-      if (!ok) { o_norm = __int_as_float(0x7fc00000); lse2 = o_norm; }
+      if (!ok) {
+        o_norm = __int_as_float(0x7fc00000); lse2 = o_norm;
+        p.comm.status[0] = kCommTimeout; p.comm.status[1] = x; p.comm.status[2] = bad_src; p.comm.status[3] = epoch;
+      }
       store_out(x, r, d, o_norm, lse2);
     }
     named_bar_sync(1, kConsumerThreads);
@@ -334,20 +356,15 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       if (world == 1) {
         store_out(x, r, d, o_norm, lse2);
       } else if (!p.comm.skip_publish) {
-        // (d) publish to every rank's slot [parity][my rank][x] (own slot included)
+        // (d) publish to every rank's slot [parity][my rank][x] (own slot included): tagged 8-byte words
         for (int dst = 0; dst < world; ++dst) {
-          float* sp = slot_ptr(dst, p.comm.rank, x) + r * (D + 4);
-          sp[d] = o_norm;
-          if (d == 0) sp[D] = lse2;
+          uint2* wp = word_ptr(dst, p.comm.rank, x) + r * (D + 2);
+          ll_store(wp + d, o_norm);
+          if (d == 0) ll_store(wp + D, lse2);
         }
       }
     }
     if (world > 1) {
-      named_bar_sync(1, kConsumerThreads);
-      if (tid < world && !p.comm.skip_publish) {
-        fence_acq_rel_sys();
-        st_release_sys_u32(flag_ptr(tid, p.comm.rank, x), epoch);
-      }
       if (tid == 0) {
         t_publish = globaltimer_ns();
         const int n = s_misc[1];
@@ -538,7 +555,7 @@ void decode_simt_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, in
   *max_parts = mp;
   *rows_per_pass = R;
   *part_floats = (size_t)BH * mp * R * (s.D + 4);
-  *comm_floats = (size_t)2 * kMaxWorldHost * BH * R * (s.D + 4);
+  *comm_floats = (size_t)2 * kMaxWorldHost * BH * R * (s.D + 2) * 2;
   *comm_flags = (size_t)2 * kMaxWorldHost * BH;
 }
 
@@ -553,9 +570,8 @@ void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const 
   const int G = s.Hq / s.Hkv;
   const int total_rows = G * s.Sq;
   if (comm.world > 1) {
-    const size_t need_data = (size_t)2 * comm.world * s.B * s.Hkv * R * (s.D + 4) * sizeof(float);
-    const size_t need_flags = (size_t)2 * comm.world * s.B * s.Hkv * sizeof(uint32_t);
-    if (need_data > comm.data_bytes || need_flags > comm.flag_bytes)
+    const size_t need_data = (size_t)2 * comm.world * s.B * s.Hkv * R * (s.D + 2) * 8;
+    if (need_data > comm.data_bytes)
       throw std::runtime_error("decode_simt: symmetric buffer too small for this problem");
   }
   CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, s.D, s.k_sb, s.k_sh, s.k_ss, 64, kTileRows,

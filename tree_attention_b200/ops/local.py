@@ -85,8 +85,8 @@ def decode_comm_bytes(b: int, hq: int, hkv: int, sq: int, s: int, d: int, world:
     """(data_bytes, flag_bytes) the decode family needs in symmetric memory."""
     rows = min(4, max(1, (hq // hkv) * sq))
     rows = 4 if rows >= 4 else (2 if rows >= 2 else 1)
-    data = 2 * world * b * hkv * rows * (d + 4) * 4
-    flags = 2 * world * b * hkv * 4
+    data = 2 * world * b * hkv * rows * (d + 2) * 8   # {fp32 value, epoch tag} words
+    flags = 4096
     return data, flags
 
 
