@@ -37,6 +37,8 @@ def main():
             res = {}
             t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0), a.steps, a.warmup)
             res["tcgen05_own"] = t["median_ms"]
+            t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=1), a.steps, a.warmup)
+            res["tcgen05_own_v1_m128"] = t["median_ms"]
             if a.libs:
                 try:
                     from flash_attn import flash_attn_func

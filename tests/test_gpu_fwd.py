@@ -39,14 +39,15 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
-def test_fwd_matches_oracle(case):
+def test_fwd_matches_oracle(case, variant):
     b, hq, hkv, sq, s, d, dtype, causal, q_pos0, kv_pos0, bshd = case
     q, k, v = _mk(b, hq, hkv, sq, s, d, dtype, bshd=bshd)
     scale = d ** -0.5
     if q_pos0 is None:
         q_pos0 = s - sq
-    out, lse = flash.attention_fwd(q, k, v, scale, causal, q_pos0, kv_pos0)
+    out, lse = flash.attention_fwd(q, k, v, scale, causal, q_pos0, kv_pos0, variant=variant)
     torch.cuda.synchronize()
     o_ref, l_ref = ref.attention_partial_ref(q, k, v, scale, causal, q_pos0, kv_pos0, torch.float32)
     assert not torch.isnan(out).any()

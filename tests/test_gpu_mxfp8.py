@@ -1,0 +1,63 @@
+"""mxfp8 quant kernels and the block-scaled-fp8 KV decode kernel vs their PyTorch oracles."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import tree_attention_b200 as ta
+from tree_attention_b200.ops import local as L
+from tree_attention_b200.ops import quant
+from tree_attention_b200.ops import reference as ref
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_quant_kernel_matches_reference(dtype):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = (torch.randn(2, 3, 257, 128, device="cuda", generator=g) * 4).to(dtype)
+    q, s = quant.quantize_mxfp8(x)
+    q_ref, s_ref = quant.quantize_mxfp8_ref(x)
+    assert torch.equal(s, s_ref)
+    y, y_ref = quant.dequantize_mxfp8(q, s), quant.dequantize_mxfp8_ref(q_ref, s_ref)
+    # identical up to round-to-nearest ties in the e4m3 conversion
+    assert (y - y_ref).abs().max().item() <= (x.float().abs().max().item() * 2 ** -3)
+    assert ((q != q_ref).float().mean().item()) < 1e-3
+    assert torch.equal(quant.dequantize_mxfp8(q_ref, s_ref), y_ref)
+
+
+CASES = [
+    (1, 32, 32, 1, 4096, False),
+    (2, 8, 8, 1, 300, False),
+    (1, 32, 8, 1, 8192, False),     # GQA -> 4 rows
+    (1, 8, 2, 2, 2000, True),       # 8 rows -> two passes, causal
+    (1, 4, 4, 1, 70000, False),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_mxfp8_decode_matches_dequantised_oracle(case):
+    b, hq, hkv, sq, s, causal = case
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(b, hq, sq, 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(b, hkv, s, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(b, hkv, s, 128, device="cuda", generator=g).bfloat16()
+    kq, vq = quant.MXFP8Tensor.from_float(k), quant.MXFP8Tensor.from_float(v)
+    scale = 128 ** -0.5
+    out, lse = L.decode_attention_mxfp8(q, kq, vq, scale, causal, s - sq, 0)
+    torch.cuda.synchronize()
+    o_ref, l_ref = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize(), scale, causal, s - sq, 0, torch.float32, block=16384)
+    assert (out.float() - o_ref).abs().max().item() < 2e-2
+    assert (lse - l_ref).abs().max().item() < 1e-2
+    # and the quantisation error vs the bf16 cache stays small
+    o_full, _ = ref.attention_partial_ref(q, k, v, scale, causal, s - sq, 0, torch.float32, block=16384)
+    assert (out.float() - o_full).abs().max().item() < 0.1
+
+
+def test_public_api_with_mxfp8_cache():
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(1, 16, 1, 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(1, 16, 5000, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(1, 16, 5000, 128, device="cuda", generator=g).bfloat16()
+    kq, vq = quant.MXFP8Tensor.from_float(k), quant.MXFP8Tensor.from_float(v)
+    out = ta.tree_attention(q, kq, vq)
+    exp, _ = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize())
+    assert (out.float() - exp).abs().max().item() < 2e-2

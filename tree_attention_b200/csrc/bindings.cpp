@@ -138,15 +138,80 @@ py::tuple attn_fwd_comm_bytes(int B, int Hq, int Sq, int D, int world) {
 }
 
 void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out, at::Tensor& lse,
-              double scale, bool causal, int64_t q_pos0, int64_t kv_pos0, py::object comm) {
+              double scale, bool causal, int64_t q_pos0, int64_t kv_pos0, py::object comm, int variant) {
   c10::cuda::CUDAGuard guard(q.device());
   AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
   TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == (int64_t)s.B * s.Hq * s.Sq,
               "lse must be contiguous fp32 (B, Hq, Sq)");
   CommCtxHost c;
   if (!comm.is_none()) c = comm.cast<Comm&>().h;
-  ta::attn_fwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
-                      at::cuda::getCurrentCUDAStream());
+  // variant 0 = auto = 1: the M=128 kernel with double-buffered S.  The M=256 ping-pong kernel (variant 2) is kept
+  // selectable; it measured slower on B200 (single-buffered S per tile exposes softmax + 2 GEMMs per step).
+  const bool use2 = variant == 2;
+  if (use2)
+    ta::attn_fwd2_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
+                         at::cuda::getCurrentCUDAStream());
+  else
+    ta::attn_fwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
+                        at::cuda::getCurrentCUDAStream());
+}
+
+// block-scaled fp8 KV cache decode: k8/v8 uint8 (B, Hkv, S, 128) e4m3, ks/vs uint8 (B, Hkv, S, 4) UE8M0
+void decode_fwd_mx(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& ks,
+                   const at::Tensor& vs, at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part,
+                   at::Tensor& tickets, py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(q.dim() == 4 && k8.dim() == 4 && v8.dim() == 4 && out.sizes() == q.sizes(), "expected (B, H, S, D) tensors");
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
+  TORCH_CHECK(out.scalar_type() == q.scalar_type() && q.stride(3) == 1 && out.stride(3) == 1);
+  TORCH_CHECK(k8.scalar_type() == at::kByte && v8.scalar_type() == at::kByte && k8.stride(3) == 1 && v8.stride(3) == 1);
+  TORCH_CHECK(k8.sizes() == v8.sizes() && k8.size(3) == 128 && q.size(3) == 128, "mxfp8 decode needs head_dim 128");
+  TORCH_CHECK(ks.scalar_type() == at::kByte && vs.scalar_type() == at::kByte && ks.is_contiguous() && vs.is_contiguous() &&
+                  ks.numel() == k8.numel() / 32 && vs.numel() == v8.numel() / 32, "scales must be contiguous uint8 (B, Hkv, S, 4)");
+  AttnShape s;
+  s.B = (int)q.size(0); s.Hq = (int)q.size(1); s.Sq = (int)q.size(2); s.D = 128;
+  s.Hkv = (int)k8.size(1); s.S = (int)k8.size(2);
+  s.is_bf16 = q.scalar_type() == at::kBFloat16;
+  s.softmax_scale = (float)scale; s.causal = causal; s.q_pos0 = q_pos0; s.kv_pos0 = kv_pos0;
+  s.q_sb = q.stride(0); s.q_sh = q.stride(1); s.q_ss = q.stride(2);
+  s.k_sb = k8.stride(0); s.k_sh = k8.stride(1); s.k_ss = k8.stride(2);
+  s.v_sb = v8.stride(0); s.v_sh = v8.stride(1); s.v_ss = v8.stride(2);
+  s.o_sb = out.stride(0); s.o_sh = out.stride(1); s.o_ss = out.stride(2);
+  int grid, mp, R;
+  size_t pf, cf, cfl;
+  ta::decode_simt_plan(s, ta::num_sms(), &grid, &mp, &R, &pf, &cf, &cfl);
+  TORCH_CHECK((size_t)part.numel() >= pf && tickets.numel() >= s.B * s.Hkv + 2, "workspace too small");
+  float* lse_p = lse.has_value() ? lse->data_ptr<float>() : nullptr;
+  CommCtxHost c;
+  if (!comm.is_none()) c = comm.cast<Comm&>().h;
+  ta::decode_simt_launch(s, q.data_ptr(), k8.data_ptr(), v8.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
+                         reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(),
+                         at::cuda::getCurrentCUDAStream(), reinterpret_cast<const uint32_t*>(ks.data_ptr()),
+                         reinterpret_cast<const uint32_t*>(vs.data_ptr()));
+}
+
+py::tuple quant_mxfp8(const at::Tensor& x) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.size(-1) % 32 == 0, "x must be contiguous with last dim % 32 == 0");
+  int dt = x.scalar_type() == at::kBFloat16 ? 0 : x.scalar_type() == at::kHalf ? 1 : 2;
+  TORCH_CHECK(dt != 2 || x.scalar_type() == at::kFloat, "x must be bf16, fp16 or fp32");
+  auto q = at::empty(x.sizes(), x.options().dtype(at::kByte));
+  auto sizes = x.sizes().vec();
+  sizes.back() /= 32;
+  auto sc = at::empty(sizes, x.options().dtype(at::kByte));
+  ta::quant_mxfp8_launch(x.data_ptr(), dt, q.data_ptr<uint8_t>(), sc.data_ptr<uint8_t>(), x.numel() / 32,
+                         at::cuda::getCurrentCUDAStream());
+  return py::make_tuple(q, sc);
+}
+
+at::Tensor dequant_mxfp8(const at::Tensor& q, const at::Tensor& sc) {
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(q.is_cuda() && q.is_contiguous() && sc.is_contiguous() && q.scalar_type() == at::kByte &&
+              sc.scalar_type() == at::kByte && sc.numel() * 32 == q.numel());
+  auto y = at::empty(q.sizes(), q.options().dtype(at::kFloat));
+  ta::dequant_mxfp8_launch(q.data_ptr<uint8_t>(), sc.data_ptr<uint8_t>(), y.data_ptr<float>(), q.numel() / 32,
+                           at::cuda::getCurrentCUDAStream());
+  return y;
 }
 
 void attn_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& o, const at::Tensor& dout,
@@ -220,6 +285,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_property_readonly("world", [](Comm& c) { return c.h.world; });
   m.def("decode_plan", &decode_plan);
   m.def("decode_fwd", &decode_fwd);
+  m.def("decode_fwd_mx", &decode_fwd_mx);
+  m.def("quant_mxfp8", &quant_mxfp8);
+  m.def("dequant_mxfp8", &dequant_mxfp8);
   m.def("attn_fwd", &attn_fwd);
   m.def("attn_fwd_comm_bytes", &attn_fwd_comm_bytes);
   m.def("attn_bwd", &attn_bwd);

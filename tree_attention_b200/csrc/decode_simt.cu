@@ -34,6 +34,8 @@ struct DecodeParams {
   const void* q;
   void* out;
   float* lse;
+  const uint32_t* kscale;  // KV8 only: (B, Hkv, S) words of 4 UE8M0 scales (one per 32 elements of D = 128)
+  const uint32_t* vscale;
   float* part;
   uint32_t* tickets;  // [BH] tickets, [BH] = done-CTA counter
   int B, Hq, Hkv, G, Sq, S;
@@ -50,19 +52,23 @@ struct DecodeParams {
   CommCtx comm;
 };
 
-template <int D>
+// KV8: block-scaled fp8 (e4m3 + UE8M0 per 32) K/V: rows are D bytes = one 128B-swizzle atom for D = 128
+template <int D, bool KV8>
 struct SmemLayout {
-  static constexpr int kAtoms = D / 64;
-  static constexpr int kTensorBytes = kTileRows * D * 2;  // one of K or V
+  static constexpr int kElem = KV8 ? 1 : 2;
+  static constexpr int kAtoms = D * kElem / 128;
+  static constexpr int kTensorBytes = kTileRows * D * kElem;  // one of K or V
   static constexpr int kStageBytes = 2 * kTensorBytes;
-  static constexpr int kStages = (D == 128) ? 3 : 6;
+  static constexpr int kStages = (D * kElem == 256) ? 3 : 6;
+  static constexpr int kPsPerWarp = KV8 ? 4 : 1;  // P x V-scale is kept per 32-wide block of D
 };
 
-template <int D, int R>
+template <int D, int R, bool KV8>
 constexpr size_t smem_bytes() {
-  return 1024 /*align slack*/ + size_t(SmemLayout<D>::kStages) * SmemLayout<D>::kStageBytes +
-         sizeof(float) * (R * D + kConsumerWarps * R * kRowsPerWarp + kConsumerWarps * R * (D + 4)) +
-         sizeof(int) * (kMaxPending + 8) + sizeof(uint64_t) * 2 * SmemLayout<D>::kStages;
+  using L = SmemLayout<D, KV8>;
+  return 1024 /*align slack*/ + size_t(L::kStages) * L::kStageBytes +
+         sizeof(float) * (R * D + kConsumerWarps * L::kPsPerWarp * R * kRowsPerWarp + kConsumerWarps * R * (D + 4)) +
+         sizeof(int) * (kMaxPending + 8) + sizeof(uint64_t) * 2 * L::kStages;
 }
 
 __device__ __forceinline__ int cta_lo(const DecodeParams& p, int c) {
@@ -96,19 +102,19 @@ __device__ __forceinline__ uint16_t to16(float f) {
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
 
-template <int D, int R, bool BF16>
+template <int D, int R, bool BF16, bool KV8>
 __global__ void __launch_bounds__(kThreads, 1)
 decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
                    const DecodeParams p) {
-  using L = SmemLayout<D>;
+  using L = SmemLayout<D, KV8>;
   constexpr int NS = L::kStages;
   constexpr int EPL = D / 32;  // output elements per lane in the PV phase
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   float* q_s = reinterpret_cast<float*>(smem + size_t(NS) * L::kStageBytes);  // [R][D], pre-scaled
-  float* p_s = q_s + R * D;                                                    // [warps][R][16]
-  float* merge_s = p_s + kConsumerWarps * R * kRowsPerWarp;                    // [warps][R][D+4]
+  float* p_s = q_s + R * D;                                                    // [warps][(blk)][R][16]
+  float* merge_s = p_s + kConsumerWarps * L::kPsPerWarp * R * kRowsPerWarp;    // [warps][R][D+4]
   int* pending = reinterpret_cast<int*>(merge_s + kConsumerWarps * R * (D + 4));
   int* s_misc = pending + kMaxPending;  // [0]=ticket, [1]=n_pending, [2]=combine ok
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_misc + 8);
@@ -164,8 +170,8 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         uint8_t* vs = ks + L::kTensorBytes;
 #pragma unroll
         for (int a = 0; a < L::kAtoms; ++a) {
-          tma_load_4d(ks + a * (kTileRows * 128), &kmap, &full_bar[stage], a * 64, j * kTileRows, h, b);
-          tma_load_4d(vs + a * (kTileRows * 128), &vmap, &full_bar[stage], a * 64, j * kTileRows, h, b);
+          tma_load_4d(ks + a * (kTileRows * 128), &kmap, &full_bar[stage], a * (128 / L::kElem), j * kTileRows, h, b);
+          tma_load_4d(vs + a * (kTileRows * 128), &vmap, &full_bar[stage], a * (128 / L::kElem), j * kTileRows, h, b);
         }
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
@@ -203,7 +209,8 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
                              (long long)(h * p.G + g) * p.q_sh + (long long)i * p.q_ss + d;
         val = cvt1<BF16>(*qp) * p.scale_log2;
       }
-      q_s[idx] = val;
+      if constexpr (KV8) reinterpret_cast<__half*>(q_s)[idx] = __float2half_rn(val);
+      else q_s[idx] = val;
     }
     named_bar_sync(1, kConsumerThreads);
   };
@@ -396,28 +403,69 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
 
     // ---------------- S = q . K^T : lane = (row r16 of this warp's 16 rows, half of D) -------------
     const int row = warp * kRowsPerWarp + r16;
-    float s_acc[R][4];
+    float s_sum[R];
+    [[maybe_unused]] uint32_t vsc_word = 0;
+    if constexpr (!KV8) {
+  float s_acc[R][4];
 #pragma unroll
-    for (int r = 0; r < R; ++r) { s_acc[r][0] = s_acc[r][1] = s_acc[r][2] = s_acc[r][3] = 0.f; }
+      for (int r = 0; r < R; ++r) { s_acc[r][0] = s_acc[r][1] = s_acc[r][2] = s_acc[r][3] = 0.f; }
 #pragma unroll
-    for (int c = 0; c < D / 16; ++c) {
-      const int cg = half * (D / 16) + c;
-      const int atom = cg >> 3, cia = cg & 7;
-      const uint4 kw = *reinterpret_cast<const uint4*>(ks + atom * (kTileRows * 128) + row * 128 + ((cia ^ (row & 7)) << 4));
-      float kf[8];
-      cvt8<BF16>(kw, kf);
+      for (int c = 0; c < D / 16; ++c) {
+        const int cg = half * (D / 16) + c;
+        const int atom = cg >> 3, cia = cg & 7;
+        const uint4 kw = *reinterpret_cast<const uint4*>(ks + atom * (kTileRows * 128) + row * 128 + ((cia ^ (row & 7)) << 4));
+        float kf[8];
+        cvt8<BF16>(kw, kf);
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float4 qa = *reinterpret_cast<const float4*>(q_s + r * D + cg * 8);
-        const float4 qb = *reinterpret_cast<const float4*>(q_s + r * D + cg * 8 + 4);
-        s_acc[r][0] = fmaf(kf[0], qa.x, s_acc[r][0]);
-        s_acc[r][1] = fmaf(kf[1], qa.y, s_acc[r][1]);
-        s_acc[r][2] = fmaf(kf[2], qa.z, s_acc[r][2]);
-        s_acc[r][3] = fmaf(kf[3], qa.w, s_acc[r][3]);
-        s_acc[r][0] = fmaf(kf[4], qb.x, s_acc[r][0]);
-        s_acc[r][1] = fmaf(kf[5], qb.y, s_acc[r][1]);
-        s_acc[r][2] = fmaf(kf[6], qb.z, s_acc[r][2]);
-        s_acc[r][3] = fmaf(kf[7], qb.w, s_acc[r][3]);
+        for (int r = 0; r < R; ++r) {
+          const float4 qa = *reinterpret_cast<const float4*>(q_s + r * D + cg * 8);
+          const float4 qb = *reinterpret_cast<const float4*>(q_s + r * D + cg * 8 + 4);
+          s_acc[r][0] = fmaf(kf[0], qa.x, s_acc[r][0]);
+          s_acc[r][1] = fmaf(kf[1], qa.y, s_acc[r][1]);
+          s_acc[r][2] = fmaf(kf[2], qa.z, s_acc[r][2]);
+          s_acc[r][3] = fmaf(kf[3], qa.w, s_acc[r][3]);
+          s_acc[r][0] = fmaf(kf[4], qb.x, s_acc[r][0]);
+          s_acc[r][1] = fmaf(kf[5], qb.y, s_acc[r][1]);
+          s_acc[r][2] = fmaf(kf[6], qb.z, s_acc[r][2]);
+          s_acc[r][3] = fmaf(kf[7], qb.w, s_acc[r][3]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) s_sum[r] = (s_acc[r][0] + s_acc[r][1]) + (s_acc[r][2] + s_acc[r][3]);
+    } else {
+      // block-scaled fp8: this lane covers 64 elements = 4 chunks of 16 = blocks {2*half, 2*half+1}; products are
+      // accumulated per chunk in fp16x2 (8 HFMA2), then scaled by the block's UE8M0 scale in fp32.
+      const long long srow = ((long long)(cur_x)*p.S) + min((long long)j * kTileRows + row, (long long)p.S - 1);
+      const uint32_t ksc_word = __ldg(p.kscale + srow);
+      vsc_word = __ldg(p.vscale + srow);
+#pragma unroll
+      for (int r = 0; r < R; ++r) s_sum[r] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int cg = half * 4 + c;
+        const uint4 kw = *reinterpret_cast<const uint4*>(ks + row * 128 + ((cg ^ (row & 7)) << 4));
+        uint32_t kh[8];
+        const uint32_t kw4[4] = {kw.x, kw.y, kw.z, kw.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(kh[2 * i]) : "h"((uint16_t)(kw4[i] & 0xffffu)));
+          asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(kh[2 * i + 1]) : "h"((uint16_t)(kw4[i] >> 16)));
+        }
+        const float ksc = __uint_as_float(((ksc_word >> (8 * (cg >> 1))) & 0xffu) << 23);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const uint4 qa = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(q_s) + r * D + cg * 16);
+          const uint4 qb = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(q_s) + r * D + cg * 16 + 8);
+          const uint32_t qh[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+          __half2 a0 = __float2half2_rn(0.f), a1 = a0;
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            a0 = __hfma2(*reinterpret_cast<const __half2*>(&kh[i]), *reinterpret_cast<const __half2*>(&qh[i]), a0);
+            a1 = __hfma2(*reinterpret_cast<const __half2*>(&kh[i + 1]), *reinterpret_cast<const __half2*>(&qh[i + 1]), a1);
+          }
+          const float2 f0 = __half22float2(a0), f1 = __half22float2(a1);
+          s_sum[r] = fmaf((f0.x + f0.y) + (f1.x + f1.y), ksc, s_sum[r]);
+        }
       }
     }
     const long long grow = (long long)j * kTileRows + row;
@@ -426,7 +474,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     float alpha[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      float s = (s_acc[r][0] + s_acc[r][1]) + (s_acc[r][2] + s_acc[r][3]);
+      float s = s_sum[r];
       s += __shfl_xor_sync(0xffffffffu, s, 16);
       const int i = (p.r_base + r) % p.Sq;
       const bool vis = inb && (!p.causal || kvpos <= p.q_pos0 + i);
@@ -442,13 +490,50 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       const float pv = fast_exp2(s - m_safe);
       l_run[r] = fmaf(l_run[r], alpha[r], pv);
       m_run[r] = m_new;
-      if (half == 0) p_s[(warp * R + r) * kRowsPerWarp + r16] = pv;
+      if constexpr (!KV8) {
+        if (half == 0) p_s[(warp * R + r) * kRowsPerWarp + r16] = pv;
+      } else {
+        // P x (V block scale), one copy per 32-wide block of D; this lane owns blocks 2*half and 2*half+1
+        const int b0 = 2 * half;
+        p_s[((warp * 4 + b0) * R + r) * kRowsPerWarp + r16] = pv * __uint_as_float(((vsc_word >> (8 * b0)) & 0xffu) << 23);
+        p_s[((warp * 4 + b0 + 1) * R + r) * kRowsPerWarp + r16] = pv * __uint_as_float(((vsc_word >> (8 * b0 + 8)) & 0xffu) << 23);
+      }
 #pragma unroll
       for (int e = 0; e < EPL; ++e) o_acc[r][e] *= alpha[r];
     }
     __syncwarp();
 
     // ---------------- O += P . V : lane = EPL consecutive output columns ---------------------------
+    if constexpr (KV8) {
+      // fp8: 4 output columns = 4 bytes; the P x scale coefficients of this lane's block come from smem
+      const int blk = lane >> 3;
+      const int chunk = lane >> 2, off = (lane & 3) * 4;
+#pragma unroll
+      for (int jj = 0; jj < kRowsPerWarp; jj += 4) {
+        float4 pr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          pr[r] = *reinterpret_cast<const float4*>(p_s + ((warp * 4 + blk) * R + r) * kRowsPerWarp + jj);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int vrow = warp * kRowsPerWarp + jj + u;
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(vs + vrow * 128 + ((chunk ^ (vrow & 7)) << 4) + off);
+          uint32_t h0, h1;
+          asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h0) : "h"((uint16_t)(w & 0xffffu)));
+          asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h1) : "h"((uint16_t)(w >> 16)));
+          const float2 v01 = __half22float2(*reinterpret_cast<const __half2*>(&h0));
+          const float2 v23 = __half22float2(*reinterpret_cast<const __half2*>(&h1));
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float pp = (u == 0) ? pr[r].x : (u == 1) ? pr[r].y : (u == 2) ? pr[r].z : pr[r].w;
+            o_acc[r][0] = fmaf(pp, v01.x, o_acc[r][0]);
+            o_acc[r][1] = fmaf(pp, v01.y, o_acc[r][1]);
+            o_acc[r][2] = fmaf(pp, v23.x, o_acc[r][2]);
+            o_acc[r][3] = fmaf(pp, v23.y, o_acc[r][3]);
+          }
+        }
+      }
+    } else
     {
       const int c0 = lane * EPL;                 // first element of this lane
       const int atom = (c0 * 2) >> 7;            // 64 elements (128 B) per atom
@@ -523,11 +608,11 @@ inline CommCtx to_device_ctx(const CommCtxHost& h) {
   return c;
 }
 
-template <int D, int R, bool BF16>
+template <int D, int R, bool BF16, bool KV8>
 void launch_one(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeParams& p, int grid,
                 cudaStream_t stream) {
-  auto kern = decode_simt_kernel<D, R, BF16>;
-  constexpr size_t smem = smem_bytes<D, R>();
+  auto kern = decode_simt_kernel<D, R, BF16, KV8>;
+  constexpr size_t smem = smem_bytes<D, R, KV8>();
   static bool configured = false;
   if (!configured) {
     TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -560,8 +645,11 @@ void decode_simt_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, in
 }
 
 void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                        float* part, uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream) {
+                        float* part, uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream,
+                        const uint32_t* kscale, const uint32_t* vscale) {
+  const bool kv8 = kscale != nullptr;
   if (s.D != 64 && s.D != 128) throw std::runtime_error("decode_simt: head_dim must be 64 or 128");
+  if (kv8 && s.D != 128) throw std::runtime_error("decode_simt(mxfp8): head_dim must be 128");
   if (s.Hq % s.Hkv != 0) throw std::runtime_error("decode_simt: Hq must be a multiple of Hkv");
   if (s.S <= 0) throw std::runtime_error("decode_simt: empty KV shard");
   int grid, max_parts, R;
@@ -574,11 +662,13 @@ void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const 
     if (need_data > comm.data_bytes)
       throw std::runtime_error("decode_simt: symmetric buffer too small for this problem");
   }
-  CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, s.D, s.k_sb, s.k_sh, s.k_ss, 64, kTileRows,
+  const int eb = kv8 ? 1 : 2;
+  CUtensorMap kmap = make_tmap_bhsd(k, eb, s.B, s.Hkv, s.S, s.D, s.k_sb, s.k_sh, s.k_ss, 128 / eb, kTileRows,
                                     CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap vmap = make_tmap_bhsd(v, 2, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 64, kTileRows,
+  CUtensorMap vmap = make_tmap_bhsd(v, eb, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 128 / eb, kTileRows,
                                     CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeParams p;
+  p.kscale = kscale; p.vscale = vscale;
   p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S;
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
@@ -594,14 +684,20 @@ void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const 
     p.r_base = r_base;
     p.rows_valid = std::min(R, total_rows - r_base);
 #define TA_LAUNCH(DD, RR)                                                              \
-  if (s.is_bf16) launch_one<DD, RR, true>(kmap, vmap, p, grid, stream);                \
-  else launch_one<DD, RR, false>(kmap, vmap, p, grid, stream);
-    if (s.D == 128) {
+  if (s.is_bf16) launch_one<DD, RR, true, false>(kmap, vmap, p, grid, stream);         \
+  else launch_one<DD, RR, false, false>(kmap, vmap, p, grid, stream);
+#define TA_LAUNCH8(RR)                                                                 \
+  if (s.is_bf16) launch_one<128, RR, true, true>(kmap, vmap, p, grid, stream);         \
+  else launch_one<128, RR, false, true>(kmap, vmap, p, grid, stream);
+    if (kv8) {
+      if (R == 4) { TA_LAUNCH8(4) } else if (R == 2) { TA_LAUNCH8(2) } else { TA_LAUNCH8(1) }
+    } else if (s.D == 128) {
       if (R == 4) { TA_LAUNCH(128, 4) } else if (R == 2) { TA_LAUNCH(128, 2) } else { TA_LAUNCH(128, 1) }
     } else {
       if (R == 4) { TA_LAUNCH(64, 4) } else if (R == 2) { TA_LAUNCH(64, 2) } else { TA_LAUNCH(64, 1) }
     }
 #undef TA_LAUNCH
+#undef TA_LAUNCH8
   }
 }
 

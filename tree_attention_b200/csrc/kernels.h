@@ -42,7 +42,9 @@ void decode_simt_plan(const AttnShape& s, int num_sms, int* grid, int* max_parts
 // part: float workspace, tickets: uint32 [B*Hkv + 2] zero-initialised once.
 void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                         float* part, uint32_t* tickets, const CommCtxHost& comm, int num_sms,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const uint32_t* kscale = nullptr, const uint32_t* vscale = nullptr);
+// kscale/vscale != null: K/V are block-scaled fp8 (e4m3 bytes, D = 128) and the scales are (B, Hkv, S) words of
+// four UE8M0 exponents (one per 32 elements); strides in AttnShape are then in BYTES == elements.
 
 // ---- stand-alone combine of W per-rank partials (o fp32 normalised, lse natural log) ----
 // local: o_part (rows, D) fp32 + lse_part (rows); result written to out (dtype of `is_bf16`/fp16/fp32)
@@ -63,6 +65,9 @@ void umma_probe_launch(const void* a, const void* b, float* c, int N, int K, int
 void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                      const CommCtxHost& comm, cudaStream_t stream);
 size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
+// two ping-ponged query tiles per CTA (M = 256); same contract and symmetric-buffer layout
+void attn_fwd2_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                      const CommCtxHost& comm, cudaStream_t stream);
 
 // ---- tcgen05 flash-attention backward over one KV shard with the GLOBAL o / lse ----
 // dq: fp32 (B, Hq, Sq, D) contiguous (this shard's partial); dk, dv: (B, Hkv, S, D) contiguous, I/O dtype;
@@ -70,5 +75,10 @@ size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
 void attn_bwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, const void* o, const void* dout,
                      const float* lse, float* dq, void* dk, void* dv, float* delta, float* lse2, int64_t do_sb,
                      int64_t do_sh, int64_t do_ss, cudaStream_t stream);
+
+// ---- block-scaled fp8 (MX): e4m3 + one UE8M0 scale per 32 elements of the innermost dimension ----
+void quant_mxfp8_launch(const void* x, int in_dtype /*0 bf16, 1 fp16, 2 fp32*/, uint8_t* q, uint8_t* scales,
+                        int64_t nblocks, cudaStream_t stream);
+void dequant_mxfp8_launch(const uint8_t* q, const uint8_t* scales, float* y, int64_t nblocks, cudaStream_t stream);
 
 }  // namespace ta

@@ -1,0 +1,82 @@
+// quant_mxfp8 -- OCP-MX style block-scaled fp8: e4m3 elements with one UE8M0 (power-of-two) scale per 32
+// consecutive elements of the innermost (head) dimension.  Used for the block-scaled-fp8 KV cache
+// (BASELINE.json config "256K, block-scaled fp8 forward").  The scale is the smallest power of two that maps
+// the block's amax into the e4m3 range (|x| <= 448), so quantisation never saturates.
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace ta {
+namespace {
+
+template <int IN>  // 0 = bf16, 1 = fp16, 2 = fp32
+__device__ __forceinline__ float load_in(const void* p, long long i) {
+  if constexpr (IN == 0) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+  else if constexpr (IN == 1) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  else return reinterpret_cast<const float*>(p)[i];
+}
+
+template <int IN>
+__global__ void quant_mxfp8_kernel(const void* __restrict__ x, uint8_t* __restrict__ q, uint8_t* __restrict__ sc,
+                                   long long nblocks) {
+  const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= nblocks) return;
+  float v[32];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { v[i] = load_in<IN>(x, blk * 32 + i); amax = fmaxf(amax, fabsf(v[i])); }
+  int e = 0;
+  if (amax > 0.f && isfinite(amax)) {
+    int ex;
+    const float m = frexpf(amax / 448.f, &ex);
+    e = (m == 0.5f) ? ex - 1 : ex;  // ceil(log2(amax / 448))
+    e = max(-127, min(127, e));
+  }
+  const float inv = exp2f((float)-e);
+  sc[blk] = (uint8_t)(e + 127);
+  uint32_t out[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(v[4 * i + 1] * inv), "f"(v[4 * i + 0] * inv));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(v[4 * i + 3] * inv), "f"(v[4 * i + 2] * inv));
+    out[i] = uint32_t(lo) | (uint32_t(hi) << 16);
+  }
+  uint4* qp = reinterpret_cast<uint4*>(q + blk * 32);
+  qp[0] = make_uint4(out[0], out[1], out[2], out[3]);
+  qp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+}
+
+__global__ void dequant_mxfp8_kernel(const uint8_t* __restrict__ q, const uint8_t* __restrict__ sc, float* __restrict__ y,
+                                     long long nblocks) {
+  const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (blk >= nblocks) return;
+  const float s = exp2f((float)((int)sc[blk] - 127));
+  const uint16_t* qp = reinterpret_cast<const uint16_t*>(q + blk * 32);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    uint32_t h2;
+    asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(qp[i]));
+    y[blk * 32 + 2 * i] = f16lo(h2) * s;
+    y[blk * 32 + 2 * i + 1] = f16hi(h2) * s;
+  }
+}
+
+}  // namespace
+
+void quant_mxfp8_launch(const void* x, int in_dtype, uint8_t* q, uint8_t* scales, int64_t nblocks, cudaStream_t stream) {
+  const int threads = 128;
+  const unsigned grid = (unsigned)((nblocks + threads - 1) / threads);
+  if (in_dtype == 0) quant_mxfp8_kernel<0><<<grid, threads, 0, stream>>>(x, q, scales, nblocks);
+  else if (in_dtype == 1) quant_mxfp8_kernel<1><<<grid, threads, 0, stream>>>(x, q, scales, nblocks);
+  else quant_mxfp8_kernel<2><<<grid, threads, 0, stream>>>(x, q, scales, nblocks);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
+
+void dequant_mxfp8_launch(const uint8_t* q, const uint8_t* scales, float* y, int64_t nblocks, cudaStream_t stream) {
+  const int threads = 128;
+  dequant_mxfp8_kernel<<<(unsigned)((nblocks + threads - 1) / threads), threads, 0, stream>>>(q, scales, y, nblocks);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace ta

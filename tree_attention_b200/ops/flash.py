@@ -6,6 +6,7 @@ the cross-GPU combine over symmetric memory without NCCL.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -40,6 +41,7 @@ def attention_fwd(
     kv_pos0: int = 0,
     out: Optional[torch.Tensor] = None,
     comm=None,
+    variant: int = 0,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Shard-local partial ``(o, lse)``; with ``comm`` (a ``_C.Comm`` of the ``fwd`` family) the SAME launch
     also performs the cross-GPU combine and ``(o, lse)`` are the global, replicated results."""
@@ -51,7 +53,8 @@ def attention_fwd(
     if out is None:
         out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
     lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
-    C.attn_fwd(q, k, v, out, lse, float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0), comm)
+    C.attn_fwd(q, k, v, out, lse, float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0), comm,
+               int(os.environ.get("TREE_ATTN_FWD_VARIANT", variant)))
     return out, lse
 
 

@@ -81,6 +81,31 @@ def decode_attention(
     return out, lse
 
 
+def decode_attention_mxfp8(
+    q: torch.Tensor,
+    k,
+    v,
+    softmax_scale: float,
+    causal: bool = False,
+    q_pos0: int = 0,
+    kv_pos0: int = 0,
+    comm=None,
+    return_lse: bool = True,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Streaming decode over a block-scaled fp8 KV shard (``k``, ``v``: ``ops.quant.MXFP8Tensor``)."""
+    C = _build.load()
+    q = _as_bhsd(q)
+    b, hq, sq, d = q.shape
+    hkv, s = k.shape[1], k.shape[2]
+    grid, max_parts, rows, part_floats, _, _ = C.decode_plan(b, hq, hkv, sq, s, d)
+    ws = _workspace(q.device, "decode", part_floats, b * hkv + 2)
+    out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
+    lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device) if return_lse else None
+    C.decode_fwd_mx(q, k.data, v.data, k.scales, v.scales, out, lse, ws["part"], ws["tickets"], comm,
+                    float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0))
+    return out, lse
+
+
 def decode_comm_bytes(b: int, hq: int, hkv: int, sq: int, s: int, d: int, world: int) -> Tuple[int, int]:
     """(data_bytes, flag_bytes) the decode family needs in symmetric memory."""
     rows = min(4, max(1, (hq // hkv) * sq))

@@ -1,0 +1,71 @@
+"""Block-scaled fp8 (OCP MX style): e4m3 elements + one UE8M0 power-of-two scale per 32 elements of the
+innermost dimension.  ``csrc/quant.cu`` holds the CUDA kernels; the PyTorch implementation below is the
+oracle and the CPU path.  Used for the mxfp8 KV cache of the streaming decode kernel (half the HBM bytes of
+bf16: decode is bandwidth bound, so this is up to 2x on the headline op)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Tuple
+
+import torch
+
+from .. import _build
+
+BLOCK = 32
+E4M3_MAX = 448.0
+
+
+def quantize_mxfp8_ref(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """PyTorch oracle: returns (uint8 e4m3 bytes, uint8 UE8M0 scales)."""
+    assert x.shape[-1] % BLOCK == 0
+    xf = x.float().reshape(*x.shape[:-1], x.shape[-1] // BLOCK, BLOCK)
+    amax = xf.abs().amax(dim=-1)
+    e = torch.ceil(torch.log2(torch.clamp(amax, min=1e-38) / E4M3_MAX))
+    e = torch.where(amax > 0, e, torch.zeros_like(e)).clamp(-127, 127)
+    q = (xf * torch.exp2(-e)[..., None]).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+    return q.view(torch.uint8).reshape(x.shape), (e + 127).to(torch.uint8)
+
+
+def dequantize_mxfp8_ref(q: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
+    qf = q.view(torch.float8_e4m3fn).float().reshape(*q.shape[:-1], q.shape[-1] // BLOCK, BLOCK)
+    s = torch.exp2(scales.float() - 127.0)
+    return (qf * s[..., None]).reshape(q.shape)
+
+
+def quantize_mxfp8(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    if x.is_cuda:
+        return tuple(_build.load().quant_mxfp8(x.contiguous()))
+    return quantize_mxfp8_ref(x)
+
+
+def dequantize_mxfp8(q: torch.Tensor, scales: torch.Tensor) -> torch.Tensor:
+    if q.is_cuda:
+        return _build.load().dequant_mxfp8(q.contiguous(), scales.contiguous())
+    return dequantize_mxfp8_ref(q, scales)
+
+
+@dataclass
+class MXFP8Tensor:
+    """A block-scaled fp8 tensor: ``data`` uint8 (..., D) e4m3 bytes, ``scales`` uint8 (..., D/32) UE8M0."""
+
+    data: torch.Tensor
+    scales: torch.Tensor
+
+    @classmethod
+    def from_float(cls, x: torch.Tensor) -> "MXFP8Tensor":
+        return cls(*quantize_mxfp8(x))
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def is_cuda(self):
+        return self.data.is_cuda
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def dequantize(self, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        return dequantize_mxfp8(self.data, self.scales).to(dtype)

@@ -185,6 +185,11 @@ def tree_attention(
     rank, world = _world(group)
     scale = ref.default_scale(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
     s_local = k.shape[2]
+    from ..ops.quant import MXFP8Tensor
+
+    if isinstance(k, MXFP8Tensor):  # block-scaled fp8 KV cache
+        return _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset, q_offset, return_lse,
+                                     backend, schedule)
     kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
     q_pos0 = (world * s_local - q.shape[2]) if q_offset is None else int(q_offset)
     be = _resolve_backend(backend, q, world)
@@ -215,6 +220,28 @@ def tree_attention(
     if layout == "bshd":
         o = o.transpose(1, 2)
     return (o, lse) if return_lse else o
+
+
+def _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset, q_offset, return_lse, backend,
+                          schedule):
+    """mxfp8 KV: fused streaming decode when eligible (CUDA, head_dim 128, few query rows); otherwise dequantise."""
+    s_local = k.shape[2]
+    kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
+    q_pos0 = (world * s_local - q.shape[2]) if q_offset is None else int(q_offset)
+    g = q.shape[1] // k.shape[1]
+    if (q.is_cuda and q.shape[-1] == 128 and q.shape[2] * g <= local_ops.DECODE_MAX_ROWS
+            and backend in ("auto", "fused", "local")):
+        comm = None
+        if world > 1:
+            b, hq, sq, d = q.shape
+            data, flags = local_ops.decode_comm_bytes(b, hq, k.shape[1], sq, s_local, d, world)
+            comm = symm.get_region("decode", data, flags, group).comm
+        o, lse = local_ops.decode_attention_mxfp8(q, k, v, scale, causal, q_pos0, kv_pos0, comm=comm,
+                                                  return_lse=return_lse)
+        return (o, lse) if return_lse else o
+    dt = q.dtype if q.is_cuda else torch.float32
+    return tree_attention(q, k.dequantize(dt), v.dequantize(dt), group=group, causal=causal, softmax_scale=scale,
+                          kv_offset=kv_pos0, q_offset=q_pos0, return_lse=return_lse, backend=backend, schedule=schedule)
 
 
 def tree_decode(
