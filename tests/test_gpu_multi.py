@@ -186,3 +186,56 @@ def _worker_fault(rank, world):
 @need2
 def test_failure_detection_bounded_spin(port):
     run_distributed(_worker_fault, 2, port)
+
+
+def _worker_reduce_and_bwd(rank, world):
+    """Symmetric-memory all-reduce (the backward's dQ tree reduce) and the distributed fwd+bwd."""
+    import torch.distributed as dist
+    import tree_attention_b200 as ta
+    from tree_attention_b200.ops import reference as ref
+    from tree_attention_b200.ops.autograd import tree_attention_func
+    from tree_attention_b200.parallel.tree import allreduce_sum
+
+    dev = torch.device("cuda", rank)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    for n in (4096, 4 * 1000, 3 * 4096 + 512, 1 << 22):
+        x = torch.randn(n, device=dev, generator=g)
+        y = allreduce_sum(x)
+        exp = x.clone()
+        dist.all_reduce(exp)
+        assert torch.allclose(y, exp, atol=1e-4), n
+        ys = [torch.empty_like(y) for _ in range(world)]
+        dist.all_gather(ys, y)
+        for t in ys:
+            assert torch.equal(t, ys[0]), "all-reduce result differs across ranks"
+    for _ in range(20):  # epoch / parity reuse
+        y = allreduce_sum(x)
+    assert torch.allclose(y, exp, atol=1e-4)
+
+    # distributed forward + backward: dK/dV local, dQ summed over ranks by the symmetric-memory kernel
+    b, hq, hkv, sq, s_local, d = 1, 8, 4, 256, 384, 128
+    q, k, v = ta.make_data((b, hq, s_local, d), rank, dev, dtype=torch.bfloat16, sq=sq, num_kv_heads=hkv, log=False)
+    do = torch.randn(b, hq, sq, d, device=dev, generator=torch.Generator(device=dev).manual_seed(7)).bfloat16()
+    ks = [torch.empty_like(k) for _ in range(world)]
+    vs = [torch.empty_like(v) for _ in range(world)]
+    dist.all_gather(ks, k)
+    dist.all_gather(vs, v)
+    qf = q.float().requires_grad_(True)
+    kf = torch.cat(ks, 2).float().requires_grad_(True)
+    vf = torch.cat(vs, 2).float().requires_grad_(True)
+    o_ref, _ = ref.attention_partial_ref(qf, kf, vf, None, True, world * s_local - sq, 0)
+    o_ref.backward(do.float())
+    ql, kl, vl = (t.clone().requires_grad_(True) for t in (q, k, v))
+    o = tree_attention_func(ql, kl, vl, causal=True)
+    o.backward(do)
+    torch.cuda.synchronize()
+    assert (o.float() - o_ref).abs().max().item() < 3e-2
+    sl = slice(rank * s_local, (rank + 1) * s_local)
+    for name, got, exp in (("dq", ql.grad, qf.grad), ("dk", kl.grad, kf.grad[:, :, sl]), ("dv", vl.grad, vf.grad[:, :, sl])):
+        err = (got.float() - exp).abs().max().item() / (exp.abs().max().item() + 1e-6)
+        assert err < 4e-2, (name, err)
+
+
+@need2
+def test_symm_allreduce_and_distributed_backward(port):
+    run_distributed(_worker_reduce_and_bwd, min(NGPU, 4) if NGPU >= 4 else 2, port)

@@ -24,7 +24,7 @@ SO_PATH = BUILD_DIR / "_C.so"
 HASH_PATH = BUILD_DIR / "_C.hash"
 
 CUDA_SOURCES = ["decode_simt.cu", "combine.cu", "umma_probe.cu", "attn_fwd_sm100.cu", "attn_fwd2_sm100.cu", "attn_bwd_sm100.cu",
-                "quant.cu"]
+                "quant.cu", "reduce.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

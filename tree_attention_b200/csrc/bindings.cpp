@@ -214,6 +214,19 @@ at::Tensor dequant_mxfp8(const at::Tensor& q, const at::Tensor& sc) {
   return y;
 }
 
+py::tuple symm_allreduce_sizes(int64_t n, int world) {
+  size_t db, fb;
+  ta::symm_allreduce_sizes(n, world, &db, &fb);
+  return py::make_tuple((int64_t)db, (int64_t)fb);
+}
+
+void symm_allreduce(const at::Tensor& x, at::Tensor& y, Comm& comm) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.scalar_type() == at::kFloat && y.scalar_type() == at::kFloat && x.is_contiguous() && y.is_contiguous() &&
+              x.numel() == y.numel() && x.numel() % 4 == 0, "symm_allreduce: contiguous fp32 tensors, numel % 4 == 0");
+  ta::symm_allreduce_launch(x.data_ptr<float>(), y.data_ptr<float>(), x.numel(), comm.h, at::cuda::getCurrentCUDAStream());
+}
+
 void attn_bwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& o, const at::Tensor& dout,
               const at::Tensor& lse, at::Tensor& dq, at::Tensor& dk, at::Tensor& dv, at::Tensor& delta, at::Tensor& lse2,
               double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
@@ -291,6 +304,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attn_fwd", &attn_fwd);
   m.def("attn_fwd_comm_bytes", &attn_fwd_comm_bytes);
   m.def("attn_bwd", &attn_bwd);
+  m.def("symm_allreduce", &symm_allreduce);
+  m.def("symm_allreduce_sizes", &symm_allreduce_sizes);
   m.def("combine", &combine);
   m.def("umma_probe", &umma_probe);
   m.def("num_sms", []() { return ta::num_sms(); });

@@ -76,6 +76,10 @@ void attn_bwd_launch(const AttnShape& s, const void* q, const void* k, const voi
                      const float* lse, float* dq, void* dk, void* dv, float* delta, float* lse2, int64_t do_sb,
                      int64_t do_sh, int64_t do_ss, cudaStream_t stream);
 
+// ---- fp32 all-reduce (sum) over symmetric memory: the backward's dQ reduce (reduce.cu) ----
+void symm_allreduce_sizes(int64_t n, int world, size_t* data_bytes, size_t* flag_bytes);
+void symm_allreduce_launch(const float* x, float* y, int64_t n, const CommCtxHost& comm, cudaStream_t stream);
+
 // ---- block-scaled fp8 (MX): e4m3 + one UE8M0 scale per 32 elements of the innermost dimension ----
 void quant_mxfp8_launch(const void* x, int in_dtype /*0 bf16, 1 fp16, 2 fp32*/, uint8_t* q, uint8_t* scales,
                         int64_t nblocks, cudaStream_t stream);

@@ -62,7 +62,9 @@ class _TreeAttentionFn(torch.autograd.Function):
         dq, dk, dv = _local_bwd(q, k, v, o, lse, do.contiguous(), scale, causal, q_pos0, kv_pos0)
         dq = dq.float().contiguous()
         if world > 1:
-            dist.all_reduce(dq, op=dist.ReduceOp.SUM, group=group)
+            from ..parallel.tree import allreduce_sum
+
+            dq = allreduce_sum(dq, group)  # symmetric-memory kernel on CUDA, all_reduce on CPU
         return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None, None, None, None, None
 
 

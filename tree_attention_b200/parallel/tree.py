@@ -29,6 +29,17 @@ from ..ops import reference as ref
 from . import symm
 from .runtime import get_runtime
 
+import contextlib
+import os as _os
+
+
+def _nvtx(name: str):
+    """NVTX range around the op when TREE_ATTN_NVTX=1 (profilers only; nothing is logged in the hot path)."""
+    if _os.environ.get("TREE_ATTN_NVTX") and torch.cuda.is_available():
+        return torch.cuda.nvtx.range(name)
+    return contextlib.nullcontext()
+
+
 _BACKENDS = ("auto", "fused", "symm", "nccl", "gloo", "collective", "local")
 _SCHEDULES = ("oneshot", "butterfly", "allreduce3", "allgather")
 
@@ -148,6 +159,36 @@ def combine_partials(
     return out.to(out_dtype), lse_g
 
 
+def allreduce_sum(x: torch.Tensor, group=None, backend: str = "auto") -> torch.Tensor:
+    """Sum ``x`` (fp32) over the ranks of ``group``.  On CUDA this is ONE hand-written kernel over symmetric
+    memory (pull reduce-scatter + push all-gather, ``csrc/reduce.cu``) -- the backward's dQ tree reduce; the
+    collective path (NCCL / gloo ``all_reduce``) is the baseline and the CPU path.  Returns a new tensor."""
+    rank, world = _world(group)
+    if world == 1:
+        return x
+    if x.is_cuda and backend in ("auto", "symm", "fused") and x.dtype == torch.float32 and x.numel() % 4 == 0:
+        import os
+
+        from .. import _build
+
+        C = _build.load()
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        flat_x, flat_y = xc.view(-1), y.view(-1)
+        cap = int(float(os.environ.get("TREE_ATTN_REDUCE_SYMM_CAP_GB", "4")) * (1 << 30))
+        chunk = max(4096, (cap // 16) // 4096 * 4096)  # floats per launch: 16 B of symmetric memory per float
+        n = flat_x.numel()
+        data, flags = C.symm_allreduce_sizes(min(n, chunk), world)
+        reg = symm.get_region("reduce", int(data), int(flags), group)
+        for s0 in range(0, n, chunk):
+            s1 = min(n, s0 + chunk)
+            C.symm_allreduce(flat_x[s0:s1], flat_y[s0:s1], reg.comm)
+        return y
+    y = x.clone()
+    dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
+    return y
+
+
 # ------------------------------------------------------------------------------------------------
 # public API
 # ------------------------------------------------------------------------------------------------
@@ -195,7 +236,8 @@ def tree_attention(
     be = _resolve_backend(backend, q, world)
 
     if be == "local":
-        o, lse = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0)
+        with _nvtx("tree_attention/local"):
+            o, lse = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0)
     elif be == "fused":
         if not q.is_cuda:
             raise RuntimeError("backend='fused' needs CUDA tensors")
@@ -211,12 +253,14 @@ def tree_attention(
             o, lse = flash.attention_fwd_fused(q, k, v, scale, causal, q_pos0, kv_pos0, group=group,
                                                return_lse=return_lse)
     else:  # symm | collective
-        o_p, lse_p = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0)
+        with _nvtx("tree_attention/local_partial"):
+            o_p, lse_p = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0)
         sched = schedule
         if be == "collective" and schedule == "oneshot":
             sched = "allgather"
-        o, lse = combine_partials(o_p, lse_p, group, "symm" if be == "symm" else "collective", sched,
-                                  out_dtype=o_p.dtype)
+        with _nvtx(f"tree_attention/combine[{be}:{sched}]"):
+            o, lse = combine_partials(o_p, lse_p, group, "symm" if be == "symm" else "collective", sched,
+                                      out_dtype=o_p.dtype)
     if layout == "bshd":
         o = o.transpose(1, 2)
     return (o, lse) if return_lse else o
