@@ -399,6 +399,16 @@ def run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier):
             out["own_kernel_plus_nccl_allreduce3_ms_per_step"] = timeit(
                 lambda i: ta.tree_attention(q, kvs[i % nb][0], kvs[i % nb][1], softmax_scale=scale, backend="nccl",
                                             schedule="allreduce3"))
+        # block-scaled fp8 (MX) KV cache: same decode step on e4m3 + UE8M0 KV (BASELINE.json fp8 config)
+        from tree_attention_b200.ops.quant import MXFP8Tensor
+
+        kq, vq = MXFP8Tensor.from_float(kvs[0][0]), MXFP8Tensor.from_float(kvs[0][1])
+        o8 = ta.tree_attention(q, kq, vq, softmax_scale=scale, backend=args.backend)
+        o16 = ta.tree_attention(q, kvs[0][0], kvs[0][1], softmax_scale=scale, backend=args.backend)
+        out["mxfp8_kv_max_abs_diff_vs_bf16"] = float((o8.float() - o16.float()).abs().max())
+        out["mxfp8_kv_eager_ms_per_step"] = timeit(
+            lambda i: ta.tree_attention(q, kq, vq, softmax_scale=scale, backend=args.backend), steps=200)
+        del kq, vq
         if world > 1:
             from tree_attention_b200.parallel import symm
 

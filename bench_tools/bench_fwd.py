@@ -10,6 +10,29 @@ import torch
 from tree_attention_b200.ops import flash
 from tree_attention_b200.utils.timing import time_cuda
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import time
+
+
+def timed_with_clocks(fn, steps, warmup):
+    """time_cuda plus SM clock / throttle sampling while a >= 1.5 s loop of the same call runs."""
+    from bench import ClockSampler
+
+    t = time_cuda(fn, steps, warmup)
+    smp = ClockSampler(torch.cuda.current_device(), period_ms=50)
+    time.sleep(0.2)
+    t0 = time.time()
+    n = max(steps, int(1500.0 / max(t["median_ms"], 1e-3)))
+    for _ in range(n):
+        fn()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    smp.stop()
+    c = smp.summary(t0 + 0.3, t1)
+    t["sustained_ms"] = (t1 - t0) * 1e3 / n
+    t["clocks"] = c
+    return t
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -35,10 +58,14 @@ def main():
             flops = 4.0 * s * s * a.dim * a.heads * (0.5 if causal else 1.0)
             scale = a.dim ** -0.5
             res = {}
-            t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0), a.steps, a.warmup)
+            t = timed_with_clocks(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0), a.steps, a.warmup)
             res["tcgen05_own"] = t["median_ms"]
+            res["tcgen05_own_sustained"] = t["sustained_ms"]
+            own_clocks = t["clocks"]
             t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=1), a.steps, a.warmup)
             res["tcgen05_own_v1_m128"] = t["median_ms"]
+            t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=3), a.steps, a.warmup)
+            res["tcgen05_own_v3_colsplit"] = t["median_ms"]
             if a.libs:
                 try:
                     from flash_attn import flash_attn_func
@@ -51,9 +78,11 @@ def main():
                 try:
                     import torch.nn.functional as F
 
-                    t = time_cuda(lambda: F.scaled_dot_product_attention(q, k, v, is_causal=bool(causal), enable_gqa=hkv != a.heads),
-                                  a.steps, a.warmup)
+                    t = timed_with_clocks(lambda: F.scaled_dot_product_attention(q, k, v, is_causal=bool(causal), enable_gqa=hkv != a.heads),
+                                          a.steps, a.warmup)
                     res["sdpa"] = t["median_ms"]
+                    res["sdpa_sustained"] = t["sustained_ms"]
+                    line_sdpa_clocks = t["clocks"]
                 except Exception as e:
                     res["sdpa_err"] = str(e)[:80]
             line = {"seq": s, "causal": causal, "heads": a.heads, "kv_heads": hkv, "dim": a.dim}
@@ -63,6 +92,9 @@ def main():
                     line[kname + "_tflops"] = round(flops / ms / 1e9, 1)
                 else:
                     line[kname] = ms
+            line["own_clocks"] = own_clocks
+            if "sdpa" in res:
+                line["sdpa_clocks"] = line_sdpa_clocks
             line["own_frac_of_measured_cublas_peak"] = round(flops / res["tcgen05_own"] / 1e9 / peak, 3)
             print(json.dumps(line), flush=True)
 

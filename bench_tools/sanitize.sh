@@ -25,6 +25,6 @@ torch.cuda.synchronize()
 print("ok", o.float().abs().max().item(), of.float().abs().max().item(), dq.abs().max().item())
 PY
 for tool in memcheck synccheck; do
-  timeout 600 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_driver.py > "$OUT/$tool.log" 2>&1
+  PYTHONPATH=$PWD timeout 600 compute-sanitizer --tool $tool --print-limit 20 python /tmp/san_driver.py > "$OUT/$tool.log" 2>&1
   echo "== $tool rc=$?"; tail -n 6 "$OUT/$tool.log"
 done

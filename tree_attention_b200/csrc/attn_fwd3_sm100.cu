@@ -1,0 +1,404 @@
+// attn_fwd3 -- attn_fwd_sm100.cu with TWO softmax warpgroups that split the columns of every S tile.
+// One softmax warp per SM sub-partition is issue-latency bound (bench_tools/ubench/exp_ubench.cu: 1751 cycles per
+// 128-element row with one warp, 1213 with two); here warps w and w+4 share TMEM lane quarter w and each owns 64 of
+// the 128 score columns, exchanging the half-row max / sum through shared memory once per tile.
+// (original header follows)
+// attn_partial_fwd -- flash-attention forward for sm_100a on the 5th-generation tensor cores.
+//
+// Replaces the reference's local attention (/root/reference/model.py:74-80: matmul -> softmax -> matmul
+// with the full score row materialised in HBM) for Sq >= 1 with GQA, causal masks
+// over GLOBAL positions, and the (o, lse) contract the tree combine needs.
+//
+// One CTA = one 128-row query tile of one (batch, q-head); 6 warps, warp-specialised:
+//   warps 0-3  softmax: tcgen05.ld S (one row per thread) -> online softmax with lazy rescale ->
+//              P (bf16/fp16) written back to TMEM over S -> epilogue O/l, lse, swizzled smem, TMA store
+//   warp  4    TMA producer: Q once, then K and V tiles through two 3-stage mbarrier rings
+//   warp  5    MMA issuer (one elected lane): S = Q K^T (SS form, K-major operands),
+//              O += P V (TS form: A = P from TMEM, B = V MN-major from smem); owns the TMEM allocation
+// TMEM (512 columns): S0 [0,128) | S1 [128,256) | O [256,256+D).  S is double-buffered so that
+// QK^T of tile j+1 and PV of tile j-1 run on the tensor pipe while the softmax of tile j runs on the
+// SIMT pipes; P_j aliases the first 64 columns of S_j.
+// All layout conventions used here are verified on hardware by csrc/umma_probe.cu (tests/test_gpu_probe.py).
+#include "attn_fwd_common.cuh"
+
+namespace ta {
+namespace {
+using namespace fwd_detail;
+
+constexpr int kFwd3Threads = 320;  // warps 0-3 / 4-7: softmax column halves, 8: TMA, 9: MMA
+constexpr int kSm3 = 256;
+
+template <int D, bool BF16, bool kComm>
+__global__ void __launch_bounds__(kFwd3Threads, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+                const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap omap,
+                const FwdParams p) {
+  using SM = FwdSmem<D>;
+  constexpr int NS = SM::kStages;   // K ring
+  constexpr int NSV = 2;            // V ring (frees 32 KB for the exchange buffers)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + SM::kQBytes;
+  uint8_t* v_s = k_s + NS * SM::kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + NSV * SM::kKVBytes);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // NS
+  uint64_t* k_empty = k_full + NS;    // NS
+  uint64_t* v_full = k_empty + NS;    // NSV
+  uint64_t* v_empty = v_full + NSV;   // NSV
+  uint64_t* s_full = v_empty + NSV;   // 2
+  uint64_t* p_full = s_full + 2;      // 2
+  uint64_t* pv_done = p_full + 2;     // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  // ---- work decode.  Single GPU: block x computes item x.  Fused multi-GPU: compute CTAs and merge CTAs
+  // share the launch, merges trail their item by `lag` compute CTAs:
+  //   x < L: compute x | L <= x < 2N-L: even -> compute, odd -> merge | x >= 2N-L: merge
+  int item = blockIdx.x;
+  uint32_t epoch = 0;
+  if constexpr (kComm) {
+    epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
+    const int N = p.n_items, L = p.lag, x = blockIdx.x;
+    bool is_merge = false;
+    if (x < L) item = x;
+    else if (x < 2 * N - L) { const int k = x - L; if (k & 1) { is_merge = true; item = k >> 1; } else item = L + (k >> 1); }
+    else { is_merge = true; item = (N - L) + (x - (2 * N - L)); }
+    if (is_merge) {
+      merge_item<D, BF16>(p, item, epoch, smem);
+      comm_kernel_exit(p, epoch);
+      return;
+    }
+  }
+  const int m_tile = p.num_m_tiles - 1 - (item % p.num_m_tiles);  // heaviest (causal) tiles first
+  const int bh = item / p.num_m_tiles;
+  const int hq = bh % p.Hq, b = bh / p.Hq;
+  const int hkv = hq / p.G;
+  const int m0 = m_tile * kBlockM;
+  constexpr int kSlotBytes = kBlockM * D * 2 + kBlockM * 4;
+  const size_t slot_off = kComm ? ((size_t)((epoch & 1) * p.comm.world + p.comm.rank) * p.n_items + item) * kSlotBytes : 0;
+  const size_t flag_off = kComm ? ((size_t)((epoch & 1) * p.comm.world + p.comm.rank) * p.n_items + item) : 0;
+
+  // number of KV tiles this query tile can see
+  int n_end = p.S;
+  if (p.causal) {
+    const long long last_q = p.q_pos0 + min(m0 + kBlockM - 1, p.Sq - 1);
+    const long long lim = last_q - p.kv_pos0 + 1;
+    n_end = (int)max(0LL, min((long long)p.S, lim));
+  }
+  const int n_tiles = (n_end + kBlockN - 1) / kBlockN;
+
+  if (n_tiles == 0) {
+    // nothing visible: the monoid identity (0, -inf)
+    if constexpr (kComm) {
+      if (!p.comm.skip_publish) {
+        for (int dst = 0; dst < p.comm.world; ++dst) {
+          uint8_t* slot = reinterpret_cast<uint8_t*>(p.comm.data[dst]) + slot_off;
+          for (int c = tid; c < kBlockM * (D / 8); c += kFwd3Threads) reinterpret_cast<uint4*>(slot)[c] = make_uint4(0, 0, 0, 0);
+          if (tid < kBlockM) reinterpret_cast<float*>(slot + kBlockM * D * 2)[tid] = neg_inf_f();
+        }
+        __syncthreads();
+        if (tid < p.comm.world) { fence_acq_rel_sys(); st_release_sys_u32(p.comm.flags[tid] + flag_off, epoch); }
+      }
+      comm_kernel_exit(p, epoch);
+    } else if (warp < 4) {
+      const int row = m0 + tid;
+      if (row < p.Sq) {
+        uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)b * p.o_sb + (long long)hq * p.o_sh + (long long)row * p.o_ss;
+        for (int d = 0; d < D; d += 8) *reinterpret_cast<uint4*>(op + d) = make_uint4(0, 0, 0, 0);
+        p.lse[((long long)b * p.Hq + hq) * p.Sq + row] = neg_inf_f();
+      }
+    }
+    return;
+  }
+
+  if (tid == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < NSV; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8); mbar_init(&pv_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&qmap); tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); tma_prefetch_desc(&omap);
+  }
+  if (warp == 9) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_o = tmem + 256;
+
+  if (warp == 8) {
+    // =============================== TMA producer ===============================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, SM::kQBytes);
+#pragma unroll
+      for (int a = 0; a < SM::kAtoms; ++a) tma_load_4d(q_s + a * SM::kAtomBytes, &qmap, q_full, a * 64, m0, hq, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % NS;
+        const uint32_t ph = (j / NS) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], SM::kKVBytes);
+#pragma unroll
+        for (int a = 0; a < SM::kAtoms; ++a)
+          tma_load_4d(k_s + st * SM::kKVBytes + a * SM::kAtomBytes, &kmap, &k_full[st], a * 64, j * kBlockN, hkv, b);
+        const int sv = j % NSV;
+        mbar_wait(&v_empty[sv], ((j / NSV) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[sv], SM::kKVBytes);
+#pragma unroll
+        for (int a = 0; a < SM::kAtoms; ++a)
+          tma_load_4d(v_s + sv * SM::kKVBytes + a * SM::kAtomBytes, &vmap, &v_full[sv], a * 64, j * kBlockN, hkv, b);
+      }
+    }
+  } else if (warp == 9) {
+    // =============================== MMA issuer =================================================
+    if (lane == 0) {
+      constexpr uint32_t fmt = BF16 ? 1u : 0u;
+      constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kBlockM, kBlockN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc(fmt, fmt, kBlockM, D, 0, 1);
+      const uint32_t q_addr = smem_u32(q_s);
+      auto issue_qk = [&](int j) {
+        const int st = j % NS;
+        mbar_wait(&k_full[st], (j / NS) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(k_s + st * SM::kKVBytes);
+        const uint32_t d_tmem = tmem + (j & 1) * 128;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * SM::kAtomBytes + (kk % 4) * 32;
+          umma_ss_f16(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
+                      idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        const int st = j % NS;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        const int sv = j % NSV;
+        mbar_wait(&v_full[sv], (j / NSV) & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(v_s + sv * SM::kKVBytes);
+        const uint32_t p_tmem = tmem + (j & 1) * 128;
+#pragma unroll
+        for (int kk = 0; kk < kBlockN / 16; ++kk) {
+          umma_ts_f16(tmem_o, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * 2048, kBlockN * 128, 1024), idesc_pv,
+                      (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[sv]);
+        umma_commit(&pv_done[j & 1]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== softmax warpgroups (column halves) ==========================
+    const int g = warp >> 2;                               // 0: columns [0,64), 1: columns [64,128)
+    const int row = tid & 127;                             // row of the tile == TMEM lane
+    const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
+    const long long q_pos = p.q_pos0 + m0 + row;
+    float* xch = reinterpret_cast<float*>(tmem_slot + 4);  // [2 parity][2 halves][128] max exchange, then [2][128] sums
+    constexpr int DH = D / 2;                              // O columns owned by this warpgroup
+    float m_used = neg_inf_f();
+    float l_sum = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int n0 = j * kBlockN;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_tmem = tmem + (j & 1) * 128 + lane_addr;
+      uint32_t sr[64];
+      tmem_ld_32x32b_x32(s_tmem + g * 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+      tmem_ld_32x32b_x32(s_tmem + g * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+      tmem_ld_wait();
+      const bool need_mask = (n0 + kBlockN > p.S) || (p.causal && (p.kv_pos0 + n0 + kBlockN - 1 > p.q_pos0 + m0));
+      if (need_mask) {
+        long long lim = (long long)p.S - n0 - 1;
+        if (p.causal) lim = min(lim, q_pos - p.kv_pos0 - n0);
+        const int limc = (int)max(-1LL, min(lim, 127LL)) - g * 64;
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (c > limc) sr[c] = 0xff800000u;
+      }
+      float mx8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
+#pragma unroll
+      for (int c = 8; c < 64; c += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(mx8[i], __uint_as_float(sr[c + i]));
+      }
+      float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+      // exchange the half-row maxima (double-buffered by tile parity; one 256-thread barrier per tile)
+      xch[((j & 1) * 2 + g) * 128 + row] = mx;
+      named_bar_sync(1, kSm3);
+      mx = fmaxf(mx, xch[((j & 1) * 2 + (1 - g)) * 128 + row]);
+      const float m_new = fmaxf(m_used, mx * p.scale_log2);
+      const bool refresh = (m_new - m_used > kRescaleThreshold) || (m_used == neg_inf_f() && m_new != neg_inf_f());
+      if (__any_sync(0xffffffffu, refresh)) {
+        const float alpha = refresh ? fast_exp2(m_used - m_new) : 1.f;
+        if (refresh) { l_sum *= alpha; m_used = m_new; }
+        if (j > 0) {
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < DH; c0 += 32) {
+            uint32_t orow[32];
+            tmem_ld_32x32b_x32(tmem_o + lane_addr + g * DH + c0, orow);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_o + lane_addr + g * DH + c0, orow);
+          }
+        }
+      }
+      const float neg_m = (m_used == neg_inf_f()) ? 0.f : -m_used;
+      float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 64; c += 8) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c + i]), p.scale_log2, neg_m));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + i + 1]), p.scale_log2, neg_m));
+          ls[i] += p0; ls[i + 1] += p1;
+          pk[(c + i) >> 1] = pack2<BF16>(p0, p1);
+        }
+      }
+      l_sum += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+      tmem_st_32x32b_x32(s_tmem + g * 32, pk);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+    }
+    // ------------------------------- epilogue --------------------------------------------------
+    const int jl = n_tiles - 1;
+    mbar_wait(&pv_done[jl & 1], (jl >> 1) & 1);
+    tc_fence_after();
+    // total row sum = sum of the two column halves (both were scaled against the same m_used)
+    named_bar_sync(1, kSm3);                 // everyone is done with the max-exchange slots
+    xch[g * 128 + row] = l_sum;
+    named_bar_sync(1, kSm3);
+    l_sum += xch[(1 - g) * 128 + row];
+    const float inv_l = l_sum > 0.f ? 1.f / l_sum : 0.f;
+#pragma unroll
+    for (int c0 = 0; c0 < DH; c0 += 32) {
+      uint32_t orow[32];
+      tmem_ld_32x32b_x32(tmem_o + lane_addr + g * DH + c0, orow);
+      tmem_ld_wait();
+      const int col0 = g * DH + c0;
+      uint8_t* base = q_s + (col0 >> 6) * SM::kAtomBytes + row * 128;
+#pragma unroll
+      for (int gg = 0; gg < 4; ++gg) {  // 4 chunks of 8 elements (16 B)
+        uint4 w;
+        w.x = pack2<BF16>(__uint_as_float(orow[gg * 8 + 0]) * inv_l, __uint_as_float(orow[gg * 8 + 1]) * inv_l);
+        w.y = pack2<BF16>(__uint_as_float(orow[gg * 8 + 2]) * inv_l, __uint_as_float(orow[gg * 8 + 3]) * inv_l);
+        w.z = pack2<BF16>(__uint_as_float(orow[gg * 8 + 4]) * inv_l, __uint_as_float(orow[gg * 8 + 5]) * inv_l);
+        w.w = pack2<BF16>(__uint_as_float(orow[gg * 8 + 6]) * inv_l, __uint_as_float(orow[gg * 8 + 7]) * inv_l);
+        const int chunk = ((col0 & 63) >> 3) + gg;
+        *reinterpret_cast<uint4*>(base + ((chunk ^ (row & 7)) << 4)) = w;
+      }
+    }
+    const float lse_row = l_sum > 0.f ? (m_used + fast_log2(l_sum)) * 0.6931471805599453f : neg_inf_f();
+    if constexpr (!kComm) {
+      if (g == 0 && m0 + row < p.Sq) p.lse[((long long)b * p.Hq + hq) * p.Sq + m0 + row] = lse_row;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(1, kSm3);
+      if (tid == 0) {
+#pragma unroll
+        for (int a = 0; a < SM::kAtoms; ++a) tma_store_4d(&omap, q_s + a * SM::kAtomBytes, a * 64, m0, hq, b);
+        tma_store_commit();
+        tma_store_wait<0>();
+      }
+    } else {
+      tc_fence_before();
+      named_bar_sync(1, kSm3);
+      if (!p.comm.skip_publish) {
+        constexpr int CPR = D / 8;
+        for (int dst = 0; dst < p.comm.world; ++dst) {
+          uint8_t* slot = reinterpret_cast<uint8_t*>(p.comm.data[dst]) + slot_off;
+#pragma unroll 4
+          for (int c = tid; c < kBlockM * CPR; c += kSm3) {
+            const int r = c / CPR, ch = c - r * CPR;
+            const uint4 w = *reinterpret_cast<const uint4*>(q_s + (ch >> 3) * SM::kAtomBytes + r * 128 + (((ch & 7) ^ (r & 7)) << 4));
+            *reinterpret_cast<uint4*>(slot + (size_t)r * D * 2 + ch * 16) = w;
+          }
+          if (g == 0) reinterpret_cast<float*>(slot + kBlockM * D * 2)[row] = lse_row;
+        }
+        named_bar_sync(1, kSm3);
+        if (tid < p.comm.world) { fence_acq_rel_sys(); st_release_sys_u32(p.comm.flags[tid] + flag_off, epoch); }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem);
+  }
+  if constexpr (kComm) comm_kernel_exit(p, epoch);
+}
+
+template <int D, bool BF16, bool kComm>
+void launch_fwd3(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                const CommCtxHost& comm, cudaStream_t stream) {
+  using SM = FwdSmem<D>;
+  CUtensorMap qmap = make_tmap_bhsd(q, 2, s.B, s.Hq, s.Sq, D, s.q_sb, s.q_sh, s.q_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, D, s.k_sb, s.k_sh, s.k_ss, 64, kBlockN, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap vmap = make_tmap_bhsd(v, 2, s.B, s.Hkv, s.S, D, s.v_sb, s.v_sh, s.v_ss, 64, kBlockN, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap omap = make_tmap_bhsd(out, 2, s.B, s.Hq, s.Sq, D, s.o_sb, s.o_sh, s.o_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+  FwdParams p;
+  p.lse = lse; p.out = out; p.o_sb = s.o_sb; p.o_sh = s.o_sh; p.o_ss = s.o_ss;
+  p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = s.Hq / s.Hkv; p.Sq = s.Sq; p.S = s.S;
+  p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
+  p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;
+  p.num_m_tiles = (s.Sq + kBlockM - 1) / kBlockM;
+  p.n_items = p.num_m_tiles * s.Hq * s.B;
+  p.lag = std::min(p.n_items, 2 * num_sms());
+  p.comm = to_device_ctx(comm);
+  if (kComm) {
+    const size_t slot = (size_t)kBlockM * D * 2 + kBlockM * 4;
+    if ((size_t)2 * comm.world * p.n_items * slot > comm.data_bytes ||
+        (size_t)2 * comm.world * p.n_items * 4 > comm.flag_bytes)
+      throw std::runtime_error("attn_fwd(fused): symmetric buffer too small");
+  }
+  auto kern = attn_fwd3_kernel<D, BF16, kComm>;
+  static bool configured = false;
+  if (!configured) {
+    TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kTotal));
+    configured = true;
+  }
+  dim3 grid(kComm ? 2 * p.n_items : p.n_items);
+  kern<<<grid, kFwd3Threads, SM::kTotal, stream>>>(qmap, kmap, vmap, omap, p);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+void attn_fwd3_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                     const CommCtxHost& comm, cudaStream_t stream) {
+  if (s.D != 64 && s.D != 128) throw std::runtime_error("attn_fwd: head_dim must be 64 or 128");
+  if (s.Hq % s.Hkv != 0) throw std::runtime_error("attn_fwd: Hq must be a multiple of Hkv");
+  if (s.S <= 0 || s.Sq <= 0) throw std::runtime_error("attn_fwd: empty problem");
+  const bool fused = comm.world > 1;
+#define TA_FWD(DD, BB)                                                               \
+  if (fused) launch_fwd3<DD, BB, true>(s, q, k, v, out, lse, comm, stream);           \
+  else launch_fwd3<DD, BB, false>(s, q, k, v, out, lse, comm, stream);
+  if (s.D == 128) {
+    if (s.is_bf16) { TA_FWD(128, true) } else { TA_FWD(128, false) }
+  } else {
+    if (s.is_bf16) { TA_FWD(64, true) } else { TA_FWD(64, false) }
+  }
+#undef TA_FWD
+}
+
+}  // namespace ta

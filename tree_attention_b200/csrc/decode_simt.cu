@@ -388,8 +388,26 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
 
   if (tid == 0) { s_misc[2] = 1; s_misc[3] = 0; }
 
+  // KV8: the block scales of the NEXT tile are prefetched into registers one iteration ahead, so that their
+  // global-load latency hides behind the current tile's math and the mbarrier wait.
+  [[maybe_unused]] uint32_t nxt_ksc = 0, nxt_vsc = 0;
+  [[maybe_unused]] auto fetch_scales = [&](int tt) {
+    if constexpr (KV8) {
+      if (tt < t_hi) {
+        const int xx = tt / p.tph, jj = tt - xx * p.tph;
+        const long long srow = (long long)xx * p.S + min((long long)jj * kTileRows + warp * kRowsPerWarp + (lane & 15), (long long)p.S - 1);
+        nxt_ksc = __ldg(p.kscale + srow);
+        nxt_vsc = __ldg(p.vscale + srow);
+      }
+    }
+  };
+  fetch_scales(t_lo);
+
   for (int t = t_lo; t < t_hi; ++t) {
     const int x = t / p.tph, j = t - x * p.tph;
+    [[maybe_unused]] const uint32_t ksc_word = nxt_ksc;
+    [[maybe_unused]] const uint32_t vsc_cur = nxt_vsc;
+    fetch_scales(t + 1);
     if (x != cur_x) {
       if (cur_x >= 0) finalize_segment(cur_x);
       load_q(x);
@@ -435,9 +453,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     } else {
       // block-scaled fp8: this lane covers 64 elements = 4 chunks of 16 = blocks {2*half, 2*half+1}; products are
       // accumulated per chunk in fp16x2 (8 HFMA2), then scaled by the block's UE8M0 scale in fp32.
-      const long long srow = ((long long)(cur_x)*p.S) + min((long long)j * kTileRows + row, (long long)p.S - 1);
-      const uint32_t ksc_word = __ldg(p.kscale + srow);
-      vsc_word = __ldg(p.vscale + srow);
+      vsc_word = vsc_cur;
 #pragma unroll
       for (int r = 0; r < R; ++r) s_sum[r] = 0.f;
 #pragma unroll

@@ -65,6 +65,9 @@ void umma_probe_launch(const void* a, const void* b, float* c, int N, int K, int
 void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                      const CommCtxHost& comm, cudaStream_t stream);
 size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
+// M = 128 with two softmax warpgroups splitting the score columns (two resident softmax warps per SM sub-partition)
+void attn_fwd3_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                      const CommCtxHost& comm, cudaStream_t stream);
 // two ping-ponged query tiles per CTA (M = 256); same contract and symmetric-buffer layout
 void attn_fwd2_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                       const CommCtxHost& comm, cudaStream_t stream);
