@@ -249,19 +249,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       }
       const float m_sub = (m_used == neg_inf_f()) ? 0.f : m_used;
       const float neg_m = -m_sub;
-      float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      // exp2(s * c - m) with packed f32x2 scale-subtract and row-sum (FFMA2 / FADD2: half the issue slots)
+      const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
+      uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[64];
 #pragma unroll
       for (int c = 0; c < 128; c += 8) {
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c + i]), p.scale_log2, neg_m));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + i + 1]), p.scale_log2, neg_m));
-          ls[i] += p0; ls[i + 1] += p1;
+          float x0, x1;
+          unpack_f32x2(fma2_f32x2(pack_f32x2(__uint_as_float(sr[c + i]), __uint_as_float(sr[c + i + 1])), sc2, nm2), x0, x1);
+          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+          ls2[i >> 1] = add2_f32x2(ls2[i >> 1], pack_f32x2(p0, p1));
           pk[(c + i) >> 1] = pack2<BF16>(p0, p1);
         }
       }
-      l_sum += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+      {
+        float a0, a1, b0, b1, c0, c1, d0, d1;
+        unpack_f32x2(ls2[0], a0, a1); unpack_f32x2(ls2[1], b0, b1); unpack_f32x2(ls2[2], c0, c1); unpack_f32x2(ls2[3], d0, d1);
+        l_sum += ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
+      }
       tmem_st_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
       tmem_st_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       tmem_st_wait();

@@ -74,6 +74,26 @@ __device__ __forceinline__ float f16hi(uint32_t w) {
   return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16)));
 }
 
+// packed fp32x2 math (sm_100: FFMA2 / FADD2 issue one instruction for two lanes of work)
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
