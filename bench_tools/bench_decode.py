@@ -23,13 +23,18 @@ for s in a.seq:
     i = [0]
     def f16():
         i[0] += 1
-        return L.decode_attention(q, *kvs[i[0] % n], 0.088, return_lse=False)
+        return L.decode_attention(q, *kvs[i[0] % n], 0.088, return_lse=False, impl="simt")
+    def ftc():
+        i[0] += 1
+        return L.decode_attention(q, *kvs[i[0] % n], 0.088, return_lse=False, impl="tc")
     def f8():
         i[0] += 1
         return L.decode_attention_mxfp8(q, *mx[i[0] % n], 0.088, return_lse=False)
     t16 = time_cuda(f16, a.steps, 10)["median_ms"]
     t8 = time_cuda(f8, a.steps, 10)["median_ms"]
+    ttc = time_cuda(ftc, a.steps, 10)["median_ms"]
     b16 = 2 * hkv * s * 128 * 2
     b8 = 2 * hkv * s * (128 + 4)
     print(json.dumps({"seq": s, "heads": a.heads, "kv_heads": hkv, "bf16_us": round(t16 * 1e3, 1), "bf16_gbs": round(b16 / t16 / 1e6, 0),
+                      "bf16_tcgen05_us": round(ttc * 1e3, 1), "bf16_tcgen05_gbs": round(b16 / ttc / 1e6, 0),
                       "mxfp8_us": round(t8 * 1e3, 1), "mxfp8_gbs": round(b8 / t8 / 1e6, 0), "speedup": round(t16 / t8, 2)}), flush=True)

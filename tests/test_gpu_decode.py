@@ -35,16 +35,19 @@ CASES = [
     (2, 8, 4, 1, 3000, 128, torch.bfloat16, False, True),     # BSHD-strided inputs
     (1, 2, 2, 1, 100000, 128, torch.bfloat16, False, False),  # few heads, many splits per head
     (3, 5, 5, 1, 129, 128, torch.bfloat16, True, False),
+    (1, 32, 8, 8, 3000, 128, torch.bfloat16, True, False),    # 32 packed rows (GQA 4 x 8 tokens: speculative decode)
+    (1, 16, 2, 16, 1111, 64, torch.float16, True, False),     # 128 packed rows: a full tile
 ]
 
 
+@pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
-def test_decode_matches_oracle(case):
+def test_decode_matches_oracle(case, impl):
     b, hq, hkv, sq, s, d, dtype, causal, bshd = case
     q, k, v = _mk(b, hq, hkv, sq, s, d, dtype, bshd=bshd)
     scale = d ** -0.5
     q_pos0 = s - sq
-    out, lse = L.decode_attention(q, k, v, scale, causal, q_pos0, 0)
+    out, lse = L.decode_attention(q, k, v, scale, causal, q_pos0, 0, impl=impl)
     o_ref, l_ref = ref.attention_partial_ref(q, k, v, scale, causal, q_pos0, 0, torch.float32, block=16384)
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
@@ -53,13 +56,14 @@ def test_decode_matches_oracle(case):
     assert (lse - l_ref).abs().max().item() < 2e-3
 
 
-def test_causal_offsets_and_fully_masked_shard():
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_causal_offsets_and_fully_masked_shard(impl):
     q, k, v = _mk(1, 4, 4, 1, 1000, 128, torch.bfloat16, seed=3)
     # shard starts AFTER the query position: every key masked -> identity (0, -inf), no NaN
-    out, lse = L.decode_attention(q, k, v, 0.1, True, q_pos0=10, kv_pos0=500)
+    out, lse = L.decode_attention(q, k, v, 0.1, True, q_pos0=10, kv_pos0=500, impl=impl)
     assert torch.all(out == 0) and torch.all(torch.isinf(lse) & (lse < 0))
     # partially visible shard
-    out, lse = L.decode_attention(q, k, v, 0.1, True, q_pos0=700, kv_pos0=500)
+    out, lse = L.decode_attention(q, k, v, 0.1, True, q_pos0=700, kv_pos0=500, impl=impl)
     o_ref, l_ref = ref.attention_partial_ref(q, k, v, 0.1, True, 700, 500)
     assert (out.float() - o_ref).abs().max().item() < 1.5e-2 and (lse - l_ref).abs().max().item() < 2e-3
 
@@ -73,12 +77,13 @@ def test_public_api_dispatches_to_kernel_and_matches():
     assert res.shape == (1, 16, 1, 128) and lse.shape == (1, 16, 1) and lse.dtype == torch.float32
 
 
-def test_repeated_calls_are_deterministic_and_reset_tickets():
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+def test_repeated_calls_are_deterministic_and_reset_tickets(impl):
     q, k, v = _mk(2, 8, 8, 1, 6000, 128, torch.bfloat16, seed=5)
-    first, _ = L.decode_attention(q, k, v, 0.088, False)
+    first, _ = L.decode_attention(q, k, v, 0.088, False, impl=impl)
     first = first.clone()
     for _ in range(200):
-        out, _ = L.decode_attention(q, k, v, 0.088, False)
+        out, _ = L.decode_attention(q, k, v, 0.088, False, impl=impl)
     torch.cuda.synchronize()
     assert torch.equal(out, first)
 

@@ -159,6 +159,38 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at:
                         at::cuda::getCurrentCUDAStream());
 }
 
+py::tuple decode_tc_plan(int B, int Hq, int Hkv, int Sq, int S, int D) {
+  AttnShape s;
+  s.B = B; s.Hq = Hq; s.Hkv = Hkv; s.Sq = Sq; s.S = S; s.D = D;
+  int grid, mp, R;
+  size_t pf, cb;
+  ta::decode_tc_plan(s, ta::num_sms(), &grid, &mp, &R, &pf, &cb);
+  return py::make_tuple(grid, mp, R, (int64_t)pf, (int64_t)cb);
+}
+
+void decode_tc_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out,
+                   c10::optional<at::Tensor> lse, at::Tensor& part, at::Tensor& tickets, py::object comm, double scale,
+                   bool causal, int64_t q_pos0, int64_t kv_pos0) {
+  c10::cuda::CUDAGuard guard(q.device());
+  AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
+  TORCH_CHECK(part.scalar_type() == at::kFloat && part.is_contiguous(), "part must be contiguous fp32");
+  int grid, mp, R;
+  size_t pf, cb;
+  ta::decode_tc_plan(s, ta::num_sms(), &grid, &mp, &R, &pf, &cb);
+  TORCH_CHECK((size_t)part.numel() >= pf, "part workspace too small: need ", pf, " floats");
+  TORCH_CHECK(tickets.scalar_type() == at::kInt && tickets.numel() >= s.B * s.Hkv + 2, "tickets too small");
+  TORCH_CHECK(q.stride(2) % 8 == 0 || q.size(2) == 1, "q rows must be 16-byte aligned");
+  float* lse_p = nullptr;
+  if (lse.has_value()) {
+    TORCH_CHECK(lse->scalar_type() == at::kFloat && lse->is_contiguous() && lse->numel() == (int64_t)s.B * s.Hq * s.Sq);
+    lse_p = lse->data_ptr<float>();
+  }
+  CommCtxHost c;
+  if (!comm.is_none()) c = comm.cast<Comm&>().h;
+  ta::decode_tc_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
+                       reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream());
+}
+
 // block-scaled fp8 KV cache decode: k8/v8 uint8 (B, Hkv, S, 128) e4m3, ks/vs uint8 (B, Hkv, S, 4) UE8M0
 void decode_fwd_mx(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& ks,
                    const at::Tensor& vs, at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part,
@@ -302,6 +334,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_plan", &decode_plan);
   m.def("decode_fwd", &decode_fwd);
   m.def("decode_fwd_mx", &decode_fwd_mx);
+  m.def("decode_tc_plan", &decode_tc_plan);
+  m.def("decode_tc_fwd", &decode_tc_fwd);
   m.def("quant_mxfp8", &quant_mxfp8);
   m.def("dequant_mxfp8", &dequant_mxfp8);
   m.def("attn_fwd", &attn_fwd);

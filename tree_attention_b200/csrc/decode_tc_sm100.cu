@@ -1,0 +1,573 @@
+// attn_tree_fused_decode (tensor-core variant) -- split-KV decode on tcgen05 with the tree combine in the epilogue.
+//
+// The CUDA-core decode kernel (decode_simt.cu) is HBM-bound for MHA (1 query row per KV head) but issue-bound once
+// a KV head serves several query rows (GQA 32q/8kv: 51-60 % of HBM peak, profiles/r1_decode/).  Here the R = G x Sq
+// query rows of one KV head are PACKED into one 128-row MMA tile (rows >= R are zero padding), so the tensor pipe
+// does all the math at a cost that does not depend on R and the kernel stays HBM-bound:
+//
+//   * persistent CTAs, stream-K over the flattened (batch, kv-head, 128-row KV tile) space -- same split, workspace
+//     and ticket scheme as decode_simt.cu; the TMA warp streams K/V tiles continuously across head boundaries;
+//   * per head segment: the softmax warps stage the packed Q tile into 128B-swizzled smem (generic stores +
+//     fence.proxy.async), the MMA thread runs S = Q K^T (SS) / O += P V (TS, P from TMEM) exactly like
+//     attn_fwd_sm100.cu (double-buffered S, lazy rescale), only warps that own valid rows do softmax work;
+//   * epilogue: (O, m, l) of the valid rows -> workspace -> atomic ticket -> the last CTA of the head merges the
+//     splits in part order -> output, or LL-tagged 8-byte words to every peer + deferred cross-GPU merge.
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace ta {
+namespace {
+
+constexpr int kTM = 128;  // MMA M (packed query rows, zero padded)
+constexpr int kTN = 128;  // KV rows per tile
+constexpr int kTcThreads = 192;
+constexpr int kSmx = 128;
+constexpr int kTcStages = 3;
+constexpr int kTcMaxPending = 32;
+constexpr float kTcRescale = 8.0f;
+
+struct DecodeTcParams {
+  const void* q;
+  void* out;
+  float* lse;
+  float* part;
+  uint32_t* tickets;
+  int B, Hq, Hkv, G, Sq, S, R;
+  float scale_log2;
+  int causal;
+  long long q_pos0, kv_pos0;
+  long long q_sb, q_sh, q_ss, o_sb, o_sh, o_ss;
+  int tph, total_tiles, tiles_q, tiles_rem, max_parts, jvis;
+  CommCtx comm;
+};
+
+template <int D>
+struct TcSmem {
+  static constexpr int kAtoms = D / 64;
+  static constexpr int kTileBytes = 128 * D * 2;
+  static constexpr int kAtomBytes = 128 * 128;
+  static constexpr size_t kTotal = 1024 + size_t(1 + 2 * kTcStages) * kTileBytes + 512;
+};
+
+__device__ __forceinline__ float tc_ninf() { return __int_as_float(0xff800000); }
+__device__ __forceinline__ int tc_cta_lo(const DecodeTcParams& p, int c) { return c * p.tiles_q + min(c, p.tiles_rem); }
+__device__ __forceinline__ int tc_cta_of_tile(const DecodeTcParams& p, int t) {
+  const int big = p.tiles_rem * (p.tiles_q + 1);
+  return t < big ? t / (p.tiles_q + 1) : p.tiles_rem + (t - big) / p.tiles_q;
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t tc_pack2(float lo, float hi) {
+  if constexpr (BF16) return pack_bf16x2(lo, hi);
+  else return pack_f16x2(lo, hi);
+}
+template <bool BF16>
+__device__ __forceinline__ uint16_t tc_to16(float f) {
+  if constexpr (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  else return __half_as_ushort(__float2half_rn(f));
+}
+
+template <int D, bool BF16>
+__global__ void __launch_bounds__(kTcThreads, 1)
+decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
+                 const DecodeTcParams p) {
+  using SM = TcSmem<D>;
+  constexpr int NS = kTcStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;
+  uint8_t* k_s = q_s + SM::kTileBytes;
+  uint8_t* v_s = k_s + NS * SM::kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + NS * SM::kTileBytes);
+  uint64_t* q_ready = bars;            // 1 (count 128)
+  uint64_t* k_full = bars + 1;         // NS
+  uint64_t* k_empty = k_full + NS;
+  uint64_t* v_full = k_empty + NS;
+  uint64_t* v_empty = v_full + NS;
+  uint64_t* s_full = v_empty + NS;     // 2
+  uint64_t* p_full = s_full + 2;       // 2
+  uint64_t* pv_done = p_full + 2;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  int* s_misc = reinterpret_cast<int*>(tmem_slot + 2);  // [0] ticket, [1] n_pending, [2] inline-combine head+1
+  int* pending = s_misc + 4;                            // [kTcMaxPending]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int t_lo = tc_cta_lo(p, cta), t_hi = tc_cta_lo(p, cta + 1);
+  const int world = p.comm.world;
+  const int BH = p.B * p.Hkv;
+  const int R = p.R;
+  const int n_active_warps = (R + 31) / 32;
+
+  if (tid == 0) {
+    mbar_init(q_ready, kSmx);
+    for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], n_active_warps); mbar_init(&pv_done[i], 1); }
+    fence_mbar_init();
+    s_misc[1] = 0; s_misc[2] = 0;
+  }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); }
+  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  // zero the whole Q tile once: rows >= R stay zero padding, rows < R are rewritten per head segment
+  if (warp < 4) {
+    for (int c = tid; c < kTM * (D / 8); c += kSmx) reinterpret_cast<uint4*>(q_s)[c] = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_o = tmem + 256;
+
+  uint32_t epoch = 0;
+  if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
+  const int parity = epoch & 1;
+  const uint64_t t_cta0 = globaltimer_ns();
+
+  // segment iteration shared by all roles: consecutive tiles of one head, clipped to the visible (causal) prefix
+  auto next_segment = [&](int t, int& x, int& j0, int& n, int& t_next) {
+    x = t / p.tph;
+    const int seg_end = min(t_hi, (x + 1) * p.tph);
+    j0 = t - x * p.tph;
+    const int j1 = seg_end - x * p.tph;
+    n = max(0, min(j1, p.jvis) - j0);
+    t_next = seg_end;
+  };
+
+  if (warp == 4) {
+    // =============================== TMA producer ===============================================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = t_lo; t < t_hi;) {
+        int x, j0, n, tn;
+        next_segment(t, x, j0, n, tn);
+        const int b = x / p.Hkv, h = x - b * p.Hkv;
+        for (int jj = 0; jj < n; ++jj, ++it) {
+          const int st = it % NS;
+          const uint32_t ph = (it / NS) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], SM::kTileBytes);
+#pragma unroll
+          for (int a = 0; a < SM::kAtoms; ++a)
+            tma_load_4d(k_s + st * SM::kTileBytes + a * SM::kAtomBytes, &kmap, &k_full[st], a * 64, (j0 + jj) * kTN, h, b);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], SM::kTileBytes);
+#pragma unroll
+          for (int a = 0; a < SM::kAtoms; ++a)
+            tma_load_4d(v_s + st * SM::kTileBytes + a * SM::kAtomBytes, &vmap, &v_full[st], a * 64, (j0 + jj) * kTN, h, b);
+        }
+        t = tn;
+      }
+    }
+  } else if (warp == 5) {
+    // =============================== MMA issuer =================================================
+    if (lane == 0) {
+      constexpr uint32_t fmt = BF16 ? 1u : 0u;
+      constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kTM, kTN, 0, 0);
+      constexpr uint32_t idesc_pv = umma_idesc(fmt, fmt, kTM, D, 0, 1);
+      const uint32_t q_addr = smem_u32(q_s);
+      auto issue_qk = [&](int i) {
+        const int st = i % NS;
+        mbar_wait(&k_full[st], (i / NS) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(k_s + st * SM::kTileBytes);
+        const uint32_t d_tmem = tmem + (i & 1) * 128;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t off = (kk / 4) * SM::kAtomBytes + (kk % 4) * 32;
+          umma_ss_f16(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
+                      idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[i & 1]);
+      };
+      int it = 0, seg = 0;
+      for (int t = t_lo; t < t_hi;) {
+        int x, j0, n, tn;
+        next_segment(t, x, j0, n, tn);
+        mbar_wait(q_ready, seg & 1);   // the packed Q tile of this head is in smem (and visible to the async proxy)
+        tc_fence_after();
+        if (n > 0) {
+          issue_qk(it);
+          for (int jj = 0; jj < n; ++jj) {
+            const int i = it + jj;
+            if (jj + 1 < n) issue_qk(i + 1);
+            const int st = i % NS;
+            mbar_wait(&p_full[i & 1], (i >> 1) & 1);
+            mbar_wait(&v_full[st], (i / NS) & 1);
+            tc_fence_after();
+            const uint32_t v_addr = smem_u32(v_s + st * SM::kTileBytes);
+            const uint32_t p_tmem = tmem + (i & 1) * 128;
+#pragma unroll
+            for (int kk = 0; kk < kTN / 16; ++kk)
+              umma_ts_f16(tmem_o, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * 2048, kTN * 128, 1024), idesc_pv,
+                          (jj > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(&v_empty[st]);
+            umma_commit(&pv_done[i & 1]);
+          }
+          it += n;
+        }
+        ++seg;
+        t = tn;
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== softmax / epilogue warps ===================================
+    const int row = tid;  // packed query row == TMEM lane;  row r -> (g = r / Sq, i = r % Sq)
+    const bool row_valid = row < R;
+    const bool warp_active = (warp * 32) < R;
+    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    const int g_row = row / p.Sq, i_row = row - g_row * p.Sq;
+    const long long q_pos = p.q_pos0 + i_row;
+
+    auto store_out = [&](int x, int r, int d, float o_norm, float lse2) {
+      const int b = x / p.Hkv, h = x - b * p.Hkv;
+      const int g = r / p.Sq, i = r - g * p.Sq;
+      uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)b * p.o_sb + (long long)(h * p.G + g) * p.o_sh +
+                     (long long)i * p.o_ss + d;
+      *op = tc_to16<BF16>(o_norm);
+      if (d == 0 && p.lse != nullptr) p.lse[((long long)b * p.Hq + (h * p.G + g)) * p.Sq + i] = lse2 * 0.6931471805599453f;
+    };
+    // ---- LL transport (tagged 8-byte words), identical protocol to decode_simt.cu ----
+    auto word_ptr = [&](int dst, int src, int x) -> uint2* {
+      return reinterpret_cast<uint2*>(p.comm.data[dst]) + ((size_t)(parity * world + src) * BH + x) * (size_t)(R * (D + 2));
+    };
+    auto ll_store = [&](uint2* w, float v) {
+      asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(w), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+    };
+    auto ll_wait = [&](const uint2* w, bool& ok) -> float {
+      uint32_t v, tag;
+      asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(w) : "memory");
+      if (tag != epoch) {
+        const uint64_t t0 = globaltimer_ns();
+        uint32_t itn = 0;
+        do {
+          asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(w) : "memory");
+          if (tag == epoch) break;
+          if ((++itn & 0x3fu) == 0 && globaltimer_ns() - t0 > p.comm.timeout_ns) { ok = false; break; }
+        } while (true);
+      }
+      return __uint_as_float(v);
+    };
+    uint64_t t_publish = 0;
+    auto combine_ranks = [&](int x) {
+      uint64_t t_got = 0;
+      for (int idx = tid; idx < R * D; idx += kSmx) {
+        const int r = idx / D, d = idx - r * D;
+        bool ok = true;
+        float lse_s[kMaxWorld];
+        float mx = tc_ninf();
+        int bad_src = -1;
+        for (int s = 0; s < world; ++s) {
+          bool oks = true;
+          lse_s[s] = ll_wait(word_ptr(p.comm.rank, s, x) + r * (D + 2) + D, oks);
+          if (!oks) { ok = false; bad_src = s; }
+          mx = fmaxf(mx, lse_s[s]);
+        }
+        const float ms = (mx == tc_ninf()) ? 0.f : mx;
+        float num = 0.f, den = 0.f;
+        for (int s = 0; s < world; ++s) {
+          bool oks = true;
+          const float val = ll_wait(word_ptr(p.comm.rank, s, x) + r * (D + 2) + d, oks);
+          if (!oks) { ok = false; bad_src = s; }
+          const float w = fast_exp2(lse_s[s] - ms);
+          num = fmaf(w, val, num);
+          den += w;
+        }
+        if (idx == 0) t_got = globaltimer_ns();
+        float o_norm = den > 0.f ? num / den : 0.f;
+        float lse2 = den > 0.f ? ms + fast_log2(den) : tc_ninf();
+        if (!ok) {
+          o_norm = __int_as_float(0x7fc00000); lse2 = o_norm;
+          p.comm.status[0] = kCommTimeout; p.comm.status[1] = x; p.comm.status[2] = bad_src; p.comm.status[3] = epoch;
+        }
+        store_out(x, r, d, o_norm, lse2);
+      }
+      named_bar_sync(1, kSmx);
+      if (tid == 0 && t_publish != 0) {
+        const uint64_t t_done = globaltimer_ns();
+        atomicMax(p.comm.status + 10, (uint32_t)min((unsigned long long)(t_got - t_publish), 0xffffffffull));
+        atomicMax(p.comm.status + 11, (uint32_t)min((unsigned long long)(t_done - t_publish), 0xffffffffull));
+        atomicMax(p.comm.status + 12, (uint32_t)min((unsigned long long)(t_publish - t_cta0), 0xffffffffull));
+      }
+    };
+
+    int it = 0;
+    for (int t = t_lo; t < t_hi;) {
+      int x, j0, n, tn;
+      next_segment(t, x, j0, n, tn);
+      const int b = x / p.Hkv, h = x - b * p.Hkv;
+      // ---- stage the packed Q tile of head x: thread r writes row r (global 16-byte loads -> swizzled smem)
+      if (row_valid) {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.q) + (long long)b * p.q_sb +
+                                                          (long long)(h * p.G + g_row) * p.q_sh + (long long)i_row * p.q_ss);
+#pragma unroll
+        for (int ch = 0; ch < D / 8; ++ch)
+          *reinterpret_cast<uint4*>(q_s + (ch >> 3) * SM::kAtomBytes + row * 128 + (((ch & 7) ^ (row & 7)) << 4)) = __ldg(src + ch);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(q_ready);
+
+      float m_used = tc_ninf(), l_sum = 0.f;
+      if (warp_active && n > 0) {
+        for (int jj = 0; jj < n; ++jj) {
+          const int i = it + jj;
+          const int n0 = (j0 + jj) * kTN;
+          mbar_wait(&s_full[i & 1], (i >> 1) & 1);
+          tc_fence_after();
+          const uint32_t s_tmem = tmem + (i & 1) * 128 + lane_addr;
+          uint32_t sr[128];
+          tmem_ld_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+          tmem_ld_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+          tmem_ld_32x32b_x32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
+          tmem_ld_32x32b_x32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
+          tmem_ld_wait();
+          const bool need_mask = (n0 + kTN > p.S) || (p.causal && (p.kv_pos0 + n0 + kTN - 1 > p.q_pos0));
+          if (need_mask) {
+            long long lim = (long long)p.S - n0 - 1;
+            if (p.causal) lim = min(lim, q_pos - p.kv_pos0 - n0);
+            const int limc = (int)max(-1LL, min(lim, 127LL));
+#pragma unroll
+            for (int c = 0; c < 128; ++c)
+              if (c > limc) sr[c] = 0xff800000u;
+          }
+          float mx8[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) mx8[u] = __uint_as_float(sr[u]);
+#pragma unroll
+          for (int c = 8; c < 128; c += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) mx8[u] = fmaxf(mx8[u], __uint_as_float(sr[c + u]));
+          }
+          const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+          const float m_new = fmaxf(m_used, mx * p.scale_log2);
+          const bool refresh = (m_new - m_used > kTcRescale) || (m_used == tc_ninf() && m_new != tc_ninf());
+          if (__any_sync(0xffffffffu, refresh)) {
+            const float alpha = refresh ? fast_exp2(m_used - m_new) : 1.f;
+            if (refresh) { l_sum *= alpha; m_used = m_new; }
+            if (jj > 0) {
+              mbar_wait(&pv_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
+              tc_fence_after();
+#pragma unroll
+              for (int c0 = 0; c0 < D; c0 += 32) {
+                uint32_t orow[32];
+                tmem_ld_32x32b_x32(tmem_o + lane_addr + c0, orow);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < 32; ++u) orow[u] = __float_as_uint(__uint_as_float(orow[u]) * alpha);
+                tmem_st_32x32b_x32(tmem_o + lane_addr + c0, orow);
+              }
+            }
+          }
+          const float neg_m = (m_used == tc_ninf()) ? 0.f : -m_used;
+          float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          uint32_t pk[64];
+#pragma unroll
+          for (int c = 0; c < 128; c += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c + u]), p.scale_log2, neg_m));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + u + 1]), p.scale_log2, neg_m));
+              ls[u] += p0; ls[u + 1] += p1;
+              pk[(c + u) >> 1] = tc_pack2<BF16>(p0, p1);
+            }
+          }
+          l_sum += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
+          tmem_st_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+          tmem_st_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[i & 1]);
+        }
+      }
+      // ---- segment epilogue: (O, m, l) of the valid rows -> CTA partial in the workspace
+      const int first_cta = tc_cta_of_tile(p, x * p.tph);
+      const int nparts = tc_cta_of_tile(p, (x + 1) * p.tph - 1) - first_cta + 1;
+      float* my_part = p.part + ((size_t)x * p.max_parts + (cta - first_cta)) * (size_t)(R * (D + 4));
+      if (warp_active) {
+        if (n > 0) {
+          const int il = it + n - 1;
+          mbar_wait(&pv_done[il & 1], (il >> 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < D; c0 += 32) {
+          uint32_t orow[32];
+          if (n > 0) {
+            tmem_ld_32x32b_x32(tmem_o + lane_addr + c0, orow);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) orow[u] = 0u;
+          }
+          if (row_valid) {
+            float4* dst = reinterpret_cast<float4*>(my_part + row * (D + 4) + c0);
+#pragma unroll
+            for (int u = 0; u < 32; u += 4)
+              __stcg(dst + (u >> 2), make_float4(__uint_as_float(orow[u]), __uint_as_float(orow[u + 1]), __uint_as_float(orow[u + 2]),
+                                                 __uint_as_float(orow[u + 3])));
+          }
+        }
+        if (row_valid) { __stcg(my_part + row * (D + 4) + D, m_used); __stcg(my_part + row * (D + 4) + D + 1, l_sum); }
+        tc_fence_before();
+      }
+      it += n;
+      __threadfence();
+      named_bar_sync(1, kSmx);
+      if (tid == 0) s_misc[0] = (int)atomicAdd(&p.tickets[x], 1u);
+      named_bar_sync(1, kSmx);
+      if (s_misc[0] == nparts - 1) {
+        __threadfence();
+        if (tid == 0) p.tickets[x] = 0;
+        const float* parts = p.part + (size_t)x * p.max_parts * (size_t)(R * (D + 4));
+        for (int idx = tid; idx < R * D; idx += kSmx) {
+          const int r = idx / D, d = idx - r * D;
+          float M = tc_ninf();
+          for (int qi = 0; qi < nparts; ++qi) M = fmaxf(M, __ldcg(parts + (size_t)qi * (R * (D + 4)) + r * (D + 4) + D));
+          const float Ms = (M == tc_ninf()) ? 0.f : M;
+          float acc = 0.f, Lsum = 0.f;
+          for (int qi = 0; qi < nparts; ++qi) {
+            const float* pp = parts + (size_t)qi * (R * (D + 4)) + r * (D + 4);
+            const float sc = fast_exp2(__ldcg(pp + D) - Ms);
+            acc = fmaf(__ldcg(pp + d), sc, acc);
+            Lsum = fmaf(__ldcg(pp + D + 1), sc, Lsum);
+          }
+          const float o_norm = Lsum > 0.f ? acc / Lsum : 0.f;
+          const float lse2 = Lsum > 0.f ? Ms + fast_log2(Lsum) : tc_ninf();
+          if (world == 1) {
+            store_out(x, r, d, o_norm, lse2);
+          } else if (!p.comm.skip_publish) {
+            for (int dst = 0; dst < world; ++dst) {
+              uint2* wp = word_ptr(dst, p.comm.rank, x) + r * (D + 2);
+              ll_store(wp + d, o_norm);
+              if (d == 0) ll_store(wp + D, lse2);
+            }
+          }
+        }
+        if (world > 1) {
+          if (tid == 0) {
+            t_publish = globaltimer_ns();
+            const int np = s_misc[1];
+            if (np < kTcMaxPending) { pending[np] = x; s_misc[1] = np + 1; }
+            else s_misc[2] = x + 1;
+          }
+          named_bar_sync(1, kSmx);
+          if (s_misc[2] != 0) {
+            named_bar_sync(1, kSmx);
+            if (tid == 0) s_misc[2] = 0;
+            combine_ranks(x);
+          }
+        }
+      }
+      named_bar_sync(1, kSmx);  // Q smem / s_misc reuse by the next segment
+      t = tn;
+    }
+    if (world > 1) {
+      named_bar_sync(1, kSmx);
+      const int np = s_misc[1];
+      for (int u = 0; u < np; ++u) combine_ranks(pending[u]);
+      if (tid == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(&p.tickets[BH], 1u);
+        if (done == gridDim.x - 1) {
+          p.tickets[BH] = 0;
+          __threadfence();
+          *reinterpret_cast<volatile uint32_t*>(p.comm.epoch) = epoch;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc<512>(tmem); }
+}
+
+inline CommCtx tc_device_ctx(const CommCtxHost& h) {
+  CommCtx c;
+  c.rank = h.rank;
+  c.world = h.world;
+  for (int i = 0; i < kMaxWorld; ++i) {
+    c.data[i] = reinterpret_cast<float*>(h.data[i]);
+    c.flags[i] = reinterpret_cast<uint32_t*>(h.flags[i]);
+  }
+  c.epoch = reinterpret_cast<uint32_t*>(h.epoch);
+  c.status = reinterpret_cast<uint32_t*>(h.status);
+  c.timeout_ns = h.timeout_ns;
+  c.skip_publish = h.skip_publish;
+  return c;
+}
+
+template <int D, bool BF16>
+void launch_tc(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeTcParams& p, int grid, cudaStream_t stream) {
+  auto kern = decode_tc_kernel<D, BF16>;
+  static bool configured = false;
+  if (!configured) {
+    TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<D>::kTotal));
+    configured = true;
+  }
+  kern<<<grid, kTcThreads, TcSmem<D>::kTotal, stream>>>(kmap, vmap, p);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+void decode_tc_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, int* rows, size_t* part_floats,
+                    size_t* comm_bytes) {
+  const int BH = s.B * s.Hkv;
+  const int tph = (s.S + kTN - 1) / kTN;
+  const long long total = (long long)BH * tph;
+  const int g = (int)std::min<long long>(nsm, std::max<long long>(total, 1));
+  const int q = (int)(total / g);
+  int mp = std::min(g, (tph + std::max(q, 1) - 1) / std::max(q, 1) + 1);
+  mp = std::max(mp, 1);
+  const int R = (s.Hq / s.Hkv) * s.Sq;
+  *grid = g;
+  *max_parts = mp;
+  *rows = R;
+  *part_floats = (size_t)BH * mp * R * (s.D + 4);
+  *comm_bytes = (size_t)2 * kMaxWorldHost * BH * R * (s.D + 2) * 8;
+}
+
+void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
+                      uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream) {
+  if (s.D != 64 && s.D != 128) throw std::runtime_error("decode_tc: head_dim must be 64 or 128");
+  if (s.Hq % s.Hkv != 0) throw std::runtime_error("decode_tc: Hq must be a multiple of Hkv");
+  const int G = s.Hq / s.Hkv;
+  const int R = G * s.Sq;
+  if (R > kTM) throw std::runtime_error("decode_tc: (Hq / Hkv) * Sq must be <= 128");
+  if (s.S <= 0) throw std::runtime_error("decode_tc: empty KV shard");
+  int grid, max_parts, rows;
+  size_t pf, cb;
+  decode_tc_plan(s, nsm, &grid, &max_parts, &rows, &pf, &cb);
+  if (comm.world > 1) {
+    const size_t need = (size_t)2 * comm.world * s.B * s.Hkv * R * (s.D + 2) * 8;
+    if (need > comm.data_bytes) throw std::runtime_error("decode_tc: symmetric buffer too small for this problem");
+  }
+  CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, s.D, s.k_sb, s.k_sh, s.k_ss, 64, kTN, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap vmap = make_tmap_bhsd(v, 2, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 64, kTN, CU_TENSOR_MAP_SWIZZLE_128B);
+  DecodeTcParams p;
+  p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
+  p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S; p.R = R;
+  p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
+  p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;
+  p.q_sb = s.q_sb; p.q_sh = s.q_sh; p.q_ss = s.q_ss; p.o_sb = s.o_sb; p.o_sh = s.o_sh; p.o_ss = s.o_ss;
+  p.tph = (s.S + kTN - 1) / kTN;
+  p.total_tiles = s.B * s.Hkv * p.tph;
+  p.tiles_q = p.total_tiles / grid;
+  p.tiles_rem = p.total_tiles % grid;
+  p.max_parts = max_parts;
+  p.jvis = p.tph;
+  if (s.causal) {
+    const long long last = s.q_pos0 + s.Sq - 1 - s.kv_pos0;  // last visible local key index
+    p.jvis = (int)std::max<long long>(0, std::min<long long>(p.tph, last < 0 ? 0 : last / kTN + 1));
+  }
+  p.comm = tc_device_ctx(comm);
+  if (s.D == 128) {
+    if (s.is_bf16) launch_tc<128, true>(kmap, vmap, p, grid, stream); else launch_tc<128, false>(kmap, vmap, p, grid, stream);
+  } else {
+    if (s.is_bf16) launch_tc<64, true>(kmap, vmap, p, grid, stream); else launch_tc<64, false>(kmap, vmap, p, grid, stream);
+  }
+}
+
+}  // namespace ta

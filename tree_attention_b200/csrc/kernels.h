@@ -46,6 +46,12 @@ void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const 
 // kscale/vscale != null: K/V are block-scaled fp8 (e4m3 bytes, D = 128) and the scales are (B, Hkv, S) words of
 // four UE8M0 exponents (one per 32 elements); strides in AttnShape are then in BYTES == elements.
 
+// ---- tensor-core decode: the R = (Hq/Hkv) x Sq <= 128 query rows of a KV head packed into one tcgen05 tile ----
+void decode_tc_plan(const AttnShape& s, int num_sms, int* grid, int* max_parts, int* rows, size_t* part_floats,
+                    size_t* comm_bytes);
+void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
+                      uint32_t* tickets, const CommCtxHost& comm, int num_sms, cudaStream_t stream);
+
 // ---- stand-alone combine of W per-rank partials (o fp32 normalised, lse natural log) ----
 // local: o_part (rows, D) fp32 + lse_part (rows); result written to out (dtype of `is_bf16`/fp16/fp32)
 // mode 0: one-shot push (every rank publishes to every peer, merges all W in rank order)

@@ -117,7 +117,7 @@ def attention_fwd_fused(
     per_row = 2 * world * b * hq * (d * 2 + 4)
     chunk = max(128, min(sq, (cap // per_row) // 128 * 128))
     data, flags = C.attn_fwd_comm_bytes(b, hq, min(chunk, sq), d, world)
-    reg = symm.get_region("fwd", int(data), int(flags), group)
+    reg = symm.get_region("fwd", int(data), int(flags), group, layout=(b, hq, min(chunk, sq), d))
     out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
     lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
     if chunk >= sq:
@@ -125,6 +125,7 @@ def attention_fwd_fused(
         return o_c, l_c
     for s0 in range(0, sq, chunk):
         s1 = min(sq, s0 + chunk)
+        reg = symm.get_region("fwd", int(data), int(flags), group, layout=(b, hq, s1 - s0, d))  # fences a ragged tail
         o_c, l_c = attention_fwd(q[:, :, s0:s1], k, v, softmax_scale, causal, q_pos0 + s0, kv_pos0,
                                  out=out[:, :, s0:s1], comm=reg.comm)
         lse[:, :, s0:s1] = l_c

@@ -21,7 +21,7 @@ from . import reference as ref
 
 _WS: Dict[tuple, Dict[str, torch.Tensor]] = {}
 
-DECODE_MAX_ROWS = 16  # Sq * (Hq / Hkv) handled by the streaming decode kernel (4 rows per pass)
+DECODE_MAX_ROWS = 128  # Sq * (Hq / Hkv): 1 row -> CUDA-core streaming kernel, 2..128 rows -> tcgen05 packed-tile kernel
 
 
 def _as_bhsd(x: torch.Tensor) -> torch.Tensor:
@@ -63,13 +63,36 @@ def decode_attention(
     out: Optional[torch.Tensor] = None,
     lse: Optional[torch.Tensor] = None,
     return_lse: bool = True,
+    impl: str = "auto",
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Launch the fused streaming decode kernel.  With ``comm`` (a ``_C.Comm``) the kernel also performs
-    the cross-GPU tree combine and ``out``/``lse`` are the GLOBAL results, identical on every rank."""
+    the cross-GPU tree combine and ``out``/``lse`` are the GLOBAL results, identical on every rank.
+
+    ``impl``: ``"simt"`` (CUDA-core math; HBM-bound for one query row per KV head), ``"tc"`` (tcgen05: the
+    (Hq/Hkv) x Sq rows of a KV head packed into one MMA tile; stays HBM-bound for GQA / multi-token decode),
+    ``"auto"`` = simt for a single row, tc otherwise."""
+    import os
+
     C = _build.load()
     q, k, v = _as_bhsd(q), _as_bhsd(k), _as_bhsd(v)
     b, hq, sq, d = q.shape
     hkv, s = k.shape[1], k.shape[2]
+    rows_total = (hq // hkv) * sq
+    impl = os.environ.get("TREE_ATTN_DECODE_IMPL", impl)
+    if impl == "auto":
+        impl = "simt" if rows_total == 1 else "tc"
+    if impl == "tc":
+        if q.stride(2) % 8 != 0 and sq > 1:
+            q = q.contiguous()
+        grid, max_parts, rows, part_floats, _ = C.decode_tc_plan(b, hq, hkv, sq, s, d)
+        ws = _workspace(q.device, "decode_tc", part_floats, b * hkv + 2)
+        if out is None:
+            out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
+        if lse is None and return_lse:
+            lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
+        C.decode_tc_fwd(q, k, v, out, lse, ws["part"], ws["tickets"], comm, float(softmax_scale), bool(causal),
+                        int(q_pos0), int(kv_pos0))
+        return out, lse
     grid, max_parts, rows, part_floats, _, _ = C.decode_plan(b, hq, hkv, sq, s, d)
     ws = _workspace(q.device, "decode", part_floats, b * hkv + 2)
     if out is None:
@@ -107,9 +130,8 @@ def decode_attention_mxfp8(
 
 
 def decode_comm_bytes(b: int, hq: int, hkv: int, sq: int, s: int, d: int, world: int) -> Tuple[int, int]:
-    """(data_bytes, flag_bytes) the decode family needs in symmetric memory."""
-    rows = min(4, max(1, (hq // hkv) * sq))
-    rows = 4 if rows >= 4 else (2 if rows >= 2 else 1)
+    """(data_bytes, flag_bytes) the decode family needs in symmetric memory (covers both decode kernels)."""
+    rows = max(4, (hq // hkv) * sq)
     data = 2 * world * b * hkv * rows * (d + 2) * 8   # {fp32 value, epoch tag} words
     flags = 4096
     return data, flags

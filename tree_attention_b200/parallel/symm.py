@@ -59,6 +59,7 @@ class SymmRegion:
     peer_ptrs: List[int]
     comm: object  # _C.Comm
     keepalive: list = field(default_factory=list)
+    layout: object = None  # slot layout of the last launch (see get_region)
 
     def status(self) -> Tuple[int, int, int, int]:
         C = _build.load()
@@ -138,12 +139,23 @@ def get_region(
     flag_bytes: int,
     group=None,
     timeout_s: Optional[float] = None,
+    layout=None,
 ) -> SymmRegion:
-    """Return (allocating or growing collectively if needed) the symmetric region of ``family``."""
+    """Return (allocating or growing collectively if needed) the symmetric region of ``family``.
+
+    ``layout`` identifies how the next kernel will carve the region into slots (e.g. the problem shape).  The
+    parity double-buffering argument assumes consecutive launches of a family use the SAME carving; when the
+    layout changes, a slow rank could still be reading the previous launch's slots under the old carving, so the
+    change is fenced with a device sync + group barrier (only on shape changes, never in a steady-state loop)."""
     assert dist.is_initialized(), "symmetric memory needs an initialised process group"
     key = (family, _group_key(group))
     reg = _REGIONS.get(key)
     if reg is not None and reg.data_bytes >= data_bytes and reg.flag_bytes >= flag_bytes:
+        if layout is not None and reg.layout is not None and layout != reg.layout:
+            torch.cuda.synchronize()
+            dist.barrier(group)
+        if layout is not None:
+            reg.layout = layout
         return reg
     if reg is not None:
         release(family, group)
@@ -165,7 +177,7 @@ def get_region(
         [p + HEADER_BYTES for p in ptrs],
         ptr, ptr + STATUS_OFFSET, data_bytes, flag_bytes, tmo,
     )
-    reg = SymmRegion(family, group, rank, world, flag_bytes, data_bytes, total, provider, ptr, ptrs, comm, keep)
+    reg = SymmRegion(family, group, rank, world, flag_bytes, data_bytes, total, provider, ptr, ptrs, comm, keep, layout)
     _REGIONS[key] = reg
     logger.debug(f"symm region {family!r}: {total >> 10} KiB per rank via {provider}")
     return reg

@@ -142,7 +142,8 @@ def combine_partials(
 
         rounds = max(1, int(math.ceil(math.log2(world))))
         slots = world if mode == 0 else rounds
-        reg = symm.get_region("combine", 2 * slots * rows * (d + 4) * 4, 2 * slots * nchunks * 4, group)
+        reg = symm.get_region("combine", 2 * slots * rows * (d + 4) * 4, 2 * slots * nchunks * 4, group,
+                              layout=(mode, rows, d))
         o32 = o.float().contiguous()
         lse32 = lse.float().contiguous()
         out = torch.empty(o.shape, dtype=out_dtype if out_dtype in (torch.float32, torch.bfloat16, torch.float16)
@@ -179,9 +180,9 @@ def allreduce_sum(x: torch.Tensor, group=None, backend: str = "auto") -> torch.T
         chunk = max(4096, (cap // 16) // 4096 * 4096)  # floats per launch: 16 B of symmetric memory per float
         n = flat_x.numel()
         data, flags = C.symm_allreduce_sizes(min(n, chunk), world)
-        reg = symm.get_region("reduce", int(data), int(flags), group)
         for s0 in range(0, n, chunk):
             s1 = min(n, s0 + chunk)
+            reg = symm.get_region("reduce", int(data), int(flags), group, layout=(s1 - s0,))
             C.symm_allreduce(flat_x[s0:s1], flat_y[s0:s1], reg.comm)
         return y
     y = x.clone()
@@ -244,7 +245,9 @@ def tree_attention(
         if local_ops.decode_eligible(q, k):
             b, hq, sq, d = q.shape
             data, flags = local_ops.decode_comm_bytes(b, hq, k.shape[1], sq, s_local, d, world)
-            reg = symm.get_region("decode", data, flags, group)
+            rows = (hq // k.shape[1]) * sq
+            reg = symm.get_region("decode" if rows == 1 else "decode_tc", data, flags, group,
+                                  layout=(b, hq, k.shape[1], sq, d))
             o, lse = local_ops.decode_attention(q, k, v, scale, causal, q_pos0, kv_pos0, comm=reg.comm,
                                                 return_lse=return_lse)
         else:
@@ -279,7 +282,7 @@ def _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset,
         if world > 1:
             b, hq, sq, d = q.shape
             data, flags = local_ops.decode_comm_bytes(b, hq, k.shape[1], sq, s_local, d, world)
-            comm = symm.get_region("decode", data, flags, group).comm
+            comm = symm.get_region("decode", data, flags, group, layout=("mx", b, hq, k.shape[1], sq, d)).comm
         o, lse = local_ops.decode_attention_mxfp8(q, k, v, scale, causal, q_pos0, kv_pos0, comm=comm,
                                                   return_lse=return_lse)
         return (o, lse) if return_lse else o
