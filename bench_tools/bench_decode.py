@@ -3,7 +3,7 @@ import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tree_attention_b200.ops import local as L
-from tree_attention_b200.ops.quant import MXFP8Tensor
+from tree_attention_b200.ops.quant import FP8ChannelTensor, MXFP8Tensor
 from tree_attention_b200.utils.timing import time_cuda
 
 ap = argparse.ArgumentParser()
@@ -19,11 +19,15 @@ for s in a.seq:
     kvs = [(torch.randn(1, hkv, s, 128, device="cuda", generator=g).bfloat16(), torch.randn(1, hkv, s, 128, device="cuda", generator=g).bfloat16())
            for _ in range(max(1, min(8, (600 << 20) // (4 * hkv * s * 128))))]
     mx = [(MXFP8Tensor.from_float(k), MXFP8Tensor.from_float(v)) for k, v in kvs]
+    c8 = [(FP8ChannelTensor.from_float(k), FP8ChannelTensor.from_float(v)) for k, v in kvs]
     n = len(kvs)
     i = [0]
     def f16():
         i[0] += 1
         return L.decode_attention(q, *kvs[i[0] % n], 0.088, return_lse=False, impl="simt")
+    def fc8():
+        i[0] += 1
+        return L.decode_attention_fp8(q, *c8[i[0] % n], 0.088, return_lse=False)
     def ftc():
         i[0] += 1
         return L.decode_attention(q, *kvs[i[0] % n], 0.088, return_lse=False, impl="tc")
@@ -33,8 +37,11 @@ for s in a.seq:
     t16 = time_cuda(f16, a.steps, 10)["median_ms"]
     t8 = time_cuda(f8, a.steps, 10)["median_ms"]
     ttc = time_cuda(ftc, a.steps, 10)["median_ms"]
+    tc8 = time_cuda(fc8, a.steps, 10)["median_ms"]
+    bc8 = 2 * hkv * s * 128
     b16 = 2 * hkv * s * 128 * 2
     b8 = 2 * hkv * s * (128 + 4)
     print(json.dumps({"seq": s, "heads": a.heads, "kv_heads": hkv, "bf16_us": round(t16 * 1e3, 1), "bf16_gbs": round(b16 / t16 / 1e6, 0),
                       "bf16_tcgen05_us": round(ttc * 1e3, 1), "bf16_tcgen05_gbs": round(b16 / ttc / 1e6, 0),
+                      "fp8_tcgen05_us": round(tc8 * 1e3, 1), "fp8_tcgen05_gbs": round(bc8 / tc8 / 1e6, 0),
                       "mxfp8_us": round(t8 * 1e3, 1), "mxfp8_gbs": round(b8 / t8 / 1e6, 0), "speedup": round(t16 / t8, 2)}), flush=True)

@@ -61,3 +61,44 @@ def test_public_api_with_mxfp8_cache():
     out = ta.tree_attention(q, kq, vq)
     exp, _ = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize())
     assert (out.float() - exp).abs().max().item() < 2e-2
+
+
+FP8_CASES = [
+    (1, 32, 32, 1, 4096, False),
+    (2, 8, 8, 1, 300, False),
+    (1, 32, 8, 1, 8192, False),     # GQA -> 4 packed rows
+    (1, 8, 2, 4, 2000, True),       # 16 packed rows, causal
+    (1, 4, 4, 1, 70000, False),
+]
+
+
+@pytest.mark.parametrize("case", FP8_CASES, ids=[str(i) for i in range(len(FP8_CASES))])
+def test_fp8_channel_tcgen05_decode_matches_dequantised_oracle(case):
+    """kind::f8f6f4 decode: per-channel-scaled e4m3 K/V, q quantised per row and P per element inside the kernel."""
+    b, hq, hkv, sq, s, causal = case
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q = torch.randn(b, hq, sq, 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(b, hkv, s, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(b, hkv, s, 128, device="cuda", generator=g).bfloat16()
+    kq, vq = quant.FP8ChannelTensor.from_float(k), quant.FP8ChannelTensor.from_float(v)
+    scale = 128 ** -0.5
+    out, lse = L.decode_attention_fp8(q, kq, vq, scale, causal, s - sq, 0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    o_ref, l_ref = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize(), scale, causal, s - sq, 0, torch.float32, block=16384)
+    # q and P are additionally rounded to e4m3 inside the kernel: tolerance is fp8-level
+    assert (out.float() - o_ref).abs().max().item() < 6e-2
+    assert (lse - l_ref).abs().max().item() < 6e-2
+    o_full, _ = ref.attention_partial_ref(q, k, v, scale, causal, s - sq, 0, torch.float32, block=16384)
+    assert (out.float() - o_full).abs().max().item() < 0.12
+
+
+def test_public_api_with_fp8_channel_cache():
+    g = torch.Generator(device="cuda").manual_seed(12)
+    q = torch.randn(1, 32, 1, 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(1, 8, 6000, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(1, 8, 6000, 128, device="cuda", generator=g).bfloat16()
+    kq, vq = quant.FP8ChannelTensor.from_float(k), quant.FP8ChannelTensor.from_float(v)
+    out = ta.tree_attention(q, kq, vq)
+    exp, _ = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize())
+    assert (out.float() - exp).abs().max().item() < 6e-2

@@ -191,6 +191,40 @@ void decode_tc_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
                        reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream());
 }
 
+// per-channel-scaled fp8 KV cache on the tensor cores: k8/v8 uint8 (B, Hkv, S, 128) e4m3, ksc/vsc fp32 (B, Hkv, 128)
+void decode_tc_fwd8(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& ksc,
+                    const at::Tensor& vsc, at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part,
+                    at::Tensor& tickets, py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(q.dim() == 4 && k8.dim() == 4 && v8.dim() == 4 && out.sizes() == q.sizes(), "expected (B, H, S, D) tensors");
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
+  TORCH_CHECK(out.scalar_type() == q.scalar_type() && q.stride(3) == 1 && out.stride(3) == 1);
+  TORCH_CHECK(k8.scalar_type() == at::kByte && v8.scalar_type() == at::kByte && k8.stride(3) == 1 && v8.stride(3) == 1);
+  TORCH_CHECK(k8.sizes() == v8.sizes() && k8.size(3) == 128 && q.size(3) == 128, "fp8 decode needs head_dim 128");
+  TORCH_CHECK(ksc.scalar_type() == at::kFloat && vsc.scalar_type() == at::kFloat && ksc.is_contiguous() && vsc.is_contiguous() &&
+                  ksc.numel() == k8.size(0) * k8.size(1) * 128 && vsc.numel() == ksc.numel(), "scales must be fp32 (B, Hkv, 128)");
+  TORCH_CHECK(q.stride(2) % 8 == 0 || q.size(2) == 1, "q rows must be 16-byte aligned");
+  AttnShape s;
+  s.B = (int)q.size(0); s.Hq = (int)q.size(1); s.Sq = (int)q.size(2); s.D = 128;
+  s.Hkv = (int)k8.size(1); s.S = (int)k8.size(2);
+  s.is_bf16 = q.scalar_type() == at::kBFloat16;
+  s.softmax_scale = (float)scale; s.causal = causal; s.q_pos0 = q_pos0; s.kv_pos0 = kv_pos0;
+  s.q_sb = q.stride(0); s.q_sh = q.stride(1); s.q_ss = q.stride(2);
+  s.k_sb = k8.stride(0); s.k_sh = k8.stride(1); s.k_ss = k8.stride(2);
+  s.v_sb = v8.stride(0); s.v_sh = v8.stride(1); s.v_ss = v8.stride(2);
+  s.o_sb = out.stride(0); s.o_sh = out.stride(1); s.o_ss = out.stride(2);
+  int grid, mp, R;
+  size_t pf, cb;
+  ta::decode_tc_plan(s, ta::num_sms(), &grid, &mp, &R, &pf, &cb);
+  TORCH_CHECK((size_t)part.numel() >= pf && tickets.numel() >= s.B * s.Hkv + 2, "workspace too small");
+  float* lse_p = lse.has_value() ? lse->data_ptr<float>() : nullptr;
+  CommCtxHost c;
+  if (!comm.is_none()) c = comm.cast<Comm&>().h;
+  ta::decode_tc_launch(s, q.data_ptr(), k8.data_ptr(), v8.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
+                       reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream(),
+                       ksc.data_ptr<float>(), vsc.data_ptr<float>());
+}
+
 // block-scaled fp8 KV cache decode: k8/v8 uint8 (B, Hkv, S, 128) e4m3, ks/vs uint8 (B, Hkv, S, 4) UE8M0
 void decode_fwd_mx(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& ks,
                    const at::Tensor& vs, at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part,
@@ -336,6 +370,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_fwd_mx", &decode_fwd_mx);
   m.def("decode_tc_plan", &decode_tc_plan);
   m.def("decode_tc_fwd", &decode_tc_fwd);
+  m.def("decode_tc_fwd8", &decode_tc_fwd8);
   m.def("quant_mxfp8", &quant_mxfp8);
   m.def("dequant_mxfp8", &dequant_mxfp8);
   m.def("attn_fwd", &attn_fwd);

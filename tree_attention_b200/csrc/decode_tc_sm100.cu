@@ -33,6 +33,8 @@ struct DecodeTcParams {
   float* lse;
   float* part;
   uint32_t* tickets;
+  const float* kscale;  // KV8: per-channel scales (B, Hkv, D) of the e4m3 K / V shards
+  const float* vscale;
   int B, Hq, Hkv, G, Sq, S, R;
   float scale_log2;
   int causal;
@@ -42,12 +44,15 @@ struct DecodeTcParams {
   CommCtx comm;
 };
 
-template <int D>
+// KV8: K, V and the staged Q are e4m3 (1 byte): a 128-row tile of D = 128 is ONE 128B-swizzle atom
+template <int D, bool KV8>
 struct TcSmem {
-  static constexpr int kAtoms = D / 64;
-  static constexpr int kTileBytes = 128 * D * 2;
+  static constexpr int kElem = KV8 ? 1 : 2;
+  static constexpr int kAtoms = D * kElem / 128;
+  static constexpr int kTileBytes = 128 * D * kElem;
   static constexpr int kAtomBytes = 128 * 128;
-  static constexpr size_t kTotal = 1024 + size_t(1 + 2 * kTcStages) * kTileBytes + 512;
+  static constexpr int kStages = KV8 ? 6 : kTcStages;
+  static constexpr size_t kTotal = 1024 + size_t(1 + 2 * kStages) * kTileBytes + 512 + (KV8 ? 2 * D * 4 : 0);
 };
 
 __device__ __forceinline__ float tc_ninf() { return __int_as_float(0xff800000); }
@@ -67,12 +72,13 @@ __device__ __forceinline__ uint16_t tc_to16(float f) {
   else return __half_as_ushort(__float2half_rn(f));
 }
 
-template <int D, bool BF16>
+template <int D, bool BF16, bool KV8>
 __global__ void __launch_bounds__(kTcThreads, 1)
 decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
                  const DecodeTcParams p) {
-  using SM = TcSmem<D>;
-  constexpr int NS = kTcStages;
+  using SM = TcSmem<D, KV8>;
+  constexpr int NS = SM::kStages;
+  constexpr int EPA = 128 / SM::kElem;  // elements per 128-byte atom row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_s = smem;
@@ -90,6 +96,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
   int* s_misc = reinterpret_cast<int*>(tmem_slot + 2);  // [0] ticket, [1] n_pending, [2] inline-combine head+1
   int* pending = s_misc + 4;                            // [kTcMaxPending]
+  [[maybe_unused]] float* ch_scale = reinterpret_cast<float*>(pending + kTcMaxPending);  // KV8: [2][D] K / V channel scales
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x;
@@ -110,7 +117,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
   if (warp == 5) tmem_alloc<512>(tmem_slot);
   // zero the whole Q tile once: rows >= R stay zero padding, rows < R are rewritten per head segment
   if (warp < 4) {
-    for (int c = tid; c < kTM * (D / 8); c += kSmx) reinterpret_cast<uint4*>(q_s)[c] = make_uint4(0, 0, 0, 0);
+    for (int c = tid; c < SM::kTileBytes / 16; c += kSmx) reinterpret_cast<uint4*>(q_s)[c] = make_uint4(0, 0, 0, 0);
   }
   tc_fence_before();
   __syncthreads();
@@ -148,12 +155,12 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
           mbar_arrive_expect_tx(&k_full[st], SM::kTileBytes);
 #pragma unroll
           for (int a = 0; a < SM::kAtoms; ++a)
-            tma_load_4d(k_s + st * SM::kTileBytes + a * SM::kAtomBytes, &kmap, &k_full[st], a * 64, (j0 + jj) * kTN, h, b);
+            tma_load_4d(k_s + st * SM::kTileBytes + a * SM::kAtomBytes, &kmap, &k_full[st], a * EPA, (j0 + jj) * kTN, h, b);
           mbar_wait(&v_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&v_full[st], SM::kTileBytes);
 #pragma unroll
           for (int a = 0; a < SM::kAtoms; ++a)
-            tma_load_4d(v_s + st * SM::kTileBytes + a * SM::kAtomBytes, &vmap, &v_full[st], a * 64, (j0 + jj) * kTN, h, b);
+            tma_load_4d(v_s + st * SM::kTileBytes + a * SM::kAtomBytes, &vmap, &v_full[st], a * EPA, (j0 + jj) * kTN, h, b);
         }
         t = tn;
       }
@@ -161,9 +168,10 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
   } else if (warp == 5) {
     // =============================== MMA issuer =================================================
     if (lane == 0) {
-      constexpr uint32_t fmt = BF16 ? 1u : 0u;
+      constexpr uint32_t fmt = KV8 ? 0u : (BF16 ? 1u : 0u);  // kind::f8f6f4: 0 = e4m3 ; kind::f16: 0 = f16, 1 = bf16
       constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kTM, kTN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc(fmt, fmt, kTM, D, 0, 1);
+      constexpr int KSTEP = 32 / SM::kElem;     // elements per MMA along K (32 bytes)
       const uint32_t q_addr = smem_u32(q_s);
       auto issue_qk = [&](int i) {
         const int st = i % NS;
@@ -172,10 +180,14 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
         const uint32_t k_addr = smem_u32(k_s + st * SM::kTileBytes);
         const uint32_t d_tmem = tmem + (i & 1) * 128;
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
+        for (int kk = 0; kk < D / KSTEP; ++kk) {
           const uint32_t off = (kk / 4) * SM::kAtomBytes + (kk % 4) * 32;
-          umma_ss_f16(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
-                      idesc_qk, kk > 0 ? 1u : 0u);
+          if constexpr (KV8)
+            umma_ss_f8(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
+                       idesc_qk, kk > 0 ? 1u : 0u);
+          else
+            umma_ss_f16(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
+                        idesc_qk, kk > 0 ? 1u : 0u);
         }
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[i & 1]);
@@ -198,9 +210,15 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
             const uint32_t v_addr = smem_u32(v_s + st * SM::kTileBytes);
             const uint32_t p_tmem = tmem + (i & 1) * 128;
 #pragma unroll
-            for (int kk = 0; kk < kTN / 16; ++kk)
-              umma_ts_f16(tmem_o, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * 2048, kTN * 128, 1024), idesc_pv,
-                          (jj > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < kTN / KSTEP; ++kk) {
+              // one MMA consumes 32 bytes of P per row (8 TMEM columns) and KSTEP rows of V (KSTEP x 128 B)
+              if constexpr (KV8)
+                umma_ts_f8(tmem_o, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * (KSTEP * 128), kTN * 128, 1024), idesc_pv,
+                           (jj > 0 || kk > 0) ? 1u : 0u);
+              else
+                umma_ts_f16(tmem_o, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * (KSTEP * 128), kTN * 128, 1024), idesc_pv,
+                            (jj > 0 || kk > 0) ? 1u : 0u);
+            }
             umma_commit(&v_empty[st]);
             umma_commit(&pv_done[i & 1]);
           }
@@ -298,15 +316,54 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
       next_segment(t, x, j0, n, tn);
       const int b = x / p.Hkv, h = x - b * p.Hkv;
       // ---- stage the packed Q tile of head x: thread r writes row r (global 16-byte loads -> swizzled smem)
+      [[maybe_unused]] float q_scale = 1.f;  // KV8: per-row scale of the e4m3 query
+      if constexpr (KV8) {
+        // per-channel scales of this head's K and V shards; K's are folded into q before it is quantised
+        if (tid < D) {
+          ch_scale[tid] = __ldg(p.kscale + (long long)x * D + tid);
+          ch_scale[D + tid] = __ldg(p.vscale + (long long)x * D + tid);
+        }
+        named_bar_sync(1, kSmx);
+      }
       if (row_valid) {
         const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(p.q) + (long long)b * p.q_sb +
                                                           (long long)(h * p.G + g_row) * p.q_sh + (long long)i_row * p.q_ss);
+        if constexpr (!KV8) {
 #pragma unroll
-        for (int ch = 0; ch < D / 8; ++ch)
-          *reinterpret_cast<uint4*>(q_s + (ch >> 3) * SM::kAtomBytes + row * 128 + (((ch & 7) ^ (row & 7)) << 4)) = __ldg(src + ch);
+          for (int ch = 0; ch < D / 8; ++ch)
+            *reinterpret_cast<uint4*>(q_s + (ch >> 3) * SM::kAtomBytes + row * 128 + (((ch & 7) ^ (row & 7)) << 4)) = __ldg(src + ch);
+        } else {
+          float qf[D];
+          float amax = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < D / 8; ++ch) {
+            const uint4 w = __ldg(src + ch);
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              float lo, hi;
+              if constexpr (BF16) { lo = bf16lo(ws[u]); hi = bf16hi(ws[u]); } else { lo = f16lo(ws[u]); hi = f16hi(ws[u]); }
+              lo *= ch_scale[ch * 8 + 2 * u]; hi *= ch_scale[ch * 8 + 2 * u + 1];
+              qf[ch * 8 + 2 * u] = lo; qf[ch * 8 + 2 * u + 1] = hi;
+              amax = fmaxf(amax, fmaxf(fabsf(lo), fabsf(hi)));
+            }
+          }
+          q_scale = amax > 0.f ? amax * (1.f / 448.f) : 1.f;
+          const float inv = 1.f / q_scale;
+#pragma unroll
+          for (int ch = 0; ch < D / 16; ++ch) {  // 16 e4m3 per 16-byte chunk
+            uint4 w;
+            w.x = pack_e4m3x4(qf[ch * 16 + 0] * inv, qf[ch * 16 + 1] * inv, qf[ch * 16 + 2] * inv, qf[ch * 16 + 3] * inv);
+            w.y = pack_e4m3x4(qf[ch * 16 + 4] * inv, qf[ch * 16 + 5] * inv, qf[ch * 16 + 6] * inv, qf[ch * 16 + 7] * inv);
+            w.z = pack_e4m3x4(qf[ch * 16 + 8] * inv, qf[ch * 16 + 9] * inv, qf[ch * 16 + 10] * inv, qf[ch * 16 + 11] * inv);
+            w.w = pack_e4m3x4(qf[ch * 16 + 12] * inv, qf[ch * 16 + 13] * inv, qf[ch * 16 + 14] * inv, qf[ch * 16 + 15] * inv);
+            *reinterpret_cast<uint4*>(q_s + row * 128 + (((ch & 7) ^ (row & 7)) << 4)) = w;
+          }
+        }
       }
       fence_proxy_async_smem();
       mbar_arrive(q_ready);
+      const float sc_row = p.scale_log2 * q_scale;  // log2-domain softmax scale of this row
 
       float m_used = tc_ninf(), l_sum = 0.f;
       if (warp_active && n > 0) {
@@ -340,7 +397,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
             for (int u = 0; u < 8; ++u) mx8[u] = fmaxf(mx8[u], __uint_as_float(sr[c + u]));
           }
           const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-          const float m_new = fmaxf(m_used, mx * p.scale_log2);
+          const float m_new = fmaxf(m_used, mx * sc_row);
           const bool refresh = (m_new - m_used > kTcRescale) || (m_used == tc_ninf() && m_new != tc_ninf());
           if (__any_sync(0xffffffffu, refresh)) {
             const float alpha = refresh ? fast_exp2(m_used - m_new) : 1.f;
@@ -361,20 +418,34 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
           }
           const float neg_m = (m_used == tc_ninf()) ? 0.f : -m_used;
           float ls[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          uint32_t pk[64];
+          if constexpr (!KV8) {
+            uint32_t pk[64];
 #pragma unroll
-          for (int c = 0; c < 128; c += 8) {
+            for (int c = 0; c < 128; c += 8) {
 #pragma unroll
-            for (int u = 0; u < 8; u += 2) {
-              const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c + u]), p.scale_log2, neg_m));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + u + 1]), p.scale_log2, neg_m));
-              ls[u] += p0; ls[u + 1] += p1;
-              pk[(c + u) >> 1] = tc_pack2<BF16>(p0, p1);
+              for (int u = 0; u < 8; u += 2) {
+                const float p0 = fast_exp2(fmaf(__uint_as_float(sr[c + u]), sc_row, neg_m));
+                const float p1 = fast_exp2(fmaf(__uint_as_float(sr[c + u + 1]), sc_row, neg_m));
+                ls[u] += p0; ls[u + 1] += p1;
+                pk[(c + u) >> 1] = tc_pack2<BF16>(p0, p1);
+              }
             }
+            tmem_st_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+            tmem_st_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
+          } else {
+            // P <= 2^8 (lazy rescale) fits e4m3 (max 448): four probabilities per 32-bit TMEM column
+            uint32_t pk[32];
+#pragma unroll
+            for (int c = 0; c < 128; c += 8) {
+              float pv[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) { pv[u] = fast_exp2(fmaf(__uint_as_float(sr[c + u]), sc_row, neg_m)); ls[u] += pv[u]; }
+              pk[c >> 2] = pack_e4m3x4(pv[0], pv[1], pv[2], pv[3]);
+              pk[(c >> 2) + 1] = pack_e4m3x4(pv[4], pv[5], pv[6], pv[7]);
+            }
+            tmem_st_32x32b_x32(s_tmem, pk);
           }
           l_sum += ((ls[0] + ls[1]) + (ls[2] + ls[3])) + ((ls[4] + ls[5]) + (ls[6] + ls[7]));
-          tmem_st_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
-          tmem_st_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
@@ -404,9 +475,15 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
           if (row_valid) {
             float4* dst = reinterpret_cast<float4*>(my_part + row * (D + 4) + c0);
 #pragma unroll
-            for (int u = 0; u < 32; u += 4)
-              __stcg(dst + (u >> 2), make_float4(__uint_as_float(orow[u]), __uint_as_float(orow[u + 1]), __uint_as_float(orow[u + 2]),
-                                                 __uint_as_float(orow[u + 3])));
+            for (int u = 0; u < 32; u += 4) {
+              float4 o4 = make_float4(__uint_as_float(orow[u]), __uint_as_float(orow[u + 1]), __uint_as_float(orow[u + 2]),
+                                      __uint_as_float(orow[u + 3]));
+              if constexpr (KV8) {  // de-quantise the V channels
+                o4.x *= ch_scale[D + c0 + u]; o4.y *= ch_scale[D + c0 + u + 1];
+                o4.z *= ch_scale[D + c0 + u + 2]; o4.w *= ch_scale[D + c0 + u + 3];
+              }
+              __stcg(dst + (u >> 2), o4);
+            }
           }
         }
         if (row_valid) { __stcg(my_part + row * (D + 4) + D, m_used); __stcg(my_part + row * (D + 4) + D + 1, l_sum); }
@@ -498,15 +575,15 @@ inline CommCtx tc_device_ctx(const CommCtxHost& h) {
   return c;
 }
 
-template <int D, bool BF16>
+template <int D, bool BF16, bool KV8>
 void launch_tc(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeTcParams& p, int grid, cudaStream_t stream) {
-  auto kern = decode_tc_kernel<D, BF16>;
+  auto kern = decode_tc_kernel<D, BF16, KV8>;
   static bool configured = false;
   if (!configured) {
-    TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<D>::kTotal));
+    TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<D, KV8>::kTotal));
     configured = true;
   }
-  kern<<<grid, kTcThreads, TcSmem<D>::kTotal, stream>>>(kmap, vmap, p);
+  kern<<<grid, kTcThreads, TcSmem<D, KV8>::kTotal, stream>>>(kmap, vmap, p);
   TA_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -530,8 +607,11 @@ void decode_tc_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, int*
 }
 
 void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
-                      uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream) {
+                      uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream, const float* kscale,
+                      const float* vscale) {
+  const bool kv8 = kscale != nullptr;
   if (s.D != 64 && s.D != 128) throw std::runtime_error("decode_tc: head_dim must be 64 or 128");
+  if (kv8 && s.D != 128) throw std::runtime_error("decode_tc(fp8): head_dim must be 128");
   if (s.Hq % s.Hkv != 0) throw std::runtime_error("decode_tc: Hq must be a multiple of Hkv");
   const int G = s.Hq / s.Hkv;
   const int R = G * s.Sq;
@@ -544,9 +624,11 @@ void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const vo
     const size_t need = (size_t)2 * comm.world * s.B * s.Hkv * R * (s.D + 2) * 8;
     if (need > comm.data_bytes) throw std::runtime_error("decode_tc: symmetric buffer too small for this problem");
   }
-  CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, s.D, s.k_sb, s.k_sh, s.k_ss, 64, kTN, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap vmap = make_tmap_bhsd(v, 2, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 64, kTN, CU_TENSOR_MAP_SWIZZLE_128B);
+  const int eb = kv8 ? 1 : 2;
+  CUtensorMap kmap = make_tmap_bhsd(k, eb, s.B, s.Hkv, s.S, s.D, s.k_sb, s.k_sh, s.k_ss, 128 / eb, kTN, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap vmap = make_tmap_bhsd(v, eb, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 128 / eb, kTN, CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeTcParams p;
+  p.kscale = kscale; p.vscale = vscale;
   p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S; p.R = R;
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
@@ -563,10 +645,12 @@ void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const vo
     p.jvis = (int)std::max<long long>(0, std::min<long long>(p.tph, last < 0 ? 0 : last / kTN + 1));
   }
   p.comm = tc_device_ctx(comm);
-  if (s.D == 128) {
-    if (s.is_bf16) launch_tc<128, true>(kmap, vmap, p, grid, stream); else launch_tc<128, false>(kmap, vmap, p, grid, stream);
+  if (kv8) {
+    if (s.is_bf16) launch_tc<128, true, true>(kmap, vmap, p, grid, stream); else launch_tc<128, false, true>(kmap, vmap, p, grid, stream);
+  } else if (s.D == 128) {
+    if (s.is_bf16) launch_tc<128, true, false>(kmap, vmap, p, grid, stream); else launch_tc<128, false, false>(kmap, vmap, p, grid, stream);
   } else {
-    if (s.is_bf16) launch_tc<64, true>(kmap, vmap, p, grid, stream); else launch_tc<64, false>(kmap, vmap, p, grid, stream);
+    if (s.is_bf16) launch_tc<64, true, false>(kmap, vmap, p, grid, stream); else launch_tc<64, false, false>(kmap, vmap, p, grid, stream);
   }
 }
 

@@ -49,8 +49,11 @@ void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const 
 // ---- tensor-core decode: the R = (Hq/Hkv) x Sq <= 128 query rows of a KV head packed into one tcgen05 tile ----
 void decode_tc_plan(const AttnShape& s, int num_sms, int* grid, int* max_parts, int* rows, size_t* part_floats,
                     size_t* comm_bytes);
+// kscale / vscale != null: K, V are e4m3 bytes with per-CHANNEL fp32 scales (B, Hkv, D); both GEMMs then run as
+// tcgen05 kind::f8f6f4 (q is quantised per row in the kernel, P per element, K's scales are folded into q).
 void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
-                      uint32_t* tickets, const CommCtxHost& comm, int num_sms, cudaStream_t stream);
+                      uint32_t* tickets, const CommCtxHost& comm, int num_sms, cudaStream_t stream,
+                      const float* kscale = nullptr, const float* vscale = nullptr);
 
 // ---- stand-alone combine of W per-rank partials (o fp32 normalised, lse natural log) ----
 // local: o_part (rows, D) fp32 + lse_part (rows); result written to out (dtype of `is_bf16`/fp16/fp32)

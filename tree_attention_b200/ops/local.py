@@ -129,6 +129,33 @@ def decode_attention_mxfp8(
     return out, lse
 
 
+def decode_attention_fp8(
+    q: torch.Tensor,
+    k,
+    v,
+    softmax_scale: float,
+    causal: bool = False,
+    q_pos0: int = 0,
+    kv_pos0: int = 0,
+    comm=None,
+    return_lse: bool = True,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """tcgen05 (kind::f8f6f4) decode over a per-channel-scaled e4m3 KV shard (``ops.quant.FP8ChannelTensor``)."""
+    C = _build.load()
+    q = _as_bhsd(q)
+    b, hq, sq, d = q.shape
+    hkv, s = k.shape[1], k.shape[2]
+    if q.stride(2) % 8 != 0 and sq > 1:
+        q = q.contiguous()
+    grid, max_parts, rows, part_floats, _ = C.decode_tc_plan(b, hq, hkv, sq, s, d)
+    ws = _workspace(q.device, "decode_tc", part_floats, b * hkv + 2)
+    out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
+    lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device) if return_lse else None
+    C.decode_tc_fwd8(q, k.data, v.data, k.scales, v.scales, out, lse, ws["part"], ws["tickets"], comm,
+                     float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0))
+    return out, lse
+
+
 def decode_comm_bytes(b: int, hq: int, hkv: int, sq: int, s: int, d: int, world: int) -> Tuple[int, int]:
     """(data_bytes, flag_bytes) the decode family needs in symmetric memory (covers both decode kernels)."""
     rows = max(4, (hq // hkv) * sq)

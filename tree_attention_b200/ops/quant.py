@@ -69,3 +69,40 @@ class MXFP8Tensor:
 
     def dequantize(self, dtype: torch.dtype = torch.float32) -> torch.Tensor:
         return dequantize_mxfp8(self.data, self.scales).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# per-channel-scaled fp8 (the tensor-core decode format)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class FP8ChannelTensor:
+    """e4m3 tensor with one fp32 scale per (batch, head, channel): ``data`` uint8 (B, H, S, D), ``scales`` (B, H, D).
+
+    This is the KV-cache format of the tcgen05 decode kernel (``csrc/decode_tc_sm100.cu``, ``kind::f8f6f4``): K's
+    channel scales fold into the query before it is quantised and V's apply to the output columns, so the inner
+    loop is two plain fp8 GEMMs.  ``headroom`` > 1 leaves room for tokens appended later."""
+
+    data: torch.Tensor
+    scales: torch.Tensor
+
+    @classmethod
+    def from_float(cls, x: torch.Tensor, headroom: float = 1.0) -> "FP8ChannelTensor":
+        amax = x.float().abs().amax(dim=2)  # (B, H, D)
+        scales = torch.where(amax > 0, amax * (headroom / E4M3_MAX), torch.ones_like(amax)).contiguous()
+        q = (x.float() / scales[:, :, None, :]).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+        return cls(q.view(torch.uint8).contiguous(), scales)
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def is_cuda(self):
+        return self.data.is_cuda
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def dequantize(self, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        return (self.data.view(torch.float8_e4m3fn).float() * self.scales[:, :, None, :]).to(dtype)

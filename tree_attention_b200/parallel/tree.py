@@ -227,9 +227,9 @@ def tree_attention(
     rank, world = _world(group)
     scale = ref.default_scale(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
     s_local = k.shape[2]
-    from ..ops.quant import MXFP8Tensor
+    from ..ops.quant import FP8ChannelTensor, MXFP8Tensor
 
-    if isinstance(k, MXFP8Tensor):  # block-scaled fp8 KV cache
+    if isinstance(k, (MXFP8Tensor, FP8ChannelTensor)):  # fp8 KV cache (block-scaled MX or per-channel scaled)
         return _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset, q_offset, return_lse,
                                      backend, schedule)
     kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
@@ -276,15 +276,19 @@ def _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset,
     kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
     q_pos0 = (world * s_local - q.shape[2]) if q_offset is None else int(q_offset)
     g = q.shape[1] // k.shape[1]
-    if (q.is_cuda and q.shape[-1] == 128 and q.shape[2] * g <= local_ops.DECODE_MAX_ROWS
-            and backend in ("auto", "fused", "local")):
+    from ..ops.quant import FP8ChannelTensor
+
+    per_channel = isinstance(k, FP8ChannelTensor)
+    max_rows = local_ops.DECODE_MAX_ROWS if per_channel else 16
+    if (q.is_cuda and q.shape[-1] == 128 and q.shape[2] * g <= max_rows and backend in ("auto", "fused", "local")):
         comm = None
         if world > 1:
             b, hq, sq, d = q.shape
             data, flags = local_ops.decode_comm_bytes(b, hq, k.shape[1], sq, s_local, d, world)
-            comm = symm.get_region("decode", data, flags, group, layout=("mx", b, hq, k.shape[1], sq, d)).comm
-        o, lse = local_ops.decode_attention_mxfp8(q, k, v, scale, causal, q_pos0, kv_pos0, comm=comm,
-                                                  return_lse=return_lse)
+            fam = "decode_tc" if per_channel else "decode"
+            comm = symm.get_region(fam, data, flags, group, layout=("fp8", per_channel, b, hq, k.shape[1], sq, d)).comm
+        fn = local_ops.decode_attention_fp8 if per_channel else local_ops.decode_attention_mxfp8
+        o, lse = fn(q, k, v, scale, causal, q_pos0, kv_pos0, comm=comm, return_lse=return_lse)
         return (o, lse) if return_lse else o
     dt = q.dtype if q.is_cuda else torch.float32
     return tree_attention(q, k.dequantize(dt), v.dequantize(dt), group=group, causal=causal, softmax_scale=scale,
