@@ -52,6 +52,8 @@ def parse_args():
     p.add_argument("--no-extras", action="store_true", help="skip the NCCL-comparator / full-forward extras")
     p.add_argument("--graph", action=argparse.BooleanOptionalAction, default=True,
                    help="replay the step from a CUDA graph (launch-bound at 8 GPUs)")
+    p.add_argument("--pdl", action=argparse.BooleanOptionalAction, default=False,
+                   help="eager launches with programmatic dependent launch instead of graph replay")
     return p.parse_args()
 
 
@@ -265,7 +267,7 @@ def main():
     C = _build.load()
     from tree_attention_b200.models.decoder import TreeDecodeSession
 
-    sess = TreeDecodeSession(kvs, softmax_scale=scale, backend=args.backend, use_graph=args.graph)
+    sess = TreeDecodeSession(kvs, softmax_scale=scale, backend=args.backend, use_graph=args.graph, pdl=args.pdl)
     launches_per_step = sess.launches_per_step
 
     # correctness gate before timing (never time a wrong kernel)
@@ -356,7 +358,7 @@ def main():
             "gpu_launches": launches_per_step * steps,
             "decode_tokens_per_s": B / (lat * 1e-3),
             "hbm_gbs_per_gpu": gbs, "hbm_frac_of_measured": gbs / hbm,
-            "max_abs_err_vs_oracle": err, "backend": args.backend, "cuda_graph": bool(sess.graphs),
+            "max_abs_err_vs_oracle": err, "backend": args.backend, "cuda_graph": bool(sess.graphs), "pdl": bool(args.pdl),
             **extras,
         })
     ta.cleanup()

@@ -113,3 +113,18 @@ def test_missing_kernel_is_loud():
     q, k, v = _mk(1, 2, 2, 1, 256, 32, torch.bfloat16)  # head_dim 32: no sm_100a kernel
     with pytest.raises(RuntimeError):
         ta.tree_attention(q, k, v)
+
+
+def test_pdl_back_to_back_steps_match_and_stay_ordered():
+    """Programmatic dependent launch: consecutive steps overlap prologue/prefetch with the previous step's drain;
+    q produced by a preceding kernel must still be honoured (griddepcontrol.wait before q is read)."""
+    q, k, v = _mk(1, 16, 16, 1, 20000, 128, torch.bfloat16, seed=9)
+    outs = []
+    for i in range(20):
+        qi = q * (1.0 + 0.05 * i)            # produced by the kernel right before the decode launch
+        o, _ = L.decode_attention(qi, k, v, 0.088, impl="simt", pdl=2)
+        outs.append((qi, o))
+    torch.cuda.synchronize()
+    for qi, o in outs[::5]:
+        exp, _ = ref.attention_partial_ref(qi, k, v, 0.088, block=16384)
+        assert (o.float() - exp).abs().max().item() < 1.5e-2

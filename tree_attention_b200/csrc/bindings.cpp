@@ -107,7 +107,7 @@ py::tuple decode_plan(int B, int Hq, int Hkv, int Sq, int S, int D) {
 
 void decode_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out,
                 c10::optional<at::Tensor> lse, at::Tensor& part, at::Tensor& tickets, py::object comm, double scale,
-                bool causal, int64_t q_pos0, int64_t kv_pos0) {
+                bool causal, int64_t q_pos0, int64_t kv_pos0, int pdl) {
   c10::cuda::CUDAGuard guard(q.device());
   AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
   TORCH_CHECK(part.scalar_type() == at::kFloat && part.is_contiguous(), "part must be contiguous fp32");
@@ -126,7 +126,7 @@ void decode_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, a
   if (!comm.is_none()) c = comm.cast<Comm&>().h;
   ta::decode_simt_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
                          reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(),
-                         at::cuda::getCurrentCUDAStream());
+                         at::cuda::getCurrentCUDAStream(), nullptr, nullptr, pdl);
 }
 
 py::tuple attn_fwd_comm_bytes(int B, int Hq, int Sq, int D, int world) {

@@ -49,6 +49,7 @@ struct DecodeParams {
   int total_tiles;
   int tiles_q, tiles_rem;  // stream-K split: first `rem` CTAs get q+1 tiles
   int max_parts;
+  int pdl;  // 0: plain launch; 1: programmatic dependent launch; 2: + K/V prefetch before the dependency wait (static KV)
   CommCtx comm;
 };
 
@@ -142,12 +143,11 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   }
   __syncthreads();
 
-  // The epoch of this launch.  Every CTA reads the counter before any CTA can have bumped it (the
-  // bump happens after ALL CTAs passed their end-of-kernel arrival).
-  uint32_t epoch = 0;
-  if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
-  const uint64_t t_cta0 = globaltimer_ns();
-  const int parity = epoch & 1;
+  // Programmatic dependent launch: let the NEXT launch of the stream start its prologue (and, for a static KV
+  // cache, its first K/V tile loads) on SMs this grid has already vacated, while our last CTAs still wait for
+  // their peers.  Everything that depends on earlier kernels (q, workspace, tickets, epoch) is touched only after
+  // griddepcontrol.wait.
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int BH = p.B * p.Hkv;
   const long long q_pos_max = p.q_pos0 + p.Sq - 1;
 
@@ -158,6 +158,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   if (warp == kConsumerWarps) {
     // ------------------------------- TMA producer --------------------------------------------
     if (lane == 0) {
+      if (p.pdl == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_lo; t < t_hi; ++t) {
@@ -180,6 +181,14 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   }
 
   // --------------------------------- consumers ----------------------------------------------
+  if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  // The epoch of this launch.  Every CTA reads the counter before any CTA of THIS launch can have bumped it (the
+  // bump happens after all CTAs passed their end-of-kernel arrival) and, under PDL, after the previous launch
+  // has completed (griddepcontrol.wait above).
+  uint32_t epoch = 0;
+  if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
+  const uint64_t t_cta0 = globaltimer_ns();
+  const int parity = epoch & 1;
   const int r16 = lane & 15;
   const int half = lane >> 4;
   float m_run[R], l_run[R], o_acc[R][EPL];
@@ -634,7 +643,21 @@ void launch_one(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodePa
     TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  kern<<<grid, kThreads, smem, stream>>>(kmap, vmap, p);
+  if (p.pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, kmap, vmap, p));
+  } else {
+    kern<<<grid, kThreads, smem, stream>>>(kmap, vmap, p);
+  }
   TA_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -662,7 +685,7 @@ void decode_simt_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, in
 
 void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                         float* part, uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream,
-                        const uint32_t* kscale, const uint32_t* vscale) {
+                        const uint32_t* kscale, const uint32_t* vscale, int pdl) {
   const bool kv8 = kscale != nullptr;
   if (s.D != 64 && s.D != 128) throw std::runtime_error("decode_simt: head_dim must be 64 or 128");
   if (kv8 && s.D != 128) throw std::runtime_error("decode_simt(mxfp8): head_dim must be 128");
@@ -684,7 +707,7 @@ void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const 
   CUtensorMap vmap = make_tmap_bhsd(v, eb, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 128 / eb, kTileRows,
                                     CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeParams p;
-  p.kscale = kscale; p.vscale = vscale;
+  p.kscale = kscale; p.vscale = vscale; p.pdl = pdl;
   p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S;
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;

@@ -42,7 +42,8 @@ void decode_simt_plan(const AttnShape& s, int num_sms, int* grid, int* max_parts
 // part: float workspace, tickets: uint32 [B*Hkv + 2] zero-initialised once.
 void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                         float* part, uint32_t* tickets, const CommCtxHost& comm, int num_sms,
-                        cudaStream_t stream, const uint32_t* kscale = nullptr, const uint32_t* vscale = nullptr);
+                        cudaStream_t stream, const uint32_t* kscale = nullptr, const uint32_t* vscale = nullptr,
+                        int pdl = 0);
 // kscale/vscale != null: K/V are block-scaled fp8 (e4m3 bytes, D = 128) and the scales are (B, Hkv, S) words of
 // four UE8M0 exponents (one per 32 elements); strides in AttnShape are then in BYTES == elements.
 

@@ -29,7 +29,11 @@ class TreeDecodeSession:
         use_graph: bool = True,
         group=None,
         q_shape: Optional[Tuple[int, int, int, int]] = None,
+        pdl: bool = False,
     ):
+        """``pdl=True``: eager launches with programmatic dependent launch + K/V prefetch (the KV caches of this
+        session are only written through ``append_kv``, never by the kernel that precedes a step) instead of CUDA
+        graph replay -- the next step's prologue and first tile loads overlap the previous step's peer wait."""
         self.kv = list(kv_layers)
         k0 = self.kv[0][0]
         self.device = k0.device
@@ -39,6 +43,8 @@ class TreeDecodeSession:
         self.backend = backend
         self.schedule = schedule
         self.group = group
+        self.pdl = 2 if pdl else 0
+        self._kv_dirty = False  # set by append_kv: the next step must not prefetch K/V ahead of the append
         b, hkv, s, d = k0.shape
         self.q_shape = tuple(q_shape) if q_shape is not None else (b, hkv, 1, d)
         self.q_static = torch.zeros(self.q_shape, dtype=self.dtype, device=self.device)
@@ -49,14 +55,16 @@ class TreeDecodeSession:
         self.launches_per_step = max(1, -(-rows // 4)) if local_ops.decode_eligible(self.q_static, k0) else 1
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         graphable = self.device.type == "cuda" and (world == 1 or backend in ("fused", "symm", "auto"))
-        self._use_graph = bool(use_graph and graphable)
+        self._use_graph = bool(use_graph and graphable and not pdl)
         self._prepared = False
 
     # -- internals ---------------------------------------------------------------------------------
     def _eager(self, q: torch.Tensor, layer: int) -> torch.Tensor:
         k, v = self.kv[layer]
+        pdl = min(self.pdl, 1) if self._kv_dirty else self.pdl
+        self._kv_dirty = False
         return tree_attention(q, k, v, group=self.group, causal=self.causal, softmax_scale=self.scale,
-                              backend=self.backend, schedule=self.schedule)
+                              backend=self.backend, schedule=self.schedule, decode_pdl=pdl)
 
     def _prepare(self) -> None:
         if self._prepared:
@@ -101,6 +109,7 @@ class TreeDecodeSession:
         """Write one new token's K/V at local row ``position`` of this rank's shard (the owner of the
         global position calls this; shards are preallocated)."""
         k, v = self.kv[layer]
+        self._kv_dirty = True
         k[:, :, position : position + k_new.shape[2]].copy_(k_new, non_blocking=True)
         v[:, :, position : position + v_new.shape[2]].copy_(v_new, non_blocking=True)
 

@@ -64,13 +64,17 @@ def decode_attention(
     lse: Optional[torch.Tensor] = None,
     return_lse: bool = True,
     impl: str = "auto",
+    pdl: int = 0,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Launch the fused streaming decode kernel.  With ``comm`` (a ``_C.Comm``) the kernel also performs
     the cross-GPU tree combine and ``out``/``lse`` are the GLOBAL results, identical on every rank.
 
     ``impl``: ``"simt"`` (CUDA-core math; HBM-bound for one query row per KV head), ``"tc"`` (tcgen05: the
     (Hq/Hkv) x Sq rows of a KV head packed into one MMA tile; stays HBM-bound for GQA / multi-token decode),
-    ``"auto"`` = simt for a single row, tc otherwise."""
+    ``"auto"`` = simt for a single row, tc otherwise.
+    ``pdl``: programmatic dependent launch for back-to-back decode steps (simt kernel): 1 = the next launch may
+    start its prologue while this one drains; 2 = additionally prefetch K/V tiles before waiting on the previous
+    kernel -- only valid when the KV cache was not written by the immediately preceding kernel of the stream."""
     import os
 
     C = _build.load()
@@ -100,7 +104,7 @@ def decode_attention(
     if lse is None and return_lse:
         lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
     C.decode_fwd(q, k, v, out, lse, ws["part"], ws["tickets"], comm, float(softmax_scale), bool(causal),
-                 int(q_pos0), int(kv_pos0))
+                 int(q_pos0), int(kv_pos0), int(os.environ.get("TREE_ATTN_PDL", pdl)))
     return out, lse
 
 

@@ -207,6 +207,7 @@ def tree_attention(
     backend: str = "auto",
     schedule: str = "oneshot",
     layout: str = "bhsd",
+    decode_pdl: int = 0,
 ) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
     """Exact attention of replicated ``q`` over a KV sequence sharded across the ranks of ``group``.
 
@@ -216,6 +217,10 @@ def tree_attention(
     Causal masking uses GLOBAL positions: key ``j`` of this shard sits at ``kv_offset + j`` (default
     ``rank * S_local``: equal contiguous shards) and query ``i`` at ``q_offset + i`` (default: the last
     ``Sq`` positions of the global sequence, i.e. decode / chunked-prefill convention).
+
+    ``decode_pdl`` (single-row decode only): launch with programmatic dependent launch so that back-to-back
+    decode steps overlap one step's drain (peer wait) with the next step's prologue; ``2`` also prefetches K/V
+    before the dependency wait and requires that the KV cache was not written by the preceding kernel.
 
     Returns the global attention output (replicated, bitwise identical across ranks for the fused and
     symm backends) and optionally the global ``lse``.
@@ -238,7 +243,10 @@ def tree_attention(
 
     if be == "local":
         with _nvtx("tree_attention/local"):
-            o, lse = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0)
+            if decode_pdl and local_ops.decode_eligible(q, k):
+                o, lse = local_ops.decode_attention(q, k, v, scale, causal, q_pos0, kv_pos0, pdl=decode_pdl)
+            else:
+                o, lse = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0)
     elif be == "fused":
         if not q.is_cuda:
             raise RuntimeError("backend='fused' needs CUDA tensors")
@@ -249,7 +257,7 @@ def tree_attention(
             reg = symm.get_region("decode" if rows == 1 else "decode_tc", data, flags, group,
                                   layout=(b, hq, k.shape[1], sq, d))
             o, lse = local_ops.decode_attention(q, k, v, scale, causal, q_pos0, kv_pos0, comm=reg.comm,
-                                                return_lse=return_lse)
+                                                return_lse=return_lse, pdl=decode_pdl)
         else:
             from ..ops import flash
 
