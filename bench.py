@@ -52,8 +52,9 @@ def parse_args():
     p.add_argument("--no-extras", action="store_true", help="skip the NCCL-comparator / full-forward extras")
     p.add_argument("--graph", action=argparse.BooleanOptionalAction, default=True,
                    help="replay the step from a CUDA graph (launch-bound at 8 GPUs)")
-    p.add_argument("--pdl", action=argparse.BooleanOptionalAction, default=False,
-                   help="eager launches with programmatic dependent launch instead of graph replay")
+    p.add_argument("--pdl", action=argparse.BooleanOptionalAction, default=True,
+                   help="device-timed loop: eager launches chained by programmatic dependent launch (the e2e loop, which "
+                        "synchronises every step, replays the CUDA graph)")
     return p.parse_args()
 
 
@@ -390,6 +391,8 @@ def run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier):
         return float(t.item())
 
     try:
+        if sess.graphs:
+            out["graph_replay_ms_per_step"] = timeit(lambda i: sess.graphs[i % nb].replay(), steps=200)
         out["eager_launch_ms_per_step"] = timeit(
             lambda i: ta.tree_attention(q, kvs[i % nb][0], kvs[i % nb][1], softmax_scale=scale, backend=args.backend))
         if world > 1:

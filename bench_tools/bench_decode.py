@@ -28,6 +28,12 @@ for s in a.seq:
     def fc8():
         i[0] += 1
         return L.decode_attention_fp8(q, *c8[i[0] % n], 0.088, return_lse=False)
+    def fsw():
+        i[0] += 1
+        return L.decode_attention(q, *kvs[i[0] % n], 0.088, return_lse=False, impl="swap")
+    def fsw8():
+        i[0] += 1
+        return L.decode_attention_fp8(q, *c8[i[0] % n], 0.088, return_lse=False, impl="swap")
     def ftc():
         i[0] += 1
         return L.decode_attention(q, *kvs[i[0] % n], 0.088, return_lse=False, impl="tc")
@@ -39,9 +45,13 @@ for s in a.seq:
     ttc = time_cuda(ftc, a.steps, 10)["median_ms"]
     tc8 = time_cuda(fc8, a.steps, 10)["median_ms"]
     bc8 = 2 * hkv * s * 128
+    tsw = time_cuda(fsw, a.steps, 10)["median_ms"]
+    tsw8 = time_cuda(fsw8, a.steps, 10)["median_ms"]
     b16 = 2 * hkv * s * 128 * 2
     b8 = 2 * hkv * s * (128 + 4)
     print(json.dumps({"seq": s, "heads": a.heads, "kv_heads": hkv, "bf16_us": round(t16 * 1e3, 1), "bf16_gbs": round(b16 / t16 / 1e6, 0),
                       "bf16_tcgen05_us": round(ttc * 1e3, 1), "bf16_tcgen05_gbs": round(b16 / ttc / 1e6, 0),
+                      "bf16_swapAB_us": round(tsw * 1e3, 1), "bf16_swapAB_gbs": round(b16 / tsw / 1e6, 0),
+                      "fp8_swapAB_us": round(tsw8 * 1e3, 1), "fp8_swapAB_gbs": round(bc8 / tsw8 / 1e6, 0),
                       "fp8_tcgen05_us": round(tc8 * 1e3, 1), "fp8_tcgen05_gbs": round(bc8 / tc8 / 1e6, 0),
                       "mxfp8_us": round(t8 * 1e3, 1), "mxfp8_gbs": round(b8 / t8 / 1e6, 0), "speedup": round(t16 / t8, 2)}), flush=True)

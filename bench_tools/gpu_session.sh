@@ -46,6 +46,10 @@ for st in $STEPS; do
         python bench_tools/bench_fwd.py --seq 16384 --steps 2 --warmup 1 > "$OUT/ncu_fwd.log" 2>&1; echo "rc=$?"; ls -la "$OUT" | grep ncu-rep;;
     fwd)
       timeout 900 python bench_tools/bench_fwd.py > "$OUT/bench_fwd.log" 2>&1; echo "rc=$?"; tail -n 30 "$OUT/bench_fwd.log";;
+    bench8pdl)
+      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29833 bench.py --gpus $NG --pdl --no-extras > "$OUT/bench_own_${NG}_pdl.json" 2> "$OUT/bench_own_${NG}_pdl.err"; echo "pdl n=$NG rc=$?"; tail -n 1 "$OUT/bench_own_${NG}_pdl.json" | cut -c1-400;;
+    sweep_gqa)
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29812 bench_tools/sweep.py --kv-heads 8 --modes decode --seqs 131072 1048576 --out "$OUT/sweep_gqa_$NG.jsonl" > "$OUT/sweep_gqa_$NG.log" 2>&1; echo "rc=$?"; tail -n 12 "$OUT/sweep_gqa_$NG.log" | cut -c1-300;;
     sweep)
       timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29811 bench_tools/sweep.py --out "$OUT/sweep_$NG.jsonl" > "$OUT/sweep_$NG.log" 2>&1; echo "rc=$?"; tail -n 20 "$OUT/sweep_$NG.log";;
     tests_multi)

@@ -72,8 +72,9 @@ FP8_CASES = [
 ]
 
 
+@pytest.mark.parametrize("impl", ["tc", "swap"])
 @pytest.mark.parametrize("case", FP8_CASES, ids=[str(i) for i in range(len(FP8_CASES))])
-def test_fp8_channel_tcgen05_decode_matches_dequantised_oracle(case):
+def test_fp8_channel_tcgen05_decode_matches_dequantised_oracle(case, impl):
     """kind::f8f6f4 decode: per-channel-scaled e4m3 K/V, q quantised per row and P per element inside the kernel."""
     b, hq, hkv, sq, s, causal = case
     g = torch.Generator(device="cuda").manual_seed(11)
@@ -82,7 +83,7 @@ def test_fp8_channel_tcgen05_decode_matches_dequantised_oracle(case):
     v = torch.randn(b, hkv, s, 128, device="cuda", generator=g).bfloat16()
     kq, vq = quant.FP8ChannelTensor.from_float(k), quant.FP8ChannelTensor.from_float(v)
     scale = 128 ** -0.5
-    out, lse = L.decode_attention_fp8(q, kq, vq, scale, causal, s - sq, 0)
+    out, lse = L.decode_attention_fp8(q, kq, vq, scale, causal, s - sq, 0, impl=impl)
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
     o_ref, l_ref = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize(), scale, causal, s - sq, 0, torch.float32, block=16384)

@@ -23,3 +23,23 @@ def test_umma_probe(n, k, b_mn_major, a_from_tmem):
     exp = a.float() @ (b.float() if b_mn_major else b.float().t())
     err = (c - exp).abs().max().item()
     assert err < 1e-2 * max(1.0, exp.abs().max().item() / 16), f"max err {err}"
+
+
+@pytest.mark.parametrize("n", [16, 64, 128])
+def test_umma_block_scaled_probe(n):
+    """tcgen05.mma.kind::mxf8f6f4.block_scale with UE8M0 scale factors staged in TMEM (32 lanes x 4 columns per 128
+    rows, replicated per lane quarter, byte k of a word = K-block k) vs the de-quantised PyTorch product."""
+    from tree_attention_b200.ops import quant
+
+    C = _build.load()
+    g = torch.Generator(device="cuda").manual_seed(n)
+    a = torch.randn(128, 128, device="cuda", generator=g) * torch.logspace(-2, 2, 128, device="cuda")[:, None]
+    b = torch.randn(n, 128, device="cuda", generator=g) * 3
+    a8, sfa = quant.quantize_mxfp8(a.contiguous())
+    b8, sfb = quant.quantize_mxfp8(b.contiguous())
+    c = torch.zeros(128, n, device="cuda", dtype=torch.float32)
+    C.umma_bs_probe(a8, b8, sfa.contiguous(), sfb.contiguous(), c)
+    torch.cuda.synchronize()
+    exp = quant.dequantize_mxfp8(a8, sfa) @ quant.dequantize_mxfp8(b8, sfb).t()
+    err = (c - exp).abs().max().item() / exp.abs().max().item()
+    assert err < 1e-5, err

@@ -170,7 +170,7 @@ py::tuple decode_tc_plan(int B, int Hq, int Hkv, int Sq, int S, int D) {
 
 void decode_tc_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out,
                    c10::optional<at::Tensor> lse, at::Tensor& part, at::Tensor& tickets, py::object comm, double scale,
-                   bool causal, int64_t q_pos0, int64_t kv_pos0) {
+                   bool causal, int64_t q_pos0, int64_t kv_pos0, bool swap) {
   c10::cuda::CUDAGuard guard(q.device());
   AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
   TORCH_CHECK(part.scalar_type() == at::kFloat && part.is_contiguous(), "part must be contiguous fp32");
@@ -187,14 +187,19 @@ void decode_tc_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
   }
   CommCtxHost c;
   if (!comm.is_none()) c = comm.cast<Comm&>().h;
-  ta::decode_tc_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
-                       reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream());
+  if (swap)
+    ta::decode_swap_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
+                           reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream());
+  else
+    ta::decode_tc_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
+                         reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream());
 }
 
 // per-channel-scaled fp8 KV cache on the tensor cores: k8/v8 uint8 (B, Hkv, S, 128) e4m3, ksc/vsc fp32 (B, Hkv, 128)
 void decode_tc_fwd8(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& ksc,
                     const at::Tensor& vsc, at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part,
-                    at::Tensor& tickets, py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
+                    at::Tensor& tickets, py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0,
+                    bool swap) {
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(q.dim() == 4 && k8.dim() == 4 && v8.dim() == 4 && out.sizes() == q.sizes(), "expected (B, H, S, D) tensors");
   TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
@@ -220,9 +225,14 @@ void decode_tc_fwd8(const at::Tensor& q, const at::Tensor& k8, const at::Tensor&
   float* lse_p = lse.has_value() ? lse->data_ptr<float>() : nullptr;
   CommCtxHost c;
   if (!comm.is_none()) c = comm.cast<Comm&>().h;
-  ta::decode_tc_launch(s, q.data_ptr(), k8.data_ptr(), v8.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
-                       reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream(),
-                       ksc.data_ptr<float>(), vsc.data_ptr<float>());
+  if (swap)
+    ta::decode_swap_launch(s, q.data_ptr(), k8.data_ptr(), v8.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
+                           reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream(),
+                           ksc.data_ptr<float>(), vsc.data_ptr<float>());
+  else
+    ta::decode_tc_launch(s, q.data_ptr(), k8.data_ptr(), v8.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
+                         reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream(),
+                         ksc.data_ptr<float>(), vsc.data_ptr<float>());
 }
 
 // block-scaled fp8 KV cache decode: k8/v8 uint8 (B, Hkv, S, 128) e4m3, ks/vs uint8 (B, Hkv, S, 4) UE8M0
@@ -348,6 +358,17 @@ void umma_probe(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, bool b_
                         at::cuda::getCurrentCUDAStream());
 }
 
+void umma_bs_probe(const at::Tensor& a8, const at::Tensor& b8, const at::Tensor& sfa, const at::Tensor& sfb, at::Tensor& c) {
+  c10::cuda::CUDAGuard guard(a8.device());
+  TORCH_CHECK(a8.scalar_type() == at::kByte && b8.scalar_type() == at::kByte && sfa.scalar_type() == at::kByte &&
+              sfb.scalar_type() == at::kByte && c.scalar_type() == at::kFloat);
+  TORCH_CHECK(a8.is_contiguous() && b8.is_contiguous() && sfa.is_contiguous() && sfb.is_contiguous() && c.is_contiguous());
+  TORCH_CHECK(a8.size(0) == 128 && a8.size(1) == 128 && b8.size(1) == 128 && sfa.numel() == 128 * 4 && sfb.numel() == b8.size(0) * 4);
+  TORCH_CHECK(c.size(0) == 128 && c.size(1) == b8.size(0));
+  ta::umma_bs_probe_launch(a8.data_ptr(), b8.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), c.data_ptr<float>(), (int)b8.size(0),
+                           at::cuda::getCurrentCUDAStream());
+}
+
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -380,5 +401,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("symm_allreduce_sizes", &symm_allreduce_sizes);
   m.def("combine", &combine);
   m.def("umma_probe", &umma_probe);
+  m.def("umma_bs_probe", &umma_bs_probe);
   m.def("num_sms", []() { return ta::num_sms(); });
 }

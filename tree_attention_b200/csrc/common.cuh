@@ -240,6 +240,30 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
   asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
   return uint32_t(lo) | (uint32_t(hi) << 16);
 }
+// block-scaled fp8 (OCP MX): D[tmem] (+)= (A o SFA) * (B o SFB); scale factors (UE8M0, one per 32 elements of K) live
+// in TMEM: 32 lanes x 4 columns per 128 rows, replicated in the 4 lane quarters; byte k of a column word is the scale
+// of K-block k, selected per instruction by the sf_id fields of the instruction descriptor.
+__device__ __forceinline__ void umma_ss_mxf8_block_scale(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                         uint32_t sfa_tmem, uint32_t sfb_tmem, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%4], [%5], p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(sfa_tmem), "r"(sfb_tmem), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor of kind::mxf8f6f4.block_scale (cute/arch/mma_sm100_desc.hpp, InstrDescriptorBlockScaled)
+__host__ __device__ constexpr uint32_t umma_idesc_block_scaled(uint32_t a_fmt, uint32_t b_fmt, uint32_t m, uint32_t n,
+                                                               uint32_t a_mn_major, uint32_t b_mn_major, uint32_t a_sf_id,
+                                                               uint32_t b_sf_id) {
+  return (b_sf_id << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((n >> 3) << 17) |
+         (1u << 23)  // scale format = UE8M0
+         | ((m >> 4) << 24) | (a_sf_id << 29);
+}
+__device__ __forceinline__ void tmem_st_32x32b_x4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+               : "memory");
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -1,0 +1,634 @@
+// attn_tree_fused_decode, swap-AB formulation -- S^T = K Q^T on tcgen05 with the KEYS on the TMEM lanes.
+//
+// decode_tc_sm100.cu packs the R query rows into the M dimension: every softmax thread then owns a full 128-key row
+// of scores (~2700 cycles per tile, independent of dtype), which caps fp8 KV at ~1.3x over bf16.  Here the tile is
+// transposed (SURVEY.md 7.1 "swap-AB"):
+//     S^T[128 keys, N = 16 queries] = K_tile (A, K-major)  x  Q^T (B = packed query rows, K-major)
+//     O^T[D = 128,  N = 16 queries] += V_tile^T (A, MN-major: the [key][d] tile exactly as TMA delivers it) x P^T (B)
+// so a softmax thread (= one key) handles 16 scores instead of 128, the two GEMMs cost 128 tensor cycles per tile
+// instead of 1024, and the kernel is HBM-bound for fp8 as well.  Column (per-query) maxima across the 128 keys are
+// taken with redux.sync + one smem exchange per tile; row sums stay per-thread until the end of a head segment.
+// P^T is written to shared memory by the softmax threads (B operands cannot come from TMEM) in the 128B-swizzled
+// K-major layout and made visible with fence.proxy.async.  Split-KV scheduling, workspace, tickets and the LL-tagged
+// cross-GPU combine are those of decode_simt.cu / decode_tc_sm100.cu.  R = (Hq/Hkv) x Sq <= 16, head_dim = 128.
+#include "common.cuh"
+#include "host_utils.h"
+#include "kernels.h"
+
+namespace ta {
+namespace {
+
+constexpr int kSwN = 16;       // query columns of the transposed tile
+constexpr int kSwKV = 128;     // keys per tile == MMA M
+constexpr int kSwD = 128;
+constexpr int kSwThreads = 192;
+constexpr int kSmx = 128;
+constexpr int kSwMaxPending = 32;
+constexpr float kSwRescale = 8.0f;
+
+struct DecodeSwParams {
+  const void* q;
+  void* out;
+  float* lse;
+  float* part;
+  uint32_t* tickets;
+  const float* kscale;  // KV8: per-channel fp32 scales (B, Hkv, D) of the e4m3 K / V shards
+  const float* vscale;
+  int B, Hq, Hkv, G, Sq, S, R;
+  float scale_log2;
+  int causal;
+  long long q_pos0, kv_pos0;
+  long long q_sb, q_sh, q_ss, o_sb, o_sh, o_ss;
+  int tph, total_tiles, tiles_q, tiles_rem, max_parts, jvis;
+  CommCtx comm;
+};
+
+template <bool KV8>
+struct SwSmem {
+  static constexpr int kElem = KV8 ? 1 : 2;
+  static constexpr int kAtoms = kSwD * kElem / 128;            // 128-byte atoms per row of K / V / Q
+  static constexpr int kTileBytes = kSwKV * kSwD * kElem;      // one K or V tile
+  static constexpr int kAtomBytes = kSwKV * 128;
+  static constexpr int kQBytes = kSwN * kSwD * kElem;          // packed query rows
+  static constexpr int kQAtomBytes = kSwN * 128;
+  static constexpr int kPBytes = kSwN * kSwKV * kElem;         // P^T [16 queries][128 keys]
+  static constexpr int kPAtoms = kSwKV * kElem / 128;
+  static constexpr int kStages = KV8 ? 6 : 3;
+  static constexpr size_t kTotal = 1024 + size_t(2 * kStages) * kTileBytes + kQBytes + 2 * kPBytes + 2048 + 1024;
+};
+
+__device__ __forceinline__ float sw_ninf() { return __int_as_float(0xff800000); }
+__device__ __forceinline__ int sw_cta_lo(const DecodeSwParams& p, int c) { return c * p.tiles_q + min(c, p.tiles_rem); }
+__device__ __forceinline__ int sw_cta_of_tile(const DecodeSwParams& p, int t) {
+  const int big = p.tiles_rem * (p.tiles_q + 1);
+  return t < big ? t / (p.tiles_q + 1) : p.tiles_rem + (t - big) / p.tiles_q;
+}
+template <bool BF16>
+__device__ __forceinline__ uint16_t sw_to16(float f) {
+  if constexpr (BF16) return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+  else return __half_as_ushort(__float2half_rn(f));
+}
+// order-preserving float <-> int so that redux.sync.max.s32 can reduce floats
+__device__ __forceinline__ int sw_f2ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float sw_ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+template <bool BF16, bool KV8>
+__global__ void __launch_bounds__(kSwThreads, 1)
+decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
+                   const DecodeSwParams p) {
+  using SM = SwSmem<KV8>;
+  constexpr int D = kSwD;
+  constexpr int NS = SM::kStages;
+  constexpr int EPA = 128 / SM::kElem;    // elements per 128-byte atom row
+  constexpr int KSTEP = 32 / SM::kElem;   // elements per MMA along the contraction (32 bytes)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* k_s = smem;
+  uint8_t* v_s = k_s + NS * SM::kTileBytes;
+  uint8_t* q_s = v_s + NS * SM::kTileBytes;          // [atoms][16 rows][128 B]
+  uint8_t* p_s = q_s + SM::kQBytes;                  // [2][atoms][16 rows][128 B]
+  int* xch = reinterpret_cast<int*>(p_s + 2 * SM::kPBytes);   // [2 parity][4 warps][16] column maxima (ordered ints)
+  float* red_s = reinterpret_cast<float*>(xch + 2 * 4 * kSwN); // [4 warps][16] row-sum reduction
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red_s + 4 * kSwN);
+  uint64_t* q_ready = bars;            // count 128
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + NS;
+  uint64_t* v_full = k_empty + NS;
+  uint64_t* v_empty = v_full + NS;
+  uint64_t* s_full = v_empty + NS;     // 2
+  uint64_t* p_full = s_full + 2;       // 2 (count 4)
+  uint64_t* pv_done = p_full + 2;      // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  int* s_misc = reinterpret_cast<int*>(tmem_slot + 2);
+  int* pending = s_misc + 4;
+  [[maybe_unused]] float* ch_scale = reinterpret_cast<float*>(pending + kSwMaxPending);  // KV8: [2][D]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x;
+  const int t_lo = sw_cta_lo(p, cta), t_hi = sw_cta_lo(p, cta + 1);
+  const int world = p.comm.world;
+  const int BH = p.B * p.Hkv;
+  const int R = p.R;
+
+  if (tid == 0) {
+    mbar_init(q_ready, kSmx);
+    for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
+    fence_mbar_init();
+    s_misc[1] = 0; s_misc[2] = 0;
+  }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); }
+  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  if (warp < 4) {  // zero Q (padding rows) and both P^T buffers once
+    for (int c = tid; c < (SM::kQBytes + 2 * SM::kPBytes) / 16; c += kSmx) reinterpret_cast<uint4*>(q_s)[c] = make_uint4(0, 0, 0, 0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;       // S^T0 [0,16) | S^T1 [32,48) | O^T [64,80)
+  const uint32_t tmem_o = tmem + 64;
+
+  uint32_t epoch = 0;
+  if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
+  const int parity = epoch & 1;
+  const uint64_t t_cta0 = globaltimer_ns();
+
+  auto next_segment = [&](int t, int& x, int& j0, int& n, int& t_next) {
+    x = t / p.tph;
+    const int seg_end = min(t_hi, (x + 1) * p.tph);
+    j0 = t - x * p.tph;
+    const int j1 = seg_end - x * p.tph;
+    n = max(0, min(j1, p.jvis) - j0);
+    t_next = seg_end;
+  };
+
+  if (warp == 4) {
+    // =============================== TMA producer ===============================================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = t_lo; t < t_hi;) {
+        int x, j0, n, tn;
+        next_segment(t, x, j0, n, tn);
+        const int b = x / p.Hkv, h = x - b * p.Hkv;
+        for (int jj = 0; jj < n; ++jj, ++it) {
+          const int st = it % NS;
+          const uint32_t ph = (it / NS) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], SM::kTileBytes);
+#pragma unroll
+          for (int a = 0; a < SM::kAtoms; ++a)
+            tma_load_4d(k_s + st * SM::kTileBytes + a * SM::kAtomBytes, &kmap, &k_full[st], a * EPA, (j0 + jj) * kSwKV, h, b);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], SM::kTileBytes);
+#pragma unroll
+          for (int a = 0; a < SM::kAtoms; ++a)
+            tma_load_4d(v_s + st * SM::kTileBytes + a * SM::kAtomBytes, &vmap, &v_full[st], a * EPA, (j0 + jj) * kSwKV, h, b);
+        }
+        t = tn;
+      }
+    }
+  } else if (warp == 5) {
+    // =============================== MMA issuer =================================================
+    if (lane == 0) {
+      constexpr uint32_t fmt = KV8 ? 0u : (BF16 ? 1u : 0u);
+      constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kSwKV, kSwN, 0, 0);   // A = K (K-major), B = Q (K-major)
+      constexpr uint32_t idesc_pv = umma_idesc(fmt, fmt, D, kSwN, 1, 0);       // A = V^T (MN-major), B = P^T (K-major)
+      const uint32_t q_addr = smem_u32(q_s);
+      auto issue_qk = [&](int i) {
+        const int st = i % NS;
+        mbar_wait(&k_full[st], (i / NS) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(k_s + st * SM::kTileBytes);
+        const uint32_t d_tmem = tmem + (i & 1) * 32;
+#pragma unroll
+        for (int kk = 0; kk < D / KSTEP; ++kk) {
+          const uint64_t ad = umma_smem_desc_sw128(k_addr + (kk / 4) * SM::kAtomBytes + (kk % 4) * 32, 0, 1024);
+          const uint64_t bd = umma_smem_desc_sw128(q_addr + (kk / 4) * SM::kQAtomBytes + (kk % 4) * 32, 0, 1024);
+          if constexpr (KV8) umma_ss_f8(d_tmem, ad, bd, idesc_qk, kk > 0 ? 1u : 0u);
+          else umma_ss_f16(d_tmem, ad, bd, idesc_qk, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[i & 1]);
+      };
+      int it = 0, seg = 0;
+      for (int t = t_lo; t < t_hi;) {
+        int x, j0, n, tn;
+        next_segment(t, x, j0, n, tn);
+        mbar_wait(q_ready, seg & 1);
+        tc_fence_after();
+        if (n > 0) {
+          issue_qk(it);
+          for (int jj = 0; jj < n; ++jj) {
+            const int i = it + jj;
+            if (jj + 1 < n) issue_qk(i + 1);
+            const int st = i % NS;
+            mbar_wait(&p_full[i & 1], (i >> 1) & 1);
+            mbar_wait(&v_full[st], (i / NS) & 1);
+            tc_fence_after();
+            const uint32_t v_addr = smem_u32(v_s + st * SM::kTileBytes);
+            const uint32_t pt_addr = smem_u32(p_s + (i & 1) * SM::kPBytes);
+#pragma unroll
+            for (int kk = 0; kk < kSwKV / KSTEP; ++kk) {
+              // A: KSTEP keys x 128 d of V^T: rows of the [key][d] tile, MN-major (LBO = next 64-wide d atom)
+              const uint64_t ad = umma_smem_desc_sw128(v_addr + kk * (KSTEP * 128), SM::kAtomBytes, 1024);
+              const uint64_t bd = umma_smem_desc_sw128(pt_addr + (kk / 4) * SM::kQAtomBytes + (kk % 4) * 32, 0, 1024);
+              if constexpr (KV8) umma_ss_f8(tmem_o, ad, bd, idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
+              else umma_ss_f16(tmem_o, ad, bd, idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&v_empty[st]);
+            umma_commit(&pv_done[i & 1]);
+          }
+          it += n;
+        }
+        ++seg;
+        t = tn;
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== softmax / epilogue warps: thread = key row / output channel ==
+    const int row = tid;
+    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    int qi_of[kSwN];  // token index (within Sq) of packed query column qn
+#pragma unroll
+    for (int qn = 0; qn < kSwN; ++qn) qi_of[qn] = qn % p.Sq;
+    auto store_out = [&](int x, int r, int d, float o_norm, float lse2) {
+      const int b = x / p.Hkv, h = x - b * p.Hkv;
+      const int g = r / p.Sq, i = r - g * p.Sq;
+      uint16_t* op = reinterpret_cast<uint16_t*>(p.out) + (long long)b * p.o_sb + (long long)(h * p.G + g) * p.o_sh +
+                     (long long)i * p.o_ss + d;
+      *op = sw_to16<BF16>(o_norm);
+      if (d == 0 && p.lse != nullptr) p.lse[((long long)b * p.Hq + (h * p.G + g)) * p.Sq + i] = lse2 * 0.6931471805599453f;
+    };
+    // ---- LL transport (tagged 8-byte words), identical protocol to decode_simt.cu ----
+    auto word_ptr = [&](int dst, int src, int x) -> uint2* {
+      return reinterpret_cast<uint2*>(p.comm.data[dst]) + ((size_t)(parity * world + src) * BH + x) * (size_t)(R * (D + 2));
+    };
+    auto ll_store = [&](uint2* w, float v) {
+      asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(w), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+    };
+    auto ll_wait = [&](const uint2* w, bool& ok) -> float {
+      uint32_t v, tag;
+      asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(w) : "memory");
+      if (tag != epoch) {
+        const uint64_t t0 = globaltimer_ns();
+        uint32_t itn = 0;
+        do {
+          asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(w) : "memory");
+          if (tag == epoch) break;
+          if ((++itn & 0x3fu) == 0 && globaltimer_ns() - t0 > p.comm.timeout_ns) { ok = false; break; }
+        } while (true);
+      }
+      return __uint_as_float(v);
+    };
+    uint64_t t_publish = 0;
+    auto combine_ranks = [&](int x) {
+      uint64_t t_got = 0;
+      for (int idx = tid; idx < R * D; idx += kSmx) {
+        const int r = idx / D, d = idx - r * D;
+        bool ok = true;
+        float lse_s[kMaxWorld];
+        float mx = sw_ninf();
+        int bad_src = -1;
+        for (int s = 0; s < world; ++s) {
+          bool oks = true;
+          lse_s[s] = ll_wait(word_ptr(p.comm.rank, s, x) + r * (D + 2) + D, oks);
+          if (!oks) { ok = false; bad_src = s; }
+          mx = fmaxf(mx, lse_s[s]);
+        }
+        const float ms = (mx == sw_ninf()) ? 0.f : mx;
+        float num = 0.f, den = 0.f;
+        for (int s = 0; s < world; ++s) {
+          bool oks = true;
+          const float val = ll_wait(word_ptr(p.comm.rank, s, x) + r * (D + 2) + d, oks);
+          if (!oks) { ok = false; bad_src = s; }
+          const float w = fast_exp2(lse_s[s] - ms);
+          num = fmaf(w, val, num);
+          den += w;
+        }
+        if (idx == 0) t_got = globaltimer_ns();
+        float o_norm = den > 0.f ? num / den : 0.f;
+        float lse2 = den > 0.f ? ms + fast_log2(den) : sw_ninf();
+        if (!ok) {
+          o_norm = __int_as_float(0x7fc00000); lse2 = o_norm;
+          p.comm.status[0] = kCommTimeout; p.comm.status[1] = x; p.comm.status[2] = bad_src; p.comm.status[3] = epoch;
+        }
+        store_out(x, r, d, o_norm, lse2);
+      }
+      named_bar_sync(1, kSmx);
+      if (tid == 0 && t_publish != 0) {
+        const uint64_t t_done = globaltimer_ns();
+        atomicMax(p.comm.status + 10, (uint32_t)min((unsigned long long)(t_got - t_publish), 0xffffffffull));
+        atomicMax(p.comm.status + 11, (uint32_t)min((unsigned long long)(t_done - t_publish), 0xffffffffull));
+        atomicMax(p.comm.status + 12, (uint32_t)min((unsigned long long)(t_publish - t_cta0), 0xffffffffull));
+      }
+    };
+
+
+    int it = 0;
+    for (int t = t_lo; t < t_hi;) {
+      int x, j0, n, tn;
+      next_segment(t, x, j0, n, tn);
+      const int b = x / p.Hkv, h = x - b * p.Hkv;
+      // ---- stage the packed query rows (B operand, K-major): thread -> (row = tid / 8, 2 chunks of 16 bytes)
+      [[maybe_unused]] float q_scale_mine = 1.f;
+      if constexpr (KV8) {
+        if (tid < D) { ch_scale[tid] = __ldg(p.kscale + (long long)x * D + tid); ch_scale[D + tid] = __ldg(p.vscale + (long long)x * D + tid); }
+        named_bar_sync(1, kSmx);
+      }
+      {
+        const int qr = tid >> 3, part8 = tid & 7;  // 16 rows x 8 threads; every thread runs the same shuffles
+        const bool qv = qr < R;
+        const int g = qv ? qr / p.Sq : 0, qi = qv ? qr - g * p.Sq : 0;
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(p.q) + (long long)b * p.q_sb + (long long)(h * p.G + g) * p.q_sh +
+                              (long long)qi * p.q_ss + part8 * 16;
+        if constexpr (!KV8) {
+          if (qv) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int ch = part8 * 2 + u;  // 16-byte chunk (8 elements) within the 256-byte row
+              const uint4 w = __ldg(reinterpret_cast<const uint4*>(src) + u);
+              *reinterpret_cast<uint4*>(q_s + (ch >> 3) * SM::kQAtomBytes + qr * 128 + (((ch & 7) ^ (qr & 7)) << 4)) = w;
+            }
+          }
+        } else {
+          // fold K's channel scales into q, quantise the row to e4m3 with one scale per row (8 threads cooperate)
+          float qf[16];
+          float amax = 0.f;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            float v = 0.f;
+            if (qv) {
+              if constexpr (BF16) v = __uint_as_float(uint32_t(src[u]) << 16); else v = __half2float(__ushort_as_half(src[u]));
+              v *= ch_scale[part8 * 16 + u];
+            }
+            qf[u] = v;
+            amax = fmaxf(amax, fabsf(v));
+          }
+          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 4));
+          const float qs = amax > 0.f ? amax * (1.f / 448.f) : 1.f;
+          const float inv = 1.f / qs;
+          uint4 w;
+          w.x = pack_e4m3x4(qf[0] * inv, qf[1] * inv, qf[2] * inv, qf[3] * inv);
+          w.y = pack_e4m3x4(qf[4] * inv, qf[5] * inv, qf[6] * inv, qf[7] * inv);
+          w.z = pack_e4m3x4(qf[8] * inv, qf[9] * inv, qf[10] * inv, qf[11] * inv);
+          w.w = pack_e4m3x4(qf[12] * inv, qf[13] * inv, qf[14] * inv, qf[15] * inv);
+          if (qv) *reinterpret_cast<uint4*>(q_s + qr * 128 + ((part8 ^ (qr & 7)) << 4)) = w;
+          if (part8 == 0) red_s[qr] = qs;  // per-query scale, read by every softmax thread below
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(q_ready);
+      float sc_q[kSwN];
+      if constexpr (KV8) {
+        named_bar_sync(1, kSmx);
+#pragma unroll
+        for (int qn = 0; qn < kSwN; ++qn) sc_q[qn] = p.scale_log2 * red_s[qn];
+        named_bar_sync(1, kSmx);  // red_s is reused for the row-sum reduction at the end of the segment
+      } else {
+#pragma unroll
+        for (int qn = 0; qn < kSwN; ++qn) sc_q[qn] = p.scale_log2;
+      }
+
+      float m_used[kSwN], l_thr[kSwN];
+#pragma unroll
+      for (int qn = 0; qn < kSwN; ++qn) { m_used[qn] = sw_ninf(); l_thr[qn] = 0.f; }
+      for (int jj = 0; jj < n; ++jj) {
+        const int i = it + jj;
+        const int n0 = (j0 + jj) * kSwKV;
+        mbar_wait(&s_full[i & 1], (i >> 1) & 1);
+        tc_fence_after();
+        uint32_t sr[16];
+        tmem_ld_32x32b_x16(tmem + (i & 1) * 32 + lane_addr, sr);
+        tmem_ld_wait();
+        const bool row_in = (n0 + row) < p.S;
+        const long long kvpos = p.kv_pos0 + n0 + row;
+        float sv[kSwN];
+#pragma unroll
+        for (int qn = 0; qn < kSwN; ++qn) {
+          const bool vis = row_in && qn < R && (!p.causal || kvpos <= p.q_pos0 + qi_of[qn]);
+          sv[qn] = vis ? __uint_as_float(sr[qn]) * sc_q[qn] : sw_ninf();
+        }
+        // column maxima over the 128 keys: redux within the warp, smem across the 4 warps
+        int* xc = xch + (i & 1) * 4 * kSwN;
+#pragma unroll
+        for (int qn = 0; qn < kSwN; ++qn) {
+          const int wm = __reduce_max_sync(0xffffffffu, sw_f2ord(sv[qn]));
+          if (lane == qn) xc[warp * kSwN + qn] = wm;
+        }
+        named_bar_sync(2, kSmx);
+        bool any_refresh = false;
+        float alpha[kSwN];
+#pragma unroll
+        for (int qn = 0; qn < kSwN; ++qn) {
+          const int m4 = max(max(xc[qn], xc[kSwN + qn]), max(xc[2 * kSwN + qn], xc[3 * kSwN + qn]));
+          const float m_new = fmaxf(m_used[qn], sw_ord2f(m4));
+          const bool refresh = (m_new - m_used[qn] > kSwRescale) || (m_used[qn] == sw_ninf() && m_new != sw_ninf());
+          alpha[qn] = refresh ? fast_exp2(m_used[qn] - m_new) : 1.f;
+          if (refresh) { m_used[qn] = m_new; l_thr[qn] *= alpha[qn]; any_refresh = true; }
+        }
+        if (any_refresh && jj > 0) {  // uniform across the CTA: every thread sees the same maxima
+          mbar_wait(&pv_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
+          tc_fence_after();
+          uint32_t orow[16];
+          tmem_ld_32x32b_x16(tmem_o + lane_addr, orow);
+          tmem_ld_wait();
+#pragma unroll
+          for (int qn = 0; qn < kSwN; ++qn) orow[qn] = __float_as_uint(__uint_as_float(orow[qn]) * alpha[qn]);
+          tmem_st_32x32b_x16(tmem_o + lane_addr, orow);
+          tmem_st_wait();
+        }
+        // the P^T buffer of tile i was last read by PV(i-2)
+        if (jj >= 2) { mbar_wait(&pv_done[i & 1], ((i - 2) >> 1) & 1); }
+        uint8_t* pt = p_s + (i & 1) * SM::kPBytes;
+#pragma unroll
+        for (int qn = 0; qn < kSwN; ++qn) {
+          const float ms = (m_used[qn] == sw_ninf()) ? 0.f : m_used[qn];
+          const float pv = fast_exp2(sv[qn] - ms);
+          l_thr[qn] += pv;
+          if constexpr (!KV8) {
+            // element (query qn, key row): 2 bytes at atom = row / 64, chunk = (row % 64) / 8
+            const int ch = (row & 63) >> 3;
+            uint16_t* dst = reinterpret_cast<uint16_t*>(pt + (row >> 6) * SM::kQAtomBytes + qn * 128 + ((ch ^ (qn & 7)) << 4)) + (row & 7);
+            *dst = sw_to16<BF16>(pv);
+          } else {
+            const int ch = row >> 4;  // 16 keys per 16-byte chunk
+            uint16_t e2;
+            asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(e2) : "f"(0.f), "f"(pv));
+            pt[qn * 128 + ((ch ^ (qn & 7)) << 4) + (row & 15)] = (uint8_t)(e2 & 0xff);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[i & 1]);
+      }
+      // ---- segment epilogue: O^T (thread = channel d, 16 query columns), row sums reduced over the 128 keys
+      const int first_cta = sw_cta_of_tile(p, x * p.tph);
+      const int nparts = sw_cta_of_tile(p, (x + 1) * p.tph - 1) - first_cta + 1;
+      float* my_part = p.part + ((size_t)x * p.max_parts + (cta - first_cta)) * (size_t)(R * (D + 4));
+      {
+        float lw[kSwN];
+#pragma unroll
+        for (int qn = 0; qn < kSwN; ++qn) {
+          float v = l_thr[qn];
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+          lw[qn] = v;
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int qn = 0; qn < kSwN; ++qn) red_s[warp * kSwN + qn] = lw[qn];
+        }
+        named_bar_sync(2, kSmx);
+        uint32_t orow[16];
+        if (n > 0) {
+          const int il = it + n - 1;
+          mbar_wait(&pv_done[il & 1], (il >> 1) & 1);
+          tc_fence_after();
+          tmem_ld_32x32b_x16(tmem_o + lane_addr, orow);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int qn = 0; qn < kSwN; ++qn) orow[qn] = 0u;
+        }
+        float vs_d = 1.f;
+        if constexpr (KV8) vs_d = ch_scale[D + row];
+#pragma unroll
+        for (int qn = 0; qn < kSwN; ++qn)
+          if (qn < R) __stcg(my_part + qn * (D + 4) + row, __uint_as_float(orow[qn]) * vs_d);   // thread = channel d
+        if (tid < R) {
+          const float lsum = red_s[tid] + red_s[kSwN + tid] + red_s[2 * kSwN + tid] + red_s[3 * kSwN + tid];
+          float mq = sw_ninf();
+#pragma unroll
+          for (int qn = 0; qn < kSwN; ++qn) mq = (qn == tid) ? m_used[qn] : mq;
+          __stcg(my_part + tid * (D + 4) + D, mq);
+          __stcg(my_part + tid * (D + 4) + D + 1, lsum);
+        }
+        tc_fence_before();
+      }
+      it += n;
+      __threadfence();
+      named_bar_sync(1, kSmx);
+      if (tid == 0) s_misc[0] = (int)atomicAdd(&p.tickets[x], 1u);
+      named_bar_sync(1, kSmx);
+      if (s_misc[0] == nparts - 1) {
+        __threadfence();
+        if (tid == 0) p.tickets[x] = 0;
+        const float* parts = p.part + (size_t)x * p.max_parts * (size_t)(R * (D + 4));
+        for (int idx = tid; idx < R * D; idx += kSmx) {
+          const int r = idx / D, d = idx - r * D;
+          float M = sw_ninf();
+          for (int qi = 0; qi < nparts; ++qi) M = fmaxf(M, __ldcg(parts + (size_t)qi * (R * (D + 4)) + r * (D + 4) + D));
+          const float Ms = (M == sw_ninf()) ? 0.f : M;
+          float acc = 0.f, Lsum = 0.f;
+          for (int qi = 0; qi < nparts; ++qi) {
+            const float* pp = parts + (size_t)qi * (R * (D + 4)) + r * (D + 4);
+            const float sc = fast_exp2(__ldcg(pp + D) - Ms);
+            acc = fmaf(__ldcg(pp + d), sc, acc);
+            Lsum = fmaf(__ldcg(pp + D + 1), sc, Lsum);
+          }
+          const float o_norm = Lsum > 0.f ? acc / Lsum : 0.f;
+          const float lse2 = Lsum > 0.f ? Ms + fast_log2(Lsum) : sw_ninf();
+          if (world == 1) {
+            store_out(x, r, d, o_norm, lse2);
+          } else if (!p.comm.skip_publish) {
+            for (int dst = 0; dst < world; ++dst) {
+              uint2* wp = word_ptr(dst, p.comm.rank, x) + r * (D + 2);
+              ll_store(wp + d, o_norm);
+              if (d == 0) ll_store(wp + D, lse2);
+            }
+          }
+        }
+        if (world > 1) {
+          if (tid == 0) {
+            t_publish = globaltimer_ns();
+            const int np = s_misc[1];
+            if (np < kSwMaxPending) { pending[np] = x; s_misc[1] = np + 1; }
+            else s_misc[2] = x + 1;
+          }
+          named_bar_sync(1, kSmx);
+          if (s_misc[2] != 0) {
+            named_bar_sync(1, kSmx);
+            if (tid == 0) s_misc[2] = 0;
+            combine_ranks(x);
+          }
+        }
+      }
+      named_bar_sync(1, kSmx);  // Q / P^T smem and s_misc reuse by the next segment
+      t = tn;
+    }
+    if (world > 1) {
+      named_bar_sync(1, kSmx);
+      const int np = s_misc[1];
+      for (int u = 0; u < np; ++u) combine_ranks(pending[u]);
+      if (tid == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(&p.tickets[BH], 1u);
+        if (done == gridDim.x - 1) {
+          p.tickets[BH] = 0;
+          __threadfence();
+          *reinterpret_cast<volatile uint32_t*>(p.comm.epoch) = epoch;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) { tc_fence_after(); tmem_dealloc<128>(tmem); }
+}
+
+inline CommCtx sw_device_ctx(const CommCtxHost& h) {
+  CommCtx c;
+  c.rank = h.rank;
+  c.world = h.world;
+  for (int i = 0; i < kMaxWorld; ++i) {
+    c.data[i] = reinterpret_cast<float*>(h.data[i]);
+    c.flags[i] = reinterpret_cast<uint32_t*>(h.flags[i]);
+  }
+  c.epoch = reinterpret_cast<uint32_t*>(h.epoch);
+  c.status = reinterpret_cast<uint32_t*>(h.status);
+  c.timeout_ns = h.timeout_ns;
+  c.skip_publish = h.skip_publish;
+  return c;
+}
+
+template <bool BF16, bool KV8>
+void launch_sw(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeSwParams& p, int grid, cudaStream_t stream) {
+  auto kern = decode_swap_kernel<BF16, KV8>;
+  static bool configured = false;
+  if (!configured) {
+    TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SwSmem<KV8>::kTotal));
+    configured = true;
+  }
+  kern<<<grid, kSwThreads, SwSmem<KV8>::kTotal, stream>>>(kmap, vmap, p);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace
+
+void decode_swap_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
+                        uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream, const float* kscale,
+                        const float* vscale) {
+  const bool kv8 = kscale != nullptr;
+  if (s.D != 128) throw std::runtime_error("decode_swap: head_dim must be 128");
+  if (s.Hq % s.Hkv != 0) throw std::runtime_error("decode_swap: Hq must be a multiple of Hkv");
+  const int G = s.Hq / s.Hkv;
+  const int R = G * s.Sq;
+  if (R > kSwN) throw std::runtime_error("decode_swap: (Hq / Hkv) * Sq must be <= 16");
+  if (s.S <= 0) throw std::runtime_error("decode_swap: empty KV shard");
+  int grid, max_parts, rows;
+  size_t pf, cb;
+  decode_tc_plan(s, nsm, &grid, &max_parts, &rows, &pf, &cb);   // same split / workspace as decode_tc
+  if (comm.world > 1) {
+    const size_t need = (size_t)2 * comm.world * s.B * s.Hkv * R * (s.D + 2) * 8;
+    if (need > comm.data_bytes) throw std::runtime_error("decode_swap: symmetric buffer too small for this problem");
+  }
+  const int eb = kv8 ? 1 : 2;
+  CUtensorMap kmap = make_tmap_bhsd(k, eb, s.B, s.Hkv, s.S, s.D, s.k_sb, s.k_sh, s.k_ss, 128 / eb, kSwKV, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap vmap = make_tmap_bhsd(v, eb, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 128 / eb, kSwKV, CU_TENSOR_MAP_SWIZZLE_128B);
+  DecodeSwParams p;
+  p.kscale = kscale; p.vscale = vscale;
+  p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
+  p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S; p.R = R;
+  p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
+  p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;
+  p.q_sb = s.q_sb; p.q_sh = s.q_sh; p.q_ss = s.q_ss; p.o_sb = s.o_sb; p.o_sh = s.o_sh; p.o_ss = s.o_ss;
+  p.tph = (s.S + kSwKV - 1) / kSwKV;
+  p.total_tiles = s.B * s.Hkv * p.tph;
+  p.tiles_q = p.total_tiles / grid;
+  p.tiles_rem = p.total_tiles % grid;
+  p.max_parts = max_parts;
+  p.jvis = p.tph;
+  if (s.causal) {
+    const long long last = s.q_pos0 + s.Sq - 1 - s.kv_pos0;
+    p.jvis = (int)std::max<long long>(0, std::min<long long>(p.tph, last < 0 ? 0 : last / kSwKV + 1));
+  }
+  p.comm = sw_device_ctx(comm);
+  if (kv8) { if (s.is_bf16) launch_sw<true, true>(kmap, vmap, p, grid, stream); else launch_sw<false, true>(kmap, vmap, p, grid, stream); }
+  else { if (s.is_bf16) launch_sw<true, false>(kmap, vmap, p, grid, stream); else launch_sw<false, false>(kmap, vmap, p, grid, stream); }
+}
+
+}  // namespace ta

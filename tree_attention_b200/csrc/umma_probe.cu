@@ -101,7 +101,101 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// ---- block-scaled fp8 probe: C[128, N] = (A8 o SFA)[128, 128] x (B8 o SFB)[N, 128]^T, e4m3 + UE8M0 per 32 ----
+struct BsProbeParams {
+  const uint32_t* sfa;  // [128] words: 4 UE8M0 bytes per row (K-blocks 0..3)
+  const uint32_t* sfb;  // [N] words
+  float* c;
+  int N;
+};
+
+__global__ void __launch_bounds__(128, 1)
+umma_bs_probe_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
+                     const BsProbeParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = p.N;
+  uint8_t* a_s = smem;              // [128 rows][128 B]  (K = 128 e4m3 = one swizzle atom)
+  uint8_t* b_s = smem + 128 * 128;  // [N rows][128 B]
+  if (tid == 0) { mbar_init(&bar_load, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bar_load, 128 * 128 + N * 128);
+    tma_load_2d(a_s, &amap, &bar_load, 0, 0);
+    tma_load_2d(b_s, &bmap, &bar_load, 0, 0);
+  }
+  // scale factors -> TMEM: lane l of EVERY lane quarter holds, in column j, the scale word of row 32 j + l
+  {
+    const uint32_t la = uint32_t(warp * 32) << 16;
+    tmem_st_32x32b_x4(tmem + la + 256, p.sfa[lane], p.sfa[32 + lane], p.sfa[64 + lane], p.sfa[96 + lane]);
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = (32 * j + lane < N) ? p.sfb[32 * j + lane] : 0x7f7f7f7fu;
+    tmem_st_32x32b_x4(tmem + la + 264, w[0], w[1], w[2], w[3]);
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    mbar_wait(&bar_load, 0);
+    tc_fence_after();
+    if (elect_one()) {
+      for (int kk = 0; kk < 4; ++kk) {  // K = 32 per instruction; scale byte kk of the column words
+        const uint32_t idesc = umma_idesc_block_scaled(0, 0, 128, N, 0, 0, kk, kk);
+        umma_ss_mxf8_block_scale(tmem, umma_smem_desc_sw128(smem_u32(a_s) + kk * 32, 0, 1024),
+                                 umma_smem_desc_sw128(smem_u32(b_s) + kk * 32, 0, 1024), idesc, tmem + 256, tmem + 264,
+                                 kk > 0 ? 1u : 0u);
+      }
+      umma_commit(&bar_mma);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 16) {
+    uint32_t v[16];
+    tmem_ld_32x32b_x16(tmem + (uint32_t(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p.c[(size_t)tid * N + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
+}
+
 }  // namespace
+
+void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const void* sfb, float* c, int N,
+                          cudaStream_t stream) {
+  if (N % 16 != 0 || N < 16 || N > 128) throw std::runtime_error("umma_bs_probe: bad N");
+  auto enc = get_encode_tiled();
+  auto mk = [&](const void* base, uint64_t rows) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {128, rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {128, (cuuint32_t)rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("umma_bs_probe: cuTensorMapEncodeTiled failed " + std::to_string((int)r));
+    return m;
+  };
+  CUtensorMap amap = mk(a8, 128), bmap = mk(b8, N);
+  BsProbeParams p{reinterpret_cast<const uint32_t*>(sfa), reinterpret_cast<const uint32_t*>(sfb), c, N};
+  const size_t smem = 1024 + 128 * 128 + (size_t)N * 128;
+  TA_CUDA_CHECK(cudaFuncSetAttribute(umma_bs_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_bs_probe_kernel<<<1, 128, smem, stream>>>(amap, bmap, p);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
 
 void umma_probe_launch(const void* a, const void* b, float* c, int N, int K, int b_mn_major, int a_from_tmem,
                        cudaStream_t stream) {

@@ -55,13 +55,15 @@ class TreeDecodeSession:
         self.launches_per_step = max(1, -(-rows // 4)) if local_ops.decode_eligible(self.q_static, k0) else 1
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         graphable = self.device.type == "cuda" and (world == 1 or backend in ("fused", "symm", "auto"))
-        self._use_graph = bool(use_graph and graphable and not pdl)
+        self._use_graph = bool(use_graph and graphable)
         self._prepared = False
 
     # -- internals ---------------------------------------------------------------------------------
-    def _eager(self, q: torch.Tensor, layer: int) -> torch.Tensor:
+    def _eager(self, q: torch.Tensor, layer: int, use_pdl: bool = False) -> torch.Tensor:
         k, v = self.kv[layer]
-        pdl = min(self.pdl, 1) if self._kv_dirty else self.pdl
+        pdl = 0
+        if use_pdl:
+            pdl = min(self.pdl, 1) if self._kv_dirty else self.pdl
         self._kv_dirty = False
         return tree_attention(q, k, v, group=self.group, causal=self.causal, softmax_scale=self.scale,
                               backend=self.backend, schedule=self.schedule, decode_pdl=pdl)
@@ -91,6 +93,8 @@ class TreeDecodeSession:
         self._prepare()
         if q is not None and q.data_ptr() != self.q_static.data_ptr():
             self.q_static.copy_(q, non_blocking=True)
+        if self.pdl:  # throughput path: eager launches chained by programmatic dependent launch
+            return self._eager(self.q_static, layer, use_pdl=True)
         if self.graphs:
             self.graphs[layer].replay()
             return self.out_static[layer]
@@ -98,9 +102,16 @@ class TreeDecodeSession:
         return self.out_static[layer]
 
     def step(self, q_host: torch.Tensor, out_host: torch.Tensor, layer: int) -> torch.Tensor:
-        """End-to-end step: pinned host query -> device, attention, result -> pinned host, synchronised."""
+        """End-to-end (latency) step: pinned host query -> device, attention, result -> pinned host, synchronised.
+        Uses the CUDA-graph replay when one was captured (lowest host overhead for a lone step)."""
+        layer %= len(self.kv)
+        self._prepare()
         self.q_static.copy_(q_host, non_blocking=True)
-        out = self.step_device(None, layer)
+        if self.graphs:
+            self.graphs[layer].replay()
+            out = self.out_static[layer]
+        else:
+            out = self._eager(self.q_static, layer)
         out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return out_host

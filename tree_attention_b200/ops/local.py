@@ -85,7 +85,7 @@ def decode_attention(
     impl = os.environ.get("TREE_ATTN_DECODE_IMPL", impl)
     if impl == "auto":
         impl = "simt" if rows_total == 1 else "tc"
-    if impl == "tc":
+    if impl in ("tc", "swap"):
         if q.stride(2) % 8 != 0 and sq > 1:
             q = q.contiguous()
         grid, max_parts, rows, part_floats, _ = C.decode_tc_plan(b, hq, hkv, sq, s, d)
@@ -95,7 +95,7 @@ def decode_attention(
         if lse is None and return_lse:
             lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
         C.decode_tc_fwd(q, k, v, out, lse, ws["part"], ws["tickets"], comm, float(softmax_scale), bool(causal),
-                        int(q_pos0), int(kv_pos0))
+                        int(q_pos0), int(kv_pos0), impl == "swap")
         return out, lse
     grid, max_parts, rows, part_floats, _, _ = C.decode_plan(b, hq, hkv, sq, s, d)
     ws = _workspace(q.device, "decode", part_floats, b * hkv + 2)
@@ -143,8 +143,10 @@ def decode_attention_fp8(
     kv_pos0: int = 0,
     comm=None,
     return_lse: bool = True,
+    impl: str = "auto",
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """tcgen05 (kind::f8f6f4) decode over a per-channel-scaled e4m3 KV shard (``ops.quant.FP8ChannelTensor``)."""
+    """tcgen05 (kind::f8f6f4) decode over a per-channel-scaled e4m3 KV shard (``ops.quant.FP8ChannelTensor``).
+    ``impl``: ``"swap"`` (keys on the TMEM lanes, <= 16 packed query rows) or ``"tc"`` (query rows on the lanes)."""
     C = _build.load()
     q = _as_bhsd(q)
     b, hq, sq, d = q.shape
@@ -155,8 +157,13 @@ def decode_attention_fp8(
     ws = _workspace(q.device, "decode_tc", part_floats, b * hkv + 2)
     out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
     lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device) if return_lse else None
+    import os
+
+    impl = os.environ.get("TREE_ATTN_DECODE_FP8_IMPL", impl)
+    if impl == "auto":
+        impl = "swap" if rows <= 16 else "tc"
     C.decode_tc_fwd8(q, k.data, v.data, k.scales, v.scales, out, lse, ws["part"], ws["tickets"], comm,
-                     float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0))
+                     float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0), impl == "swap")
     return out, lse
 
 
