@@ -27,7 +27,7 @@ for s in a.seq:
         return L.decode_attention(q, *kvs[i[0] % n], 0.088, return_lse=False, impl="simt")
     def fc8():
         i[0] += 1
-        return L.decode_attention_fp8(q, *c8[i[0] % n], 0.088, return_lse=False)
+        return L.decode_attention_fp8(q, *c8[i[0] % n], 0.088, return_lse=False, impl="tc")
     def fsw():
         i[0] += 1
         return L.decode_attention(q, *kvs[i[0] % n], 0.088, return_lse=False, impl="swap")

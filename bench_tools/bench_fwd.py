@@ -66,6 +66,8 @@ def main():
             res["tcgen05_own_v1_m128"] = t["median_ms"]
             t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=3), a.steps, a.warmup)
             res["tcgen05_own_v3_colsplit"] = t["median_ms"]
+            t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=4), a.steps, a.warmup)
+            res["tcgen05_own_v4_m256"] = t["median_ms"]
             if a.libs:
                 try:
                     from flash_attn import flash_attn_func

@@ -56,6 +56,21 @@ def _worker_fused(rank, world):
                 dist.all_gather(outs, out.contiguous())
                 for o in outs:
                     assert torch.equal(o, outs[0]), f"{backend}/{sched}: ranks disagree bitwise"
+    # per-channel fp8 KV cache through the fused tcgen05 decode kernels (swap-AB for <= 16 rows, packed rows above)
+    from tree_attention_b200.ops.quant import FP8ChannelTensor
+
+    for (b, hq, hkv, sq, s) in [(1, 8, 8, 1, 2048), (2, 8, 2, 2, 1111), (1, 32, 1, 1, 777)]:
+        q, k, v = ta.make_data((b, hq, s, 128), rank, dev, dtype=torch.bfloat16, sq=sq, num_kv_heads=hkv, log=False)
+        k8, v8 = FP8ChannelTensor.from_float(k), FP8ChannelTensor.from_float(v)
+        o_ref, l_ref = _oracle(q, k8.dequantize(torch.bfloat16), v8.dequantize(torch.bfloat16), world, 128 ** -0.5, False)
+        out, lse = ta.tree_attention(q, k8, v8, return_lse=True)
+        torch.cuda.synchronize()
+        assert (out.float() - o_ref).abs().max().item() < 6e-2, (hq, hkv, sq)
+        assert (lse - l_ref).abs().max().item() < 6e-2, (hq, hkv, sq)
+        outs = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(outs, out.contiguous())
+        for o in outs:
+            assert torch.equal(o, outs[0]), "fp8 fused decode: ranks disagree bitwise"
 
 
 @need2

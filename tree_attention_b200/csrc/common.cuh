@@ -47,6 +47,22 @@ __device__ __forceinline__ float fast_log2(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// explicit shared-state-space accesses (pointers carved out of the dynamic smem block are generic to the compiler)
+__device__ __forceinline__ void st_shared_v4f(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 ld_shared_v4f(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t a, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
+}
+__device__ __forceinline__ void st_shared_u8(uint32_t a, uint16_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "h"(v) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

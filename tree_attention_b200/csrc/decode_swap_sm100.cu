@@ -87,8 +87,8 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   uint8_t* v_s = k_s + NS * SM::kTileBytes;
   uint8_t* q_s = v_s + NS * SM::kTileBytes;          // [atoms][16 rows][128 B]
   uint8_t* p_s = q_s + SM::kQBytes;                  // [2][atoms][16 rows][128 B]
-  int* xch = reinterpret_cast<int*>(p_s + 2 * SM::kPBytes);   // [2 parity][4 warps][16] column maxima (ordered ints)
-  float* red_s = reinterpret_cast<float*>(xch + 2 * 4 * kSwN); // [4 warps][16] row-sum reduction
+  float* xch = reinterpret_cast<float*>(p_s + 2 * SM::kPBytes);   // [2 parity][4 warps][16] column maxima
+  float* red_s = xch + 2 * 4 * kSwN; // [4 warps][16] row-sum reduction
   uint64_t* bars = reinterpret_cast<uint64_t*>(red_s + 4 * kSwN);
   uint64_t* q_ready = bars;            // count 128
   uint64_t* k_full = bars + 1;
@@ -305,6 +305,7 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     };
 
 
+    const uint32_t xch_a = smem_u32(xch), pt_a = smem_u32(p_s);
     int it = 0;
     for (int t = t_lo; t < t_hi;) {
       int x, j0, n, tn;
@@ -372,9 +373,20 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         for (int qn = 0; qn < kSwN; ++qn) sc_q[qn] = p.scale_log2;
       }
 
-      float m_used[kSwN], l_thr[kSwN];
+      // Running state per query column.  m_used is the (stale) maximum the exponent uses; it is refreshed for all
+      // 16 queries at once, and only when some column maximum grew by more than kSwRescale (exact lazy rescale:
+      // the same m_used is applied to P and to the row sums, so the final normalisation is exact).
+      float m_used[kSwN], neg_ms[kSwN], l_thr[kSwN];
 #pragma unroll
-      for (int qn = 0; qn < kSwN; ++qn) { m_used[qn] = sw_ninf(); l_thr[qn] = 0.f; }
+      for (int qn = 0; qn < kSwN; ++qn) { m_used[qn] = sw_ninf(); neg_ms[qn] = 0.f; l_thr[qn] = 0.f; }
+      // P^T store addresses: element (query qn, key row) of the 128B-swizzled K-major B tile
+      uint32_t pa[8];
+      {
+        const int ch = KV8 ? (row >> 4) : ((row & 63) >> 3);       // 16-byte chunk of this key inside a 128-byte row
+        const uint32_t pbase = KV8 ? uint32_t(row & 15) : uint32_t((row >> 6) * SM::kQAtomBytes + (row & 7) * 2);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pa[c] = pbase + uint32_t((ch ^ c) << 4);
+      }
       for (int jj = 0; jj < n; ++jj) {
         const int i = it + jj;
         const int n0 = (j0 + jj) * kSwKV;
@@ -383,61 +395,79 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         uint32_t sr[16];
         tmem_ld_32x32b_x16(tmem + (i & 1) * 32 + lane_addr, sr);
         tmem_ld_wait();
-        const bool row_in = (n0 + row) < p.S;
-        const long long kvpos = p.kv_pos0 + n0 + row;
         float sv[kSwN];
 #pragma unroll
-        for (int qn = 0; qn < kSwN; ++qn) {
-          const bool vis = row_in && qn < R && (!p.causal || kvpos <= p.q_pos0 + qi_of[qn]);
-          sv[qn] = vis ? __uint_as_float(sr[qn]) * sc_q[qn] : sw_ninf();
-        }
-        // column maxima over the 128 keys: redux within the warp, smem across the 4 warps
-        int* xc = xch + (i & 1) * 4 * kSwN;
+        for (int qn = 0; qn < kSwN; ++qn) sv[qn] = __uint_as_float(sr[qn]) * sc_q[qn];
+        if (p.causal || n0 + kSwKV > p.S) {  // edge / causal tiles only (padding columns qn >= R hold q = 0: harmless)
+          const bool row_in = (n0 + row) < p.S;
+          const long long kvpos = p.kv_pos0 + n0 + row;
 #pragma unroll
-        for (int qn = 0; qn < kSwN; ++qn) {
-          const int wm = __reduce_max_sync(0xffffffffu, sw_f2ord(sv[qn]));
-          if (lane == qn) xc[warp * kSwN + qn] = wm;
+          for (int qn = 0; qn < kSwN; ++qn) {
+            const bool vis = row_in && (!p.causal || kvpos <= p.q_pos0 + qi_of[qn]);
+            sv[qn] = vis ? sv[qn] : sw_ninf();
+          }
+        }
+        // column maxima over the 128 keys: redux within the warp, one smem exchange across the 4 warps
+        const uint32_t xc = xch_a + uint32_t(i & 1) * (4 * kSwN * 4);
+        {
+          float wm[kSwN];
+#pragma unroll
+          for (int qn = 0; qn < kSwN; ++qn) wm[qn] = sw_ord2f(__reduce_max_sync(0xffffffffu, sw_f2ord(sv[qn])));
+          if (lane == 0) {
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4)
+              st_shared_v4f(xc + warp * (kSwN * 4) + g4 * 16, wm[4 * g4], wm[4 * g4 + 1], wm[4 * g4 + 2], wm[4 * g4 + 3]);
+          }
         }
         named_bar_sync(2, kSmx);
-        bool any_refresh = false;
-        float alpha[kSwN];
+        float m4[kSwN];
 #pragma unroll
-        for (int qn = 0; qn < kSwN; ++qn) {
-          const int m4 = max(max(xc[qn], xc[kSwN + qn]), max(xc[2 * kSwN + qn], xc[3 * kSwN + qn]));
-          const float m_new = fmaxf(m_used[qn], sw_ord2f(m4));
-          const bool refresh = (m_new - m_used[qn] > kSwRescale) || (m_used[qn] == sw_ninf() && m_new != sw_ninf());
-          alpha[qn] = refresh ? fast_exp2(m_used[qn] - m_new) : 1.f;
-          if (refresh) { m_used[qn] = m_new; l_thr[qn] *= alpha[qn]; any_refresh = true; }
+        for (int g4 = 0; g4 < 4; ++g4) {
+          float4 a0 = ld_shared_v4f(xc + g4 * 16), a1 = ld_shared_v4f(xc + kSwN * 4 + g4 * 16);
+          float4 a2 = ld_shared_v4f(xc + 2 * kSwN * 4 + g4 * 16), a3 = ld_shared_v4f(xc + 3 * kSwN * 4 + g4 * 16);
+          m4[4 * g4 + 0] = fmaxf(fmaxf(a0.x, a1.x), fmaxf(a2.x, a3.x));
+          m4[4 * g4 + 1] = fmaxf(fmaxf(a0.y, a1.y), fmaxf(a2.y, a3.y));
+          m4[4 * g4 + 2] = fmaxf(fmaxf(a0.z, a1.z), fmaxf(a2.z, a3.z));
+          m4[4 * g4 + 3] = fmaxf(fmaxf(a0.w, a1.w), fmaxf(a2.w, a3.w));
         }
-        if (any_refresh && jj > 0) {  // uniform across the CTA: every thread sees the same maxima
-          mbar_wait(&pv_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
-          tc_fence_after();
-          uint32_t orow[16];
-          tmem_ld_32x32b_x16(tmem_o + lane_addr, orow);
-          tmem_ld_wait();
+        float grow = sw_ninf();   // max over queries of (new maximum - used maximum); NaN (-inf - -inf) drops out of fmaxf
 #pragma unroll
-          for (int qn = 0; qn < kSwN; ++qn) orow[qn] = __float_as_uint(__uint_as_float(orow[qn]) * alpha[qn]);
-          tmem_st_32x32b_x16(tmem_o + lane_addr, orow);
-          tmem_st_wait();
+        for (int qn = 0; qn < kSwN; ++qn) grow = fmaxf(grow, m4[qn] - m_used[qn]);
+        if (grow > kSwRescale) {  // uniform across the CTA: every thread sees the same maxima
+          float alpha[kSwN];
+#pragma unroll
+          for (int qn = 0; qn < kSwN; ++qn) {
+            const float m_new = fmaxf(m_used[qn], m4[qn]);
+            alpha[qn] = (m_new == sw_ninf()) ? 1.f : fast_exp2(m_used[qn] - m_new);
+            l_thr[qn] *= alpha[qn];
+            m_used[qn] = m_new;
+            neg_ms[qn] = (m_new == sw_ninf()) ? 0.f : -m_new;
+          }
+          if (jj > 0) {
+            mbar_wait(&pv_done[(i - 1) & 1], ((i - 1) >> 1) & 1);
+            tc_fence_after();
+            uint32_t orow[16];
+            tmem_ld_32x32b_x16(tmem_o + lane_addr, orow);
+            tmem_ld_wait();
+#pragma unroll
+            for (int qn = 0; qn < kSwN; ++qn) orow[qn] = __float_as_uint(__uint_as_float(orow[qn]) * alpha[qn]);
+            tmem_st_32x32b_x16(tmem_o + lane_addr, orow);
+            tmem_st_wait();
+          }
         }
         // the P^T buffer of tile i was last read by PV(i-2)
         if (jj >= 2) { mbar_wait(&pv_done[i & 1], ((i - 2) >> 1) & 1); }
-        uint8_t* pt = p_s + (i & 1) * SM::kPBytes;
+        const uint32_t pt = pt_a + uint32_t(i & 1) * SM::kPBytes;
 #pragma unroll
         for (int qn = 0; qn < kSwN; ++qn) {
-          const float ms = (m_used[qn] == sw_ninf()) ? 0.f : m_used[qn];
-          const float pv = fast_exp2(sv[qn] - ms);
+          const float pv = fast_exp2(sv[qn] + neg_ms[qn]);
           l_thr[qn] += pv;
           if constexpr (!KV8) {
-            // element (query qn, key row): 2 bytes at atom = row / 64, chunk = (row % 64) / 8
-            const int ch = (row & 63) >> 3;
-            uint16_t* dst = reinterpret_cast<uint16_t*>(pt + (row >> 6) * SM::kQAtomBytes + qn * 128 + ((ch ^ (qn & 7)) << 4)) + (row & 7);
-            *dst = sw_to16<BF16>(pv);
+            st_shared_u16(pt + pa[qn & 7] + qn * 128, sw_to16<BF16>(pv));
           } else {
-            const int ch = row >> 4;  // 16 keys per 16-byte chunk
             uint16_t e2;
             asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(e2) : "f"(0.f), "f"(pv));
-            pt[qn * 128 + ((ch ^ (qn & 7)) << 4) + (row & 15)] = (uint8_t)(e2 & 0xff);
+            st_shared_u8(pt + pa[qn & 7] + qn * 128, e2);
           }
         }
         fence_proxy_async_smem();
@@ -599,9 +629,9 @@ void decode_swap_launch(const AttnShape& s, const void* q, const void* k, const 
   const int R = G * s.Sq;
   if (R > kSwN) throw std::runtime_error("decode_swap: (Hq / Hkv) * Sq must be <= 16");
   if (s.S <= 0) throw std::runtime_error("decode_swap: empty KV shard");
-  int grid, max_parts, rows;
-  size_t pf, cb;
-  decode_tc_plan(s, nsm, &grid, &max_parts, &rows, &pf, &cb);   // same split / workspace as decode_tc
+  int grid, max_parts;
+  // one persistent CTA per SM (the driver keeps tcgen05 kernels at one resident CTA per SM: a second CTA only queues)
+  decode_tc_split(s, nsm, &grid, &max_parts);   // split / workspace of decode_tc
   if (comm.world > 1) {
     const size_t need = (size_t)2 * comm.world * s.B * s.Hkv * R * (s.D + 2) * 8;
     if (need > comm.data_bytes) throw std::runtime_error("decode_swap: symmetric buffer too small for this problem");

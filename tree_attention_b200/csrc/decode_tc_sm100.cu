@@ -589,20 +589,25 @@ void launch_tc(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeTcP
 
 }  // namespace
 
-void decode_tc_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, int* rows, size_t* part_floats,
-                    size_t* comm_bytes) {
+// split of the (B x Hkv x tiles) work list over ncta persistent CTAs; max_parts bounds the CTAs sharing one KV head
+void decode_tc_split(const AttnShape& s, int ncta, int* grid, int* max_parts) {
   const int BH = s.B * s.Hkv;
   const int tph = (s.S + kTN - 1) / kTN;
   const long long total = (long long)BH * tph;
-  const int g = (int)std::min<long long>(nsm, std::max<long long>(total, 1));
+  const int g = (int)std::min<long long>(ncta, std::max<long long>(total, 1));
   const int q = (int)(total / g);
   int mp = std::min(g, (tph + std::max(q, 1) - 1) / std::max(q, 1) + 1);
-  mp = std::max(mp, 1);
-  const int R = (s.Hq / s.Hkv) * s.Sq;
   *grid = g;
-  *max_parts = mp;
+  *max_parts = std::max(mp, 1);
+}
+
+void decode_tc_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, int* rows, size_t* part_floats,
+                    size_t* comm_bytes) {
+  const int BH = s.B * s.Hkv;
+  decode_tc_split(s, nsm, grid, max_parts);
+  const int R = (s.Hq / s.Hkv) * s.Sq;
   *rows = R;
-  *part_floats = (size_t)BH * mp * R * (s.D + 4);
+  *part_floats = (size_t)BH * *max_parts * R * (s.D + 4);
   *comm_bytes = (size_t)2 * kMaxWorldHost * BH * R * (s.D + 2) * 8;
 }
 

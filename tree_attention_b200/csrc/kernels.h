@@ -48,6 +48,7 @@ void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const 
 // four UE8M0 exponents (one per 32 elements); strides in AttnShape are then in BYTES == elements.
 
 // ---- tensor-core decode: the R = (Hq/Hkv) x Sq <= 128 query rows of a KV head packed into one tcgen05 tile ----
+void decode_tc_split(const AttnShape& s, int ncta, int* grid, int* max_parts);
 void decode_tc_plan(const AttnShape& s, int num_sms, int* grid, int* max_parts, int* rows, size_t* part_floats,
                     size_t* comm_bytes);
 // kscale / vscale != null: K, V are e4m3 bytes with per-CHANNEL fp32 scales (B, Hkv, D); both GEMMs then run as
@@ -87,6 +88,9 @@ void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const voi
 size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
 // M = 128 with two softmax warpgroups splitting the score columns (two resident softmax warps per SM sub-partition)
 void attn_fwd3_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                      const CommCtxHost& comm, cudaStream_t stream);
+// two ping-ponged query tiles per CTA (M = 256), single-pass register softmax, setmaxnreg register split
+void attn_fwd4_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                       const CommCtxHost& comm, cudaStream_t stream);
 // two ping-ponged query tiles per CTA (M = 256); same contract and symmetric-buffer layout
 void attn_fwd2_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,

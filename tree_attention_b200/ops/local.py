@@ -71,7 +71,8 @@ def decode_attention(
 
     ``impl``: ``"simt"`` (CUDA-core math; HBM-bound for one query row per KV head), ``"tc"`` (tcgen05: the
     (Hq/Hkv) x Sq rows of a KV head packed into one MMA tile; stays HBM-bound for GQA / multi-token decode),
-    ``"auto"`` = simt for a single row, tc otherwise.
+    ``"swap"`` (tcgen05 swap-AB: keys on the TMEM lanes, <= 16 packed rows, head_dim 128; the fastest for small
+    GQA groups), ``"auto"`` = simt for a single row, swap for 2..16 rows at head_dim 128, tc otherwise.
     ``pdl``: programmatic dependent launch for back-to-back decode steps (simt kernel): 1 = the next launch may
     start its prologue while this one drains; 2 = additionally prefetch K/V tiles before waiting on the previous
     kernel -- only valid when the KV cache was not written by the immediately preceding kernel of the stream."""
@@ -84,7 +85,7 @@ def decode_attention(
     rows_total = (hq // hkv) * sq
     impl = os.environ.get("TREE_ATTN_DECODE_IMPL", impl)
     if impl == "auto":
-        impl = "simt" if rows_total == 1 else "tc"
+        impl = "simt" if rows_total == 1 else ("swap" if (rows_total <= 16 and d == 128) else "tc")
     if impl in ("tc", "swap"):
         if q.stride(2) % 8 != 0 and sq > 1:
             q = q.contiguous()
