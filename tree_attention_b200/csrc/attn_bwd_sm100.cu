@@ -188,35 +188,42 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ 
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    // The whole warp runs the issue loop convergently (descriptors stay in uniform registers, no per-MMA R2UR
+    // waterfall); one elected lane issues the tcgen05 instructions.
+    {
+      const bool leader = elect_one();
       constexpr uint32_t fmt = BF16 ? 1u : 0u;
       constexpr uint32_t idesc_s = umma_idesc(fmt, fmt, kBM, kBN, 0, 0);   // [128 q] x [64 kv], K = d
       constexpr uint32_t idesc_dq = umma_idesc(fmt, fmt, kBM, D, 0, 1);    // [128 q] x [D], K = 64 kv, B MN-major
-      const uint32_t q_addr = smem_u32(q_s), do_addr = smem_u32(do_s);
+      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(q_s), 0, 1024), do_desc = umma_smem_desc_sw128(smem_u32(do_s), 0, 1024);
       auto issue_sdp = [&](int j) {
         const int st = j % NS;
         const uint32_t ph = (j / NS) & 1;
         const uint32_t buf = tmem + (j & 1) * 128;
         mbar_wait(&k_full[st], ph);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(k_s + st * SM::kSmallBytes);
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(k_s + st * SM::kSmallBytes), 0, 1024);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t offb = (kk / 4) * SM::kBigAtom + (kk % 4) * 32, offs = (kk / 4) * SM::kSmallAtom + (kk % 4) * 32;
-          umma_ss_f16(buf, umma_smem_desc_sw128(q_addr + offb, 0, 1024), umma_smem_desc_sw128(k_addr + offs, 0, 1024),
-                      idesc_s, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t offb = ((kk / 4) * SM::kBigAtom + (kk % 4) * 32) >> 4, offs = ((kk / 4) * SM::kSmallAtom + (kk % 4) * 32) >> 4;
+            umma_ss_f16(buf, q_desc + offb, k_desc + offs, idesc_s, kk > 0 ? 1u : 0u);
+          }
         }
+        __syncwarp();
         mbar_wait(&v_full[st], ph);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(v_s + st * SM::kSmallBytes);
+        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(v_s + st * SM::kSmallBytes), 0, 1024);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t offb = (kk / 4) * SM::kBigAtom + (kk % 4) * 32, offs = (kk / 4) * SM::kSmallAtom + (kk % 4) * 32;
-          umma_ss_f16(buf + 64, umma_smem_desc_sw128(do_addr + offb, 0, 1024), umma_smem_desc_sw128(v_addr + offs, 0, 1024),
-                      idesc_s, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t offb = ((kk / 4) * SM::kBigAtom + (kk % 4) * 32) >> 4, offs = ((kk / 4) * SM::kSmallAtom + (kk % 4) * 32) >> 4;
+            umma_ss_f16(buf + 64, do_desc + offb, v_desc + offs, idesc_s, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&v_empty[st]);
+          umma_commit(&sdp_full[j & 1]);
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(&sdp_full[j & 1]);
+        __syncwarp();
       };
       mbar_wait(qdo_full, 0);
       issue_sdp(0);
@@ -225,14 +232,16 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ 
         const int st = j % NS;
         mbar_wait(&ds_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(k_s + st * SM::kSmallBytes);
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(k_s + st * SM::kSmallBytes), SM::kSmallAtom, 1024);
         const uint32_t ds_tmem = tmem + (j & 1) * 128;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < kBN / 16; ++kk)
-          umma_ts_f16(tmem_dq, ds_tmem + kk * 8, umma_smem_desc_sw128(k_addr + kk * 2048, SM::kSmallAtom, 1024), idesc_dq,
-                      (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&k_empty[st]);
-        umma_commit(&dq_done[j & 1]);
+          for (int kk = 0; kk < kBN / 16; ++kk)
+            umma_ts_f16(tmem_dq, ds_tmem + kk * 8, k_desc + ((kk * 2048) >> 4), idesc_dq, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&k_empty[st]);
+          umma_commit(&dq_done[j & 1]);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -401,34 +410,39 @@ bwd_dkv_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();   // whole warp convergent, one elected lane issues (see bwd_dq_kernel)
       constexpr uint32_t fmt = BF16 ? 1u : 0u;
       constexpr uint32_t idesc_s = umma_idesc(fmt, fmt, kBM, kBN, 0, 0);    // [128 kv] x [64 q], K = d
       constexpr uint32_t idesc_acc = umma_idesc(fmt, fmt, kBM, D, 0, 1);    // [128 kv] x [D], K = 64 q, B MN-major
-      const uint32_t k_addr = smem_u32(k_s), v_addr = smem_u32(v_s);
+      const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(k_s), 0, 1024), v_desc = umma_smem_desc_sw128(smem_u32(v_s), 0, 1024);
       auto issue_sdp = [&](int it) {
         const int st = it % NS;
         const uint32_t ph = (it / NS) & 1;
         const uint32_t buf = tmem + (it & 1) * 128;
         mbar_wait(&q_full[st], ph);
         tc_fence_after();
-        const uint32_t q_addr = smem_u32(q_s + st * SM::kSmallBytes);
+        const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(q_s + st * SM::kSmallBytes), 0, 1024);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t offb = (kk / 4) * SM::kBigAtom + (kk % 4) * 32, offs = (kk / 4) * SM::kSmallAtom + (kk % 4) * 32;
-          umma_ss_f16(buf, umma_smem_desc_sw128(k_addr + offb, 0, 1024), umma_smem_desc_sw128(q_addr + offs, 0, 1024),
-                      idesc_s, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t offb = ((kk / 4) * SM::kBigAtom + (kk % 4) * 32) >> 4, offs = ((kk / 4) * SM::kSmallAtom + (kk % 4) * 32) >> 4;
+            umma_ss_f16(buf, k_desc + offb, q_desc + offs, idesc_s, kk > 0 ? 1u : 0u);
+          }
         }
+        __syncwarp();
         mbar_wait(&do_full[st], ph);
         tc_fence_after();
-        const uint32_t do_addr = smem_u32(do_s + st * SM::kSmallBytes);
+        const uint64_t do_desc = umma_smem_desc_sw128(smem_u32(do_s + st * SM::kSmallBytes), 0, 1024);
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t offb = (kk / 4) * SM::kBigAtom + (kk % 4) * 32, offs = (kk / 4) * SM::kSmallAtom + (kk % 4) * 32;
-          umma_ss_f16(buf + 64, umma_smem_desc_sw128(v_addr + offb, 0, 1024), umma_smem_desc_sw128(do_addr + offs, 0, 1024),
-                      idesc_s, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t offb = ((kk / 4) * SM::kBigAtom + (kk % 4) * 32) >> 4, offs = ((kk / 4) * SM::kSmallAtom + (kk % 4) * 32) >> 4;
+            umma_ss_f16(buf + 64, v_desc + offb, do_desc + offs, idesc_s, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&sdp_full[it & 1]);
         }
-        umma_commit(&sdp_full[it & 1]);
+        __syncwarp();
       };
       mbar_wait(kv_full, 0);
       issue_sdp(0);
@@ -437,20 +451,21 @@ bwd_dkv_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__
         const int st = it % NS;
         mbar_wait(&ds_full[it & 1], (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t q_addr = smem_u32(q_s + st * SM::kSmallBytes);
-        const uint32_t do_addr = smem_u32(do_s + st * SM::kSmallBytes);
+        const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(q_s + st * SM::kSmallBytes), SM::kSmallAtom, 1024);
+        const uint64_t do_desc = umma_smem_desc_sw128(smem_u32(do_s + st * SM::kSmallBytes), SM::kSmallAtom, 1024);
         const uint32_t buf = tmem + (it & 1) * 128;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < kBN / 16; ++kk)   // dV += P^T dO
-          umma_ts_f16(tmem_dv, buf + kk * 8, umma_smem_desc_sw128(do_addr + kk * 2048, SM::kSmallAtom, 1024), idesc_acc,
-                      (it > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&do_empty[st]);
+          for (int kk = 0; kk < kBN / 16; ++kk)   // dV += P^T dO
+            umma_ts_f16(tmem_dv, buf + kk * 8, do_desc + ((kk * 2048) >> 4), idesc_acc, (it > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&do_empty[st]);
 #pragma unroll
-        for (int kk = 0; kk < kBN / 16; ++kk)   // dK += dS^T Q
-          umma_ts_f16(tmem_dk, buf + 64 + kk * 8, umma_smem_desc_sw128(q_addr + kk * 2048, SM::kSmallAtom, 1024), idesc_acc,
-                      (it > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&q_empty[st]);
-        umma_commit(&acc_done[it & 1]);
+          for (int kk = 0; kk < kBN / 16; ++kk)   // dK += dS^T Q
+            umma_ts_f16(tmem_dk, buf + 64 + kk * 8, q_desc + ((kk * 2048) >> 4), idesc_acc, (it > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&q_empty[st]);
+          umma_commit(&acc_done[it & 1]);
+        }
+        __syncwarp();
       }
     }
     __syncwarp();

@@ -364,6 +364,7 @@ void launch_fwd3(const AttnShape& s, const void* q, const void* k, const void* v
   p.num_m_tiles = (s.Sq + kBlockM - 1) / kBlockM;
   p.n_items = p.num_m_tiles * s.Hq * s.B;
   p.lag = std::min(p.n_items, 2 * num_sms());
+  p.q_in_tmem = 0;
   p.comm = to_device_ctx(comm);
   if (kComm) {
     const size_t slot = (size_t)kBlockM * D * 2 + kBlockM * 4;

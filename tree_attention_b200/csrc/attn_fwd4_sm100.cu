@@ -8,8 +8,8 @@
 //     softmax runs, and every SM sub-partition holds two softmax warps that hide each other's MUFU / TMEM latency;
 //   * each K/V tile fetched from L2 feeds 256 query rows;
 //   * the softmax keeps the whole 128-score row in registers (one tcgen05.ld pass, FMNMX3 max, packed f32x2
-//     scale-subtract and row sum, lazy rescale); register budget via setmaxnreg: 216 for the softmax warpgroups,
-//     80 for the TMA / MMA warpgroup.
+//     scale-subtract and row sum, lazy rescale); register budget via setmaxnreg: 208 for the softmax warpgroups,
+//     88 for the TMA / MMA warpgroup.
 // TMEM: S_A [0,128) | S_B [128,256) | O_A [256,384) | O_B [384,512);  P_t aliases S_t[0,64).
 #include "attn_fwd_common.cuh"
 
@@ -121,9 +121,11 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  if (warp >= 8) {
+  // warpgroup 2 (TMA, MMA, two idle warps): one setmaxnreg site for the whole warpgroup
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 8) {
     // =============================== TMA producer ===============================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, 2 * SM::kTileBytes);
 #pragma unroll
@@ -148,7 +150,6 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
     }
   } else if (warp == 9) {
     // =============================== MMA issuer =================================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (lane == 0) {
       constexpr uint32_t fmt = BF16 ? 1u : 0u;
       constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kBlockM, kBlockN, 0, 0);
@@ -206,9 +207,10 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
       }
     }
     __syncwarp();
-  } else if (warp < 8) {
+  }
+  } else {
     // =============================== softmax warpgroups =========================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int t = warp >> 2;  // 0 = tile A, 1 = tile B
     if (t == 0 || has_b) {
       const int row = tid & (kWG - 1);
@@ -351,9 +353,6 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
       }
     }
   }
-  else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-  }
   tc_fence_before();
   __syncthreads();
   if (warp == 9) { tc_fence_after(); tmem_dealloc<512>(tmem); }
@@ -376,6 +375,7 @@ void launch_fwd4(const AttnShape& s, const void* q, const void* k, const void* v
   p.num_m_tiles = (s.Sq + kBlockM - 1) / kBlockM;
   p.n_items = p.num_m_tiles * s.Hq * s.B;
   p.lag = 0;
+  p.q_in_tmem = 0;
   p.comm = to_device_ctx(comm);
   const int num_pairs = (p.num_m_tiles + 1) / 2;
   const int n_compute = num_pairs * s.Hq * s.B;

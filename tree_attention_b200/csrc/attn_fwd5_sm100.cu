@@ -1,55 +1,60 @@
-// attn_fwd2 -- tcgen05 flash forward with TWO ping-ponged 128-row query tiles per CTA (M = 256).
+// attn_fwd5 -- tcgen05 flash forward: two 128-row query tiles per CTA (M = 256), BLOCK_N = 64, scores double-buffered
+// per query tile.
 //
-// Same contract as attn_fwd_sm100.cu (local partial (o, lse) or, in fused mode, the whole cross-GPU tree
-// combine in the same launch).  Differences that buy throughput:
-//   * two softmax warpgroups (A: warps 0-3, B: warps 4-7) each own one query tile; the single MMA thread
-//     interleaves  PV_A(j) | S_A(j+1) | PV_B(j) | S_B(j+1)  so that while one warpgroup runs its softmax the
-//     tensor pipe is busy with the other tile's GEMMs (two resident softmax warps per SM sub-partition hide
-//     each other's MUFU / TMEM latencies);
-//   * every K/V tile fetched from L2 feeds 256 query rows (half the L2->SMEM traffic per FLOP);
-//   * the softmax is two-pass over TMEM in 32-column chunks (max, then exp/pack), so a row needs ~40
-//     registers instead of 128 and the CTA runs 12 warps without spills.
-// TMEM: S_A [0,128) | S_B [128,256) | O_A [256,384) | O_B [384,512);  P_t aliases S_t[0,64).
+// Same contract as attn_fwd_sm100.cu (local partial (o, lse) or, in fused mode, the whole cross-GPU tree combine in
+// the same launch); the reference's matmul -> softmax -> matmul (/root/reference/model.py:74-80) as one pipeline.
+// It is "two M=128 pipelines in one CTA sharing every K/V tile":
+//   * softmax warpgroups A (warps 0-3) and B (warps 4-7) each own one query tile and TWO 64-column score buffers, so
+//     QK^T of step j+1 / j+2 is already in TMEM when the softmax of step j retires: a warpgroup never waits for the
+//     tensor pipe, and each SM sub-partition always has two softmax warps in flight (MUFU-bound, not latency-bound);
+//   * the MMA thread issues  PV_A(j) | S_A(j+2) | PV_B(j) | S_B(j+2);
+//   * single-pass register softmax (64 scores per thread per step), packed f32x2 math, lazy rescale;
+//     setmaxnreg: 208 registers for the softmax warpgroups, 88 for the TMA / MMA warpgroup.
+// TMEM (512 columns): S_A0 | S_A1 | S_B0 | S_B1 (64 each) | O_A | O_B (128 each);  P aliases the first 32 columns
+// of its score buffer.
 #include "attn_fwd_common.cuh"
 
 namespace ta {
 namespace {
 using namespace fwd_detail;
 
-constexpr int kFwd2Threads = 384;
+constexpr int kFwd5Threads = 384;
+constexpr int kBN = 64;   // keys per step
 constexpr int kWG = 128;
 
 template <int D>
-struct Fwd2Smem {
-  static constexpr int kStages = 2;
+struct Fwd5Smem {
+  static constexpr int kStages = 4;
   static constexpr int kAtoms = D / 64;
-  static constexpr int kTileBytes = 128 * D * 2;
+  static constexpr int kTileBytes = 128 * D * 2;     // one query tile
   static constexpr int kAtomBytes = 128 * 128;
-  static constexpr size_t kTotal = 1024 + size_t(2 + 2 * kStages) * kTileBytes + 256;
+  static constexpr int kKVBytes = kBN * D * 2;       // one K or V step tile
+  static constexpr int kKVAtomBytes = kBN * 128;
+  static constexpr size_t kTotal = 1024 + size_t(2) * kTileBytes + size_t(2 * kStages) * kKVBytes + 512;
 };
 
 template <int D, bool BF16, bool kComm>
-__global__ void __launch_bounds__(kFwd2Threads, 1)
-attn_fwd2_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
+__global__ void __launch_bounds__(kFwd5Threads, 1)
+attn_fwd5_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
                  const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap omap,
                  const FwdParams p, const int num_pairs, const int n_compute) {
-  using SM = Fwd2Smem<D>;
+  using SM = Fwd5Smem<D>;
   constexpr int NS = SM::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_s = smem;                          // [2 tiles]
   uint8_t* k_s = q_s + 2 * SM::kTileBytes;      // [NS]
-  uint8_t* v_s = k_s + NS * SM::kTileBytes;     // [NS]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + NS * SM::kTileBytes);
+  uint8_t* v_s = k_s + NS * SM::kKVBytes;       // [NS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + NS * SM::kKVBytes);
   uint64_t* q_full = bars;             // 1
   uint64_t* k_full = bars + 1;         // NS
   uint64_t* k_empty = k_full + NS;
   uint64_t* v_full = k_empty + NS;
   uint64_t* v_empty = v_full + NS;
-  uint64_t* s_full = v_empty + NS;     // 2 (per tile)
-  uint64_t* p_full = s_full + 2;       // 2
-  uint64_t* pv_done = p_full + 2;      // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* s_full = v_empty + NS;     // [tile 2][buffer 2]
+  uint64_t* p_full = s_full + 4;       // [tile 2][buffer 2]
+  uint64_t* pv_done = p_full + 4;      // [tile 2][step parity 2]: a softmax warpgroup may run two steps ahead of its PV
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint32_t epoch = 0;
@@ -74,7 +79,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
     const long long last_q = p.q_pos0 + min(m0 + 2 * kBlockM - 1, p.Sq - 1);
     n_end = (int)max(0LL, min((long long)p.S, last_q - p.kv_pos0 + 1));
   }
-  const int n_tiles = (n_end + kBlockN - 1) / kBlockN;
+  const int n_tiles = (n_end + kBN - 1) / kBN;
 
   // slot / item bookkeeping for the fused mode
   auto item_of = [&](int t) { return bh * p.num_m_tiles + (p.num_m_tiles - 1 - (pair * 2 + t)); };
@@ -88,7 +93,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
         if (!p.comm.skip_publish) {
           for (int dst = 0; dst < p.comm.world; ++dst) {
             uint8_t* slot = reinterpret_cast<uint8_t*>(p.comm.data[dst]) + slot_off(t);
-            for (int c = tid; c < kBlockM * (D / 8); c += kFwd2Threads) reinterpret_cast<uint4*>(slot)[c] = make_uint4(0, 0, 0, 0);
+            for (int c = tid; c < kBlockM * (D / 8); c += kFwd5Threads) reinterpret_cast<uint4*>(slot)[c] = make_uint4(0, 0, 0, 0);
             if (tid < kBlockM) reinterpret_cast<float*>(slot + kBlockM * D * 2)[tid] = neg_inf_f();
           }
           __syncthreads();
@@ -110,7 +115,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
   if (tid == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
   }
   if (warp == 8 && lane == 0) { tma_prefetch_desc(&qmap); tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); tma_prefetch_desc(&omap); }
@@ -120,6 +125,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
+  if (warp >= 8) {
+  // warpgroup 2 (TMA, MMA, two idle warps): one setmaxnreg site for the whole warpgroup
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
   if (warp == 8) {
     // =============================== TMA producer ===============================================
     if (lane == 0) {
@@ -133,113 +141,132 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
         const int st = j % NS;
         const uint32_t ph = (j / NS) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], SM::kTileBytes);
+        mbar_arrive_expect_tx(&k_full[st], SM::kKVBytes);
 #pragma unroll
         for (int a = 0; a < SM::kAtoms; ++a)
-          tma_load_4d(k_s + st * SM::kTileBytes + a * SM::kAtomBytes, &kmap, &k_full[st], a * 64, j * kBlockN, hkv, b);
+          tma_load_4d(k_s + st * SM::kKVBytes + a * SM::kKVAtomBytes, &kmap, &k_full[st], a * 64, j * kBN, hkv, b);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], SM::kTileBytes);
+        mbar_arrive_expect_tx(&v_full[st], SM::kKVBytes);
 #pragma unroll
         for (int a = 0; a < SM::kAtoms; ++a)
-          tma_load_4d(v_s + st * SM::kTileBytes + a * SM::kAtomBytes, &vmap, &v_full[st], a * 64, j * kBlockN, hkv, b);
+          tma_load_4d(v_s + st * SM::kKVBytes + a * SM::kKVAtomBytes, &vmap, &v_full[st], a * 64, j * kBN, hkv, b);
       }
     }
   } else if (warp == 9) {
     // =============================== MMA issuer =================================================
-    if (lane == 0) {
+    {
+      // whole warp convergent (operands in uniform registers), one elected lane issues
+      const bool leader = elect_one();
       constexpr uint32_t fmt = BF16 ? 1u : 0u;
-      constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kBlockM, kBlockN, 0, 0);
+      constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kBlockM, kBN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc(fmt, fmt, kBlockM, D, 0, 1);
-      auto issue_qk = [&](int t, int j) {
-        const uint32_t q_addr = smem_u32(q_s + t * SM::kTileBytes);
-        const uint32_t k_addr = smem_u32(k_s + (j % NS) * SM::kTileBytes);
-        const uint32_t d_tmem = tmem + t * 128;
+      const uint64_t q_desc0 = umma_smem_desc_sw128(smem_u32(q_s), 0, 1024);
+      auto issue_qk = [&](int t, int j) {   // S_t[j & 1] = Q_t K_j^T
+        const uint64_t q_desc = q_desc0 + ((t * SM::kTileBytes) >> 4);
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(k_s + (j % NS) * SM::kKVBytes), 0, 1024);
+        const uint32_t d_tmem = tmem + t * 128 + (j & 1) * kBN;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk / 4) * SM::kAtomBytes + (kk % 4) * 32;
-          umma_ss_f16(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
-                      idesc_qk, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk)
+            umma_ss_f16(d_tmem, q_desc + (((kk / 4) * SM::kAtomBytes + (kk % 4) * 32) >> 4),
+                        k_desc + (((kk / 4) * SM::kKVAtomBytes + (kk % 4) * 32) >> 4), idesc_qk, kk > 0 ? 1u : 0u);
+          umma_commit(&s_full[t * 2 + (j & 1)]);
         }
-        umma_commit(&s_full[t]);
+        __syncwarp();
       };
-      auto issue_pv = [&](int t, int j) {
-        const uint32_t v_addr = smem_u32(v_s + (j % NS) * SM::kTileBytes);
-        const uint32_t p_tmem = tmem + t * 128;
+      auto issue_pv = [&](int t, int j) {   // O_t += P_t[j & 1] V_j
+        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(v_s + (j % NS) * SM::kKVBytes), SM::kKVAtomBytes, 1024);
+        const uint32_t p_tmem = tmem + t * 128 + (j & 1) * kBN;
         const uint32_t o_tmem = tmem + 256 + t * 128;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < kBlockN / 16; ++kk)
-          umma_ts_f16(o_tmem, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * 2048, kBlockN * 128, 1024), idesc_pv,
-                      (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&pv_done[t]);
+          for (int kk = 0; kk < kBN / 16; ++kk)
+            umma_ts_f16(o_tmem, p_tmem + kk * 8, v_desc + ((kk * 2048) >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&pv_done[t * 2 + (j & 1)]);
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (leader) umma_commit(bar);
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      if (has_b) issue_qk(1, 0);
-      umma_commit(&k_empty[0]);
+      for (int j = 0; j < min(2, n_tiles); ++j) {
+        mbar_wait(&k_full[j % NS], 0);
+        tc_fence_after();
+        issue_qk(0, j);
+        if (has_b) issue_qk(1, j);
+        commit(&k_empty[j % NS]);
+      }
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % NS;
         const uint32_t ph = (j / NS) & 1;
-        mbar_wait(&p_full[0], j & 1);
+        const uint32_t pph = (j >> 1) & 1;
+        const bool more = j + 2 < n_tiles;
+        mbar_wait(&p_full[0 + (j & 1)], pph);
         mbar_wait(&v_full[st], ph);
         tc_fence_after();
         issue_pv(0, j);
-        if (j + 1 < n_tiles) {
-          mbar_wait(&k_full[(j + 1) % NS], ((j + 1) / NS) & 1);
+        if (more) {
+          mbar_wait(&k_full[(j + 2) % NS], ((j + 2) / NS) & 1);
           tc_fence_after();
-          issue_qk(0, j + 1);
+          issue_qk(0, j + 2);
         }
         if (has_b) {
-          mbar_wait(&p_full[1], j & 1);
+          mbar_wait(&p_full[2 + (j & 1)], pph);
           tc_fence_after();
           issue_pv(1, j);
         }
-        umma_commit(&v_empty[st]);
-        if (j + 1 < n_tiles) {
-          if (has_b) issue_qk(1, j + 1);
-          umma_commit(&k_empty[(j + 1) % NS]);
+        commit(&v_empty[st]);
+        if (more) {
+          if (has_b) issue_qk(1, j + 2);
+          commit(&k_empty[(j + 2) % NS]);
         }
       }
     }
     __syncwarp();
-  } else if (warp < 8) {
+  }
+  } else {
     // =============================== softmax warpgroups =========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
     const int t = warp >> 2;  // 0 = tile A, 1 = tile B
     if (t == 0 || has_b) {
       const int row = tid & (kWG - 1);
       const uint32_t lane_addr = uint32_t((warp & 3) * 32) << 16;
       const int m0t = m0 + t * kBlockM;
       const long long q_pos = p.q_pos0 + m0t + row;
-      const uint32_t s_tmem = tmem + t * 128 + lane_addr;
+      const uint32_t s_tmem0 = tmem + t * 128 + lane_addr;
       const uint32_t o_tmem = tmem + 256 + t * 128 + lane_addr;
       uint8_t* stage = q_s + t * SM::kTileBytes;
       float m_used = neg_inf_f();
       float l_sum = 0.f;
       for (int j = 0; j < n_tiles; ++j) {
-        const int n0 = j * kBlockN;
-        mbar_wait(&s_full[t], j & 1);
+        const int n0 = j * kBN;
+        const uint32_t s_tmem = s_tmem0 + (j & 1) * kBN;
+        mbar_wait(&s_full[t * 2 + (j & 1)], (j >> 1) & 1);
         tc_fence_after();
-        int limc = 127;
-        if ((n0 + kBlockN > p.S) || (p.causal && (p.kv_pos0 + n0 + kBlockN - 1 > p.q_pos0 + m0t))) {
+        int limc = kBN - 1;
+        if ((n0 + kBN > p.S) || (p.causal && (p.kv_pos0 + n0 + kBN - 1 > p.q_pos0 + m0t))) {
           long long lim = (long long)p.S - n0 - 1;
           if (p.causal) lim = min(lim, q_pos - p.kv_pos0 - n0);
-          limc = (int)max(-1LL, min(lim, 127LL));
+          limc = (int)max(-1LL, min(lim, (long long)(kBN - 1)));
         }
-        // ---- pass 1: row max
+        uint32_t sr[kBN];
+        tmem_ld_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+        tmem_ld_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+        tmem_ld_wait();
+        if (limc < kBN - 1) {  // diagonal steps and the ragged last step only
+#pragma unroll
+          for (int c = 0; c < kBN; ++c)
+            if (c > limc) sr[c] = 0xff800000u;
+        }
         float mx8[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = neg_inf_f();
+        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t sr[32];
-          tmem_ld_32x32b_x32(s_tmem + c0, sr);
-          tmem_ld_wait();
+        for (int c = 8; c < kBN; c += 8) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float v = (c0 + i <= limc) ? __uint_as_float(sr[i]) : neg_inf_f();
-            mx8[i & 7] = fmaxf(mx8[i & 7], v);
-          }
+          for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(mx8[i], __uint_as_float(sr[c + i]));
         }
         const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
         const float m_new = fmaxf(m_used, mx * p.scale_log2);
@@ -248,7 +275,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
           const float alpha = refresh ? fast_exp2(m_used - m_new) : 1.f;
           if (refresh) { l_sum *= alpha; m_used = m_new; }
           if (j > 0) {
-            mbar_wait(&pv_done[t], (j - 1) & 1);
+            mbar_wait(&pv_done[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
             tc_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < D; c0 += 32) {
@@ -262,33 +289,34 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
           }
         }
         const float neg_m = (m_used == neg_inf_f()) ? 0.f : -m_used;
-        // ---- pass 2: P = exp2(S * c - m), row sum, pack, store over S
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
+        uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
+        uint32_t pk[kBN / 2];
 #pragma unroll
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t sr[32];
-          tmem_ld_32x32b_x32(s_tmem + c0, sr);
-          tmem_ld_wait();
-          uint32_t pk[16];
+        for (int c = 0; c < kBN; c += 8) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = fast_exp2(fmaf(__uint_as_float(sr[i]), p.scale_log2, neg_m));
-            float p1 = fast_exp2(fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, neg_m));
-            p0 = (c0 + i <= limc) ? p0 : 0.f;
-            p1 = (c0 + i + 1 <= limc) ? p1 : 0.f;
-            ls[(i >> 1) & 3] += p0 + p1;
-            pk[i >> 1] = pack2<BF16>(p0, p1);
+          for (int i = 0; i < 8; i += 2) {
+            float x0, x1;
+            unpack_f32x2(fma2_f32x2(pack_f32x2(__uint_as_float(sr[c + i]), __uint_as_float(sr[c + i + 1])), sc2, nm2), x0, x1);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+            ls2[i >> 1] = add2_f32x2(ls2[i >> 1], pack_f32x2(p0, p1));
+            pk[(c + i) >> 1] = pack2<BF16>(p0, p1);
           }
-          tmem_st_32x32b_x16(s_tmem + (c0 >> 1), pk);
         }
-        l_sum += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        tmem_st_32x32b_x32(s_tmem, pk);
+        {
+          float a0, a1, b0, b1, c0, c1, d0, d1;
+          unpack_f32x2(ls2[0], a0, a1); unpack_f32x2(ls2[1], b0, b1); unpack_f32x2(ls2[2], c0, c1); unpack_f32x2(ls2[3], d0, d1);
+          l_sum += ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
+        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) mbar_arrive(&p_full[t * 2 + (j & 1)]);
       }
       // ------------------------------- epilogue --------------------------------------------------
-      mbar_wait(&pv_done[t], (n_tiles - 1) & 1);
+      if (n_tiles > 1) mbar_wait(&pv_done[t * 2 + ((n_tiles - 2) & 1)], ((n_tiles - 2) >> 1) & 1);
+      mbar_wait(&pv_done[t * 2 + ((n_tiles - 1) & 1)], ((n_tiles - 1) >> 1) & 1);
       tc_fence_after();
       const float inv_l = l_sum > 0.f ? 1.f / l_sum : 0.f;
 #pragma unroll
@@ -349,12 +377,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
 }
 
 template <int D, bool BF16, bool kComm>
-void launch_fwd2(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+void launch_fwd5(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                  const CommCtxHost& comm, cudaStream_t stream) {
-  using SM = Fwd2Smem<D>;
+  using SM = Fwd5Smem<D>;
   CUtensorMap qmap = make_tmap_bhsd(q, 2, s.B, s.Hq, s.Sq, D, s.q_sb, s.q_sh, s.q_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, D, s.k_sb, s.k_sh, s.k_ss, 64, kBlockN, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap vmap = make_tmap_bhsd(v, 2, s.B, s.Hkv, s.S, D, s.v_sb, s.v_sh, s.v_ss, 64, kBlockN, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, D, s.k_sb, s.k_sh, s.k_ss, 64, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap vmap = make_tmap_bhsd(v, 2, s.B, s.Hkv, s.S, D, s.v_sb, s.v_sh, s.v_ss, 64, kBN, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap omap = make_tmap_bhsd(out, 2, s.B, s.Hq, s.Sq, D, s.o_sb, s.o_sh, s.o_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
   FwdParams p;
   p.lse = lse; p.out = out; p.o_sb = s.o_sb; p.o_sh = s.o_sh; p.o_ss = s.o_ss;
@@ -371,36 +399,36 @@ void launch_fwd2(const AttnShape& s, const void* q, const void* k, const void* v
   if (kComm) {
     const size_t slot = (size_t)kBlockM * D * 2 + kBlockM * 4;
     if ((size_t)2 * comm.world * p.n_items * slot > comm.data_bytes || (size_t)2 * comm.world * p.n_items * 4 > comm.flag_bytes)
-      throw std::runtime_error("attn_fwd2(fused): symmetric buffer too small");
+      throw std::runtime_error("attn_fwd5(fused): symmetric buffer too small");
   }
-  auto kern = attn_fwd2_kernel<D, BF16, kComm>;
+  auto kern = attn_fwd5_kernel<D, BF16, kComm>;
   static bool configured = false;
   if (!configured) {
     TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::kTotal));
     configured = true;
   }
   const int grid = n_compute + (kComm ? p.n_items : 0);
-  kern<<<grid, kFwd2Threads, SM::kTotal, stream>>>(qmap, kmap, vmap, omap, p, num_pairs, n_compute);
+  kern<<<grid, kFwd5Threads, SM::kTotal, stream>>>(qmap, kmap, vmap, omap, p, num_pairs, n_compute);
   TA_CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace
 
-void attn_fwd2_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+void attn_fwd5_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                       const CommCtxHost& comm, cudaStream_t stream) {
-  if (s.D != 64 && s.D != 128) throw std::runtime_error("attn_fwd2: head_dim must be 64 or 128");
-  if (s.Hq % s.Hkv != 0) throw std::runtime_error("attn_fwd2: Hq must be a multiple of Hkv");
-  if (s.S <= 0 || s.Sq <= 0) throw std::runtime_error("attn_fwd2: empty problem");
+  if (s.D != 64 && s.D != 128) throw std::runtime_error("attn_fwd5: head_dim must be 64 or 128");
+  if (s.Hq % s.Hkv != 0) throw std::runtime_error("attn_fwd5: Hq must be a multiple of Hkv");
+  if (s.S <= 0 || s.Sq <= 0) throw std::runtime_error("attn_fwd5: empty problem");
   const bool fused = comm.world > 1;
-#define TA_FWD2(DD, BB)                                                               \
-  if (fused) launch_fwd2<DD, BB, true>(s, q, k, v, out, lse, comm, stream);           \
-  else launch_fwd2<DD, BB, false>(s, q, k, v, out, lse, comm, stream);
+#define TA_FWD5(DD, BB)                                                               \
+  if (fused) launch_fwd5<DD, BB, true>(s, q, k, v, out, lse, comm, stream);           \
+  else launch_fwd5<DD, BB, false>(s, q, k, v, out, lse, comm, stream);
   if (s.D == 128) {
-    if (s.is_bf16) { TA_FWD2(128, true) } else { TA_FWD2(128, false) }
+    if (s.is_bf16) { TA_FWD5(128, true) } else { TA_FWD5(128, false) }
   } else {
-    if (s.is_bf16) { TA_FWD2(64, true) } else { TA_FWD2(64, false) }
+    if (s.is_bf16) { TA_FWD5(64, true) } else { TA_FWD5(64, false) }
   }
-#undef TA_FWD2
+#undef TA_FWD5
 }
 
 }  // namespace ta

@@ -25,6 +25,7 @@ struct FwdParams {
   int num_m_tiles;
   int n_items;   // B * Hq * num_m_tiles
   int lag;       // merge CTA of item i is dispatched about `lag` compute CTAs after item i
+  int q_in_tmem; // attn_fwd_kernel: keep the query tile in TMEM (QK^T as a TS MMA: half the smem operand traffic)
   CommCtx comm;  // world == 1: unused
 };
 

@@ -41,7 +41,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   uint64_t* s_full = v_empty + NS;    // 2
   uint64_t* p_full = s_full + 2;      // 2
   uint64_t* pv_done = p_full + 2;     // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* qt_ready = pv_done + 2;   // 1 (count 4): the query tile has been copied to TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qt_ready + 1);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -108,6 +109,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
   if (tid == 0) {
     mbar_init(q_full, 1);
+    mbar_init(qt_ready, 4);
     for (int i = 0; i < NS; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
@@ -126,6 +128,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_o = tmem + 256;
+  const uint32_t tmem_q = tmem + 384;   // q_in_tmem: Q as the TMEM A operand, D/2 columns
 
   if (warp == 4) {
     // =============================== TMA producer ===============================================
@@ -150,27 +153,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     }
   } else if (warp == 5) {
     // =============================== MMA issuer =================================================
-    if (lane == 0) {
+    // The whole warp runs this loop convergently so that every descriptor / address stays in uniform registers
+    // (issuing from inside `if (lane == 0)` makes ptxas wrap each tcgen05.mma in an R2UR waterfall loop: ~17
+    // instructions per MMA, enough to make the single issuing thread the bottleneck); one elected lane issues.
+    {
+      const bool leader = elect_one();
       constexpr uint32_t fmt = BF16 ? 1u : 0u;
       constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kBlockM, kBlockN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc(fmt, fmt, kBlockM, D, 0, 1);
       const uint32_t q_addr = smem_u32(q_s);
+      const uint64_t q_desc0 = umma_smem_desc_sw128(q_addr, 0, 1024);
       auto issue_qk = [&](int j) {
         const int st = j % NS;
         mbar_wait(&k_full[st], (j / NS) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(k_s + st * SM::kKVBytes);
+        const uint64_t k_desc0 = umma_smem_desc_sw128(smem_u32(k_s + st * SM::kKVBytes), 0, 1024);
         const uint32_t d_tmem = tmem + (j & 1) * 128;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk / 4) * SM::kAtomBytes + (kk % 4) * 32;
-          umma_ss_f16(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
-                      idesc_qk, kk > 0 ? 1u : 0u);
+          if (p.q_in_tmem) {
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk)
+              umma_ts_f16(d_tmem, tmem_q + kk * 8, k_desc0 + (((kk / 4) * SM::kAtomBytes + (kk % 4) * 32) >> 4), idesc_qk, kk > 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t off = ((kk / 4) * SM::kAtomBytes + (kk % 4) * 32) >> 4;   // descriptor address field: bytes / 16
+              umma_ss_f16(d_tmem, q_desc0 + off, k_desc0 + off, idesc_qk, kk > 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&k_empty[st]);
+          umma_commit(&s_full[j & 1]);
         }
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[j & 1]);
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
+      if (p.q_in_tmem) { mbar_wait(qt_ready, 0); tc_fence_after(); }
       issue_qk(0);
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) issue_qk(j + 1);
@@ -178,15 +196,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         mbar_wait(&v_full[st], (j / NS) & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(v_s + st * SM::kKVBytes);
+        const uint64_t v_desc0 = umma_smem_desc_sw128(smem_u32(v_s + st * SM::kKVBytes), kBlockN * 128, 1024);
         const uint32_t p_tmem = tmem + (j & 1) * 128;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < kBlockN / 16; ++kk) {
-          umma_ts_f16(tmem_o, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * 2048, kBlockN * 128, 1024), idesc_pv,
-                      (j > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < kBlockN / 16; ++kk)
+            umma_ts_f16(tmem_o, p_tmem + kk * 8, v_desc0 + ((kk * 2048) >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&v_empty[st]);
+          umma_commit(&pv_done[j & 1]);
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(&pv_done[j & 1]);
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -197,6 +216,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     const long long q_pos = p.q_pos0 + m0 + row;
     float m_used = neg_inf_f();  // running (stale) max, scaled log2 domain
     float l_sum = 0.f;
+    if (p.q_in_tmem) {
+      // one-time: this thread's query row, un-swizzled from the TMA tile, becomes lane `row` of the TMEM A operand
+      mbar_wait(q_full, 0);
+#pragma unroll
+      for (int a = 0; a < SM::kAtoms; ++a) {
+        uint32_t w[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 u = *reinterpret_cast<const uint4*>(q_s + a * SM::kAtomBytes + row * 128 + ((c ^ (row & 7)) << 4));
+          w[c * 4 + 0] = u.x; w[c * 4 + 1] = u.y; w[c * 4 + 2] = u.z; w[c * 4 + 3] = u.w;
+        }
+        tmem_st_32x32b_x32(tmem_q + lane_addr + a * 32, w);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qt_ready);
+    }
     for (int j = 0; j < n_tiles; ++j) {
       const int n0 = j * kBlockN;
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
@@ -346,7 +383,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
 template <int D, bool BF16, bool kComm>
 void launch_fwd(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                const CommCtxHost& comm, cudaStream_t stream) {
+                const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem) {
   using SM = FwdSmem<D>;
   CUtensorMap qmap = make_tmap_bhsd(q, 2, s.B, s.Hq, s.Sq, D, s.q_sb, s.q_sh, s.q_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, D, s.k_sb, s.k_sh, s.k_ss, 64, kBlockN, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -360,6 +397,7 @@ void launch_fwd(const AttnShape& s, const void* q, const void* k, const void* v,
   p.num_m_tiles = (s.Sq + kBlockM - 1) / kBlockM;
   p.n_items = p.num_m_tiles * s.Hq * s.B;
   p.lag = std::min(p.n_items, 2 * num_sms());
+  p.q_in_tmem = q_in_tmem;
   p.comm = to_device_ctx(comm);
   if (kComm) {
     const size_t slot = (size_t)kBlockM * D * 2 + kBlockM * 4;
@@ -388,14 +426,14 @@ size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes) {
 }
 
 void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                     const CommCtxHost& comm, cudaStream_t stream) {
+                     const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem) {
   if (s.D != 64 && s.D != 128) throw std::runtime_error("attn_fwd: head_dim must be 64 or 128");
   if (s.Hq % s.Hkv != 0) throw std::runtime_error("attn_fwd: Hq must be a multiple of Hkv");
   if (s.S <= 0 || s.Sq <= 0) throw std::runtime_error("attn_fwd: empty problem");
   const bool fused = comm.world > 1;
 #define TA_FWD(DD, BB)                                                               \
-  if (fused) launch_fwd<DD, BB, true>(s, q, k, v, out, lse, comm, stream);           \
-  else launch_fwd<DD, BB, false>(s, q, k, v, out, lse, comm, stream);
+  if (fused) launch_fwd<DD, BB, true>(s, q, k, v, out, lse, comm, stream, q_in_tmem);           \
+  else launch_fwd<DD, BB, false>(s, q, k, v, out, lse, comm, stream, q_in_tmem);
   if (s.D == 128) {
     if (s.is_bf16) { TA_FWD(128, true) } else { TA_FWD(128, false) }
   } else {

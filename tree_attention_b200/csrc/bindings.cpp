@@ -148,7 +148,10 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at:
   // variant 0 = auto = 1: the M=128 kernel with double-buffered S.  The M=256 ping-pong kernel (variant 2) is kept
   // selectable; it measured slower on B200 (single-buffered S per tile exposes softmax + 2 GEMMs per step).
   const bool use2 = variant == 2;
-  if (variant == 4)
+  if (variant == 5)
+    ta::attn_fwd5_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
+                         at::cuda::getCurrentCUDAStream());
+  else if (variant == 4)
     ta::attn_fwd4_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
                          at::cuda::getCurrentCUDAStream());
   else if (variant == 3)
@@ -159,7 +162,7 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at:
                          at::cuda::getCurrentCUDAStream());
   else
     ta::attn_fwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
-                        at::cuda::getCurrentCUDAStream());
+                        at::cuda::getCurrentCUDAStream(), variant == 6 ? 1 : 0);
 }
 
 py::tuple decode_tc_plan(int B, int Hq, int Hkv, int Sq, int S, int D) {

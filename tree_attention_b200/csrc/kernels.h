@@ -84,10 +84,13 @@ void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const
 // comm.world > 1: fused mode -- compute CTAs push their partial tiles to every peer, merge CTAs in the same
 // launch produce the final (replicated) output; no NCCL.
 void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                     const CommCtxHost& comm, cudaStream_t stream);
+                     const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem = 0);
 size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
 // M = 128 with two softmax warpgroups splitting the score columns (two resident softmax warps per SM sub-partition)
 void attn_fwd3_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                      const CommCtxHost& comm, cudaStream_t stream);
+// M = 256 (two query tiles), BLOCK_N = 64, scores double-buffered per tile
+void attn_fwd5_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                       const CommCtxHost& comm, cudaStream_t stream);
 // two ping-ponged query tiles per CTA (M = 256), single-pass register softmax, setmaxnreg register split
 void attn_fwd4_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
