@@ -169,26 +169,32 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     }
   } else if (warp == 5) {
     // =============================== MMA issuer =================================================
-    if (lane == 0) {
+    {
+      // whole warp convergent (descriptors in uniform registers, no per-MMA R2UR waterfall); one elected lane issues
+      const bool leader = elect_one();
       constexpr uint32_t fmt = KV8 ? 0u : (BF16 ? 1u : 0u);
       constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kSwKV, kSwN, 0, 0);   // A = K (K-major), B = Q (K-major)
       constexpr uint32_t idesc_pv = umma_idesc(fmt, fmt, D, kSwN, 1, 0);       // A = V^T (MN-major), B = P^T (K-major)
-      const uint32_t q_addr = smem_u32(q_s);
+      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(q_s), 0, 1024);
+      const uint64_t pt_desc0 = umma_smem_desc_sw128(smem_u32(p_s), 0, 1024);
       auto issue_qk = [&](int i) {
         const int st = i % NS;
         mbar_wait(&k_full[st], (i / NS) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(k_s + st * SM::kTileBytes);
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(k_s + st * SM::kTileBytes), 0, 1024);
         const uint32_t d_tmem = tmem + (i & 1) * 32;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / KSTEP; ++kk) {
-          const uint64_t ad = umma_smem_desc_sw128(k_addr + (kk / 4) * SM::kAtomBytes + (kk % 4) * 32, 0, 1024);
-          const uint64_t bd = umma_smem_desc_sw128(q_addr + (kk / 4) * SM::kQAtomBytes + (kk % 4) * 32, 0, 1024);
-          if constexpr (KV8) umma_ss_f8(d_tmem, ad, bd, idesc_qk, kk > 0 ? 1u : 0u);
-          else umma_ss_f16(d_tmem, ad, bd, idesc_qk, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / KSTEP; ++kk) {
+            const uint64_t ad = k_desc + (((kk / 4) * SM::kAtomBytes + (kk % 4) * 32) >> 4);
+            const uint64_t bd = q_desc + (((kk / 4) * SM::kQAtomBytes + (kk % 4) * 32) >> 4);
+            if constexpr (KV8) umma_ss_f8(d_tmem, ad, bd, idesc_qk, kk > 0 ? 1u : 0u);
+            else umma_ss_f16(d_tmem, ad, bd, idesc_qk, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&k_empty[st]);
+          umma_commit(&s_full[i & 1]);
         }
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[i & 1]);
+        __syncwarp();
       };
       int it = 0, seg = 0;
       for (int t = t_lo; t < t_hi;) {
@@ -205,18 +211,21 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
             mbar_wait(&p_full[i & 1], (i >> 1) & 1);
             mbar_wait(&v_full[st], (i / NS) & 1);
             tc_fence_after();
-            const uint32_t v_addr = smem_u32(v_s + st * SM::kTileBytes);
-            const uint32_t pt_addr = smem_u32(p_s + (i & 1) * SM::kPBytes);
+            // A: KSTEP keys x 128 d of V^T: rows of the [key][d] tile, MN-major (LBO = next 64-wide d atom)
+            const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(v_s + st * SM::kTileBytes), SM::kAtomBytes, 1024);
+            const uint64_t pt_desc = pt_desc0 + (((i & 1) * SM::kPBytes) >> 4);
+            if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < kSwKV / KSTEP; ++kk) {
-              // A: KSTEP keys x 128 d of V^T: rows of the [key][d] tile, MN-major (LBO = next 64-wide d atom)
-              const uint64_t ad = umma_smem_desc_sw128(v_addr + kk * (KSTEP * 128), SM::kAtomBytes, 1024);
-              const uint64_t bd = umma_smem_desc_sw128(pt_addr + (kk / 4) * SM::kQAtomBytes + (kk % 4) * 32, 0, 1024);
-              if constexpr (KV8) umma_ss_f8(tmem_o, ad, bd, idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
-              else umma_ss_f16(tmem_o, ad, bd, idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
+              for (int kk = 0; kk < kSwKV / KSTEP; ++kk) {
+                const uint64_t ad = v_desc + ((kk * (KSTEP * 128)) >> 4);
+                const uint64_t bd = pt_desc + (((kk / 4) * SM::kQAtomBytes + (kk % 4) * 32) >> 4);
+                if constexpr (KV8) umma_ss_f8(tmem_o, ad, bd, idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
+                else umma_ss_f16(tmem_o, ad, bd, idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
+              }
+              umma_commit(&v_empty[st]);
+              umma_commit(&pv_done[i & 1]);
             }
-            umma_commit(&v_empty[st]);
-            umma_commit(&pv_done[i & 1]);
+            __syncwarp();
           }
           it += n;
         }

@@ -167,30 +167,31 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
     }
   } else if (warp == 5) {
     // =============================== MMA issuer =================================================
-    if (lane == 0) {
+    {
+      // whole warp convergent (descriptors in uniform registers, no per-MMA R2UR waterfall); one elected lane issues
+      const bool leader = elect_one();
       constexpr uint32_t fmt = KV8 ? 0u : (BF16 ? 1u : 0u);  // kind::f8f6f4: 0 = e4m3 ; kind::f16: 0 = f16, 1 = bf16
       constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kTM, kTN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc(fmt, fmt, kTM, D, 0, 1);
       constexpr int KSTEP = 32 / SM::kElem;     // elements per MMA along K (32 bytes)
-      const uint32_t q_addr = smem_u32(q_s);
+      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(q_s), 0, 1024);
       auto issue_qk = [&](int i) {
         const int st = i % NS;
         mbar_wait(&k_full[st], (i / NS) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(k_s + st * SM::kTileBytes);
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(k_s + st * SM::kTileBytes), 0, 1024);
         const uint32_t d_tmem = tmem + (i & 1) * 128;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / KSTEP; ++kk) {
-          const uint32_t off = (kk / 4) * SM::kAtomBytes + (kk % 4) * 32;
-          if constexpr (KV8)
-            umma_ss_f8(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
-                       idesc_qk, kk > 0 ? 1u : 0u);
-          else
-            umma_ss_f16(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
-                        idesc_qk, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / KSTEP; ++kk) {
+            const uint32_t off = ((kk / 4) * SM::kAtomBytes + (kk % 4) * 32) >> 4;
+            if constexpr (KV8) umma_ss_f8(d_tmem, q_desc + off, k_desc + off, idesc_qk, kk > 0 ? 1u : 0u);
+            else umma_ss_f16(d_tmem, q_desc + off, k_desc + off, idesc_qk, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&k_empty[st]);
+          umma_commit(&s_full[i & 1]);
         }
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[i & 1]);
+        __syncwarp();
       };
       int it = 0, seg = 0;
       for (int t = t_lo; t < t_hi;) {
@@ -207,20 +208,19 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
             mbar_wait(&p_full[i & 1], (i >> 1) & 1);
             mbar_wait(&v_full[st], (i / NS) & 1);
             tc_fence_after();
-            const uint32_t v_addr = smem_u32(v_s + st * SM::kTileBytes);
+            const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(v_s + st * SM::kTileBytes), kTN * 128, 1024);
             const uint32_t p_tmem = tmem + (i & 1) * 128;
+            if (leader) {
 #pragma unroll
-            for (int kk = 0; kk < kTN / KSTEP; ++kk) {
-              // one MMA consumes 32 bytes of P per row (8 TMEM columns) and KSTEP rows of V (KSTEP x 128 B)
-              if constexpr (KV8)
-                umma_ts_f8(tmem_o, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * (KSTEP * 128), kTN * 128, 1024), idesc_pv,
-                           (jj > 0 || kk > 0) ? 1u : 0u);
-              else
-                umma_ts_f16(tmem_o, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * (KSTEP * 128), kTN * 128, 1024), idesc_pv,
-                            (jj > 0 || kk > 0) ? 1u : 0u);
+              for (int kk = 0; kk < kTN / KSTEP; ++kk) {
+                // one MMA consumes 32 bytes of P per row (8 TMEM columns) and KSTEP rows of V (KSTEP x 128 B)
+                if constexpr (KV8) umma_ts_f8(tmem_o, p_tmem + kk * 8, v_desc + ((kk * (KSTEP * 128)) >> 4), idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
+                else umma_ts_f16(tmem_o, p_tmem + kk * 8, v_desc + ((kk * (KSTEP * 128)) >> 4), idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
+              }
+              umma_commit(&v_empty[st]);
+              umma_commit(&pv_done[i & 1]);
             }
-            umma_commit(&v_empty[st]);
-            umma_commit(&pv_done[i & 1]);
+            __syncwarp();
           }
           it += n;
         }
