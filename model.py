@@ -109,7 +109,10 @@ def _spawn_entry(rank: int, world_size: int, cfg: TreeAttentionConfig) -> None:
     main(rank, world_size)
 
 
-if __name__ == "__main__":
+def cli() -> None:
+    """`python3 model.py` / the `tree-attention` console script: one rank per visible GPU, or one CPU rank
+    (reference launcher: /root/reference/model.py:159-169)."""
+    global _CFG
     _CFG = from_args()
     add_file_sink(_CFG.log_file, _CFG.log_rotation)  # model.py:160
     if "RANK" in os.environ and "WORLD_SIZE" in os.environ:  # launched by torchrun
@@ -124,4 +127,8 @@ if __name__ == "__main__":
     else:
         logger.info("Running on CPU.")
         main(rank=0, world_size=1)
+
+
+if __name__ == "__main__":
+    cli()
     sys.exit(0)
