@@ -3,7 +3,7 @@ import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from tree_attention_b200.ops import local as L
-from tree_attention_b200.ops.quant import FP8ChannelTensor, MXFP8Tensor
+from tree_attention_b200.ops.quant import FP8ChannelTensor, MXFP8SeqTensor, MXFP8Tensor
 from tree_attention_b200.utils.timing import time_cuda
 
 ap = argparse.ArgumentParser()
@@ -20,6 +20,7 @@ for s in a.seq:
            for _ in range(max(1, min(8, (600 << 20) // (4 * hkv * s * 128))))]
     mx = [(MXFP8Tensor.from_float(k), MXFP8Tensor.from_float(v)) for k, v in kvs]
     c8 = [(FP8ChannelTensor.from_float(k), FP8ChannelTensor.from_float(v)) for k, v in kvs]
+    mxs = [(MXFP8Tensor.from_float(k), MXFP8SeqTensor.from_float(v)) for k, v in kvs]
     n = len(kvs)
     i = [0]
     def f16():
@@ -40,7 +41,11 @@ for s in a.seq:
     def f8():
         i[0] += 1
         return L.decode_attention_mxfp8(q, *mx[i[0] % n], 0.088, return_lse=False)
+    def fmxtc():
+        i[0] += 1
+        return L.decode_attention_mx_tc(q, *mxs[i[0] % n], 0.088, return_lse=False)
     t16 = time_cuda(f16, a.steps, 10)["median_ms"]
+    tmxtc = time_cuda(fmxtc, a.steps, 10)["median_ms"]
     t8 = time_cuda(f8, a.steps, 10)["median_ms"]
     ttc = time_cuda(ftc, a.steps, 10)["median_ms"]
     tc8 = time_cuda(fc8, a.steps, 10)["median_ms"]
@@ -54,4 +59,5 @@ for s in a.seq:
                       "bf16_swapAB_us": round(tsw * 1e3, 1), "bf16_swapAB_gbs": round(b16 / tsw / 1e6, 0),
                       "fp8_swapAB_us": round(tsw8 * 1e3, 1), "fp8_swapAB_gbs": round(bc8 / tsw8 / 1e6, 0),
                       "fp8_tcgen05_us": round(tc8 * 1e3, 1), "fp8_tcgen05_gbs": round(bc8 / tc8 / 1e6, 0),
+                      "mxfp8_block_scaled_tcgen05_us": round(tmxtc * 1e3, 1), "mxfp8_block_scaled_tcgen05_gbs": round(b8 / tmxtc / 1e6, 0),
                       "mxfp8_us": round(t8 * 1e3, 1), "mxfp8_gbs": round(b8 / t8 / 1e6, 0), "speedup": round(t16 / t8, 2)}), flush=True)

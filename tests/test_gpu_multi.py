@@ -71,6 +71,21 @@ def _worker_fused(rank, world):
         dist.all_gather(outs, out.contiguous())
         for o in outs:
             assert torch.equal(o, outs[0]), "fp8 fused decode: ranks disagree bitwise"
+    # block-scaled (MX) fp8 KV on the tensor cores, fused combine
+    from tree_attention_b200.ops.quant import MXFP8SeqTensor, MXFP8Tensor
+
+    for (b, hq, hkv, sq, s) in [(1, 8, 8, 1, 2048), (2, 8, 2, 2, 1111)]:
+        q, k, v = ta.make_data((b, hq, s, 128), rank, dev, dtype=torch.bfloat16, sq=sq, num_kv_heads=hkv, log=False)
+        kq, vq = MXFP8Tensor.from_float(k), MXFP8SeqTensor.from_float(v)
+        o_ref, l_ref = _oracle(q, kq.dequantize(torch.bfloat16), vq.dequantize(torch.bfloat16), world, 128 ** -0.5, False)
+        out, lse = ta.tree_attention(q, kq, vq, return_lse=True)
+        torch.cuda.synchronize()
+        assert (out.float() - o_ref).abs().max().item() < 6e-2, (hq, hkv, sq)
+        assert (lse - l_ref).abs().max().item() < 6e-2, (hq, hkv, sq)
+        outs = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(outs, out.contiguous())
+        for o in outs:
+            assert torch.equal(o, outs[0]), "mx fused decode: ranks disagree bitwise"
 
 
 @need2

@@ -103,3 +103,47 @@ def test_public_api_with_fp8_channel_cache():
     out = ta.tree_attention(q, kq, vq)
     exp, _ = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize())
     assert (out.float() - exp).abs().max().item() < 6e-2
+
+
+MX_TC_CASES = [
+    (1, 32, 32, 1, 4096, False),
+    (2, 8, 8, 1, 300, False),       # ragged last tile (scales padded to the 128-key tile)
+    (1, 32, 8, 1, 8192, False),     # GQA -> 4 packed rows
+    (1, 8, 2, 4, 2000, True),       # 16 packed rows, causal
+    (1, 4, 4, 1, 70000, False),     # many tiles per CTA, split heads
+    (1, 2, 1, 3, 129, True),        # one full + one 1-key tile
+]
+
+
+@pytest.mark.parametrize("case", MX_TC_CASES, ids=[str(i) for i in range(len(MX_TC_CASES))])
+def test_mx_block_scaled_tcgen05_decode_matches_dequantised_oracle(case):
+    """tcgen05.mma.kind::mxf8f6f4.block_scale decode: K blocks of 32 along the channels, V blocks of 32 along the keys,
+    scale factors staged in TMEM; q MX-quantised and P rounded to e4m3 inside the kernel."""
+    b, hq, hkv, sq, s, causal = case
+    g = torch.Generator(device="cuda").manual_seed(21)
+    q = torch.randn(b, hq, sq, 128, device="cuda", generator=g).bfloat16()
+    # spread the magnitudes so that block scales differ along both the channels and the sequence
+    k = (torch.randn(b, hkv, s, 128, device="cuda", generator=g) * torch.logspace(-1, 1, 128, device="cuda")).bfloat16()
+    v = (torch.randn(b, hkv, s, 128, device="cuda", generator=g) * torch.logspace(-1.5, 1.5, s, device="cuda")[:, None]).bfloat16()
+    kq, vq = quant.MXFP8Tensor.from_float(k), quant.MXFP8SeqTensor.from_float(v)
+    scale = 128 ** -0.5 * 0.3
+    out, lse = L.decode_attention_mx_tc(q, kq, vq, scale, causal, s - sq, 0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    vd = vq.dequantize()
+    o_ref, l_ref = ref.attention_partial_ref(q, kq.dequantize(), vd, scale, causal, s - sq, 0, torch.float32, block=16384)
+    # q (MX e4m3) and P (e4m3) carry 3 mantissa bits: ~3 % of the output range, independent of shape / masking
+    tol = 6e-2 * max(1.0, o_ref.abs().max().item())
+    assert (out.float() - o_ref).abs().max().item() < tol
+    assert (lse - l_ref).abs().max().item() < 6e-2
+
+
+def test_public_api_with_mx_block_scaled_cache():
+    g = torch.Generator(device="cuda").manual_seed(22)
+    q = torch.randn(1, 32, 1, 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(1, 8, 6000, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(1, 8, 6000, 128, device="cuda", generator=g).bfloat16()
+    kq, vq = quant.MXFP8Tensor.from_float(k), quant.MXFP8SeqTensor.from_float(v)
+    out = ta.tree_attention(q, kq, vq)
+    exp, _ = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize())
+    assert (out.float() - exp).abs().max().item() < 6e-2

@@ -25,8 +25,9 @@ def test_umma_probe(n, k, b_mn_major, a_from_tmem):
     assert err < 1e-2 * max(1.0, exp.abs().max().item() / 16), f"max err {err}"
 
 
+@pytest.mark.parametrize("a_mn_major", [False, True])
 @pytest.mark.parametrize("n", [16, 64, 128])
-def test_umma_block_scaled_probe(n):
+def test_umma_block_scaled_probe(n, a_mn_major):
     """tcgen05.mma.kind::mxf8f6f4.block_scale with UE8M0 scale factors staged in TMEM (32 lanes x 4 columns per 128
     rows, replicated per lane quarter, byte k of a word = K-block k) vs the de-quantised PyTorch product."""
     from tree_attention_b200.ops import quant
@@ -38,7 +39,8 @@ def test_umma_block_scaled_probe(n):
     a8, sfa = quant.quantize_mxfp8(a.contiguous())
     b8, sfb = quant.quantize_mxfp8(b.contiguous())
     c = torch.zeros(128, n, device="cuda", dtype=torch.float32)
-    C.umma_bs_probe(a8, b8, sfa.contiguous(), sfb.contiguous(), c)
+    # MN-major A: the operand is stored transposed ([K][M]) -- how a [key][channel] V tile is consumed along the keys
+    C.umma_bs_probe(a8.t().contiguous() if a_mn_major else a8, b8, sfa.contiguous(), sfb.contiguous(), c, a_mn_major)
     torch.cuda.synchronize()
     exp = quant.dequantize_mxfp8(a8, sfa) @ quant.dequantize_mxfp8(b8, sfb).t()
     err = (c - exp).abs().max().item() / exp.abs().max().item()

@@ -31,3 +31,26 @@ def test_tree_attention_accepts_mxfp8_kv_on_cpu():
     assert torch.allclose(out, exp, atol=1e-5)
     full, _ = ref.attention_partial_ref(q, k, v)
     assert (out - full).abs().max() < 0.1  # quantisation error only
+
+
+def test_seq_blocked_mx_roundtrip_and_cpu_path():
+    """MXFP8SeqTensor: 32-key blocks per channel, scale words grouped per 128-key tile (the tensor-core V layout)."""
+    import tree_attention_b200 as ta
+    from tree_attention_b200.ops import reference as ref
+
+    g = torch.Generator().manual_seed(5)
+    v = torch.randn(2, 3, 300, 128, generator=g) * torch.logspace(-2, 2, 300)[:, None]
+    vq = quant.MXFP8SeqTensor.from_float(v)
+    assert vq.data.shape == (2, 3, 300, 128) and vq.scales.shape == (2, 3, 3, 128, 4)
+    back = vq.dequantize()
+    # e4m3 has 3 mantissa bits: relative error per element <= 2^-4 of its block maximum
+    blk_max = torch.nn.functional.pad(v, (0, 0, 0, 84)).reshape(2, 3, 12, 32, 128).abs().amax(3, keepdim=True)
+    err = (torch.nn.functional.pad(back - v, (0, 0, 0, 84)).reshape(2, 3, 12, 32, 128).abs() / blk_max.clamp(min=1e-30)).max()
+    assert err <= 2 ** -4 + 1e-6
+    assert (vq.scales[:, :, 2, :, 2:] == 127).all()   # blocks past the end of the sequence are scale 1
+    q = torch.randn(2, 6, 1, 128, generator=g)
+    k = torch.randn(2, 3, 300, 128, generator=g)
+    kq = quant.MXFP8Tensor.from_float(k)
+    out = ta.tree_attention(q, kq, vq)
+    exp, _ = ref.attention_partial_ref(q, kq.dequantize(), back)
+    assert (out - exp).abs().max().item() < 1e-4

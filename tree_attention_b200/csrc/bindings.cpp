@@ -201,6 +201,46 @@ void decode_tc_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
                          reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream());
 }
 
+// block-scaled (MX) fp8 KV cache on the tensor cores (tcgen05.mma.kind::mxf8f6f4.block_scale, swap-AB decode kernel):
+//   k8 / v8 uint8 (B, Hkv, S, 128) e4m3;  k_sf uint8 (B, Hkv, S, 4): K's UE8M0 scales per 32 channels (standard MX);
+//   v_sf uint8 (B, Hkv, ceil(S / 128), 128, 4): V's UE8M0 scales per 32 KEYS, grouped per 128-key tile and channel.
+void decode_mx_tc_fwd(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& k_sf,
+                      const at::Tensor& v_sf, at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part,
+                      at::Tensor& tickets, py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
+  c10::cuda::CUDAGuard guard(q.device());
+  TORCH_CHECK(q.dim() == 4 && k8.dim() == 4 && v8.dim() == 4 && out.sizes() == q.sizes(), "expected (B, H, S, D) tensors");
+  TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
+  TORCH_CHECK(out.scalar_type() == q.scalar_type() && q.stride(3) == 1 && out.stride(3) == 1);
+  TORCH_CHECK(k8.scalar_type() == at::kByte && v8.scalar_type() == at::kByte && k8.stride(3) == 1 && v8.stride(3) == 1);
+  TORCH_CHECK(k8.sizes() == v8.sizes() && k8.size(3) == 128 && q.size(3) == 128, "mx fp8 decode needs head_dim 128");
+  const int64_t B = k8.size(0), H = k8.size(1), S = k8.size(2), T = (S + 127) / 128;
+  TORCH_CHECK(k_sf.scalar_type() == at::kByte && k_sf.is_contiguous() && k_sf.numel() == B * H * S * 4, "k_sf must be uint8 (B, Hkv, S, 4)");
+  TORCH_CHECK(v_sf.scalar_type() == at::kByte && v_sf.is_contiguous() && v_sf.numel() == B * H * T * 128 * 4,
+              "v_sf must be uint8 (B, Hkv, ceil(S/128), 128, 4)");
+  TORCH_CHECK(q.stride(2) % 8 == 0 || q.size(2) == 1, "q rows must be 16-byte aligned");
+  AttnShape s;
+  s.B = (int)q.size(0); s.Hq = (int)q.size(1); s.Sq = (int)q.size(2); s.D = 128;
+  s.Hkv = (int)k8.size(1); s.S = (int)k8.size(2);
+  s.is_bf16 = q.scalar_type() == at::kBFloat16;
+  s.softmax_scale = (float)scale; s.causal = causal; s.q_pos0 = q_pos0; s.kv_pos0 = kv_pos0;
+  s.q_sb = q.stride(0); s.q_sh = q.stride(1); s.q_ss = q.stride(2);
+  s.k_sb = k8.stride(0); s.k_sh = k8.stride(1); s.k_ss = k8.stride(2);
+  s.v_sb = v8.stride(0); s.v_sh = v8.stride(1); s.v_ss = v8.stride(2);
+  s.o_sb = out.stride(0); s.o_sh = out.stride(1); s.o_ss = out.stride(2);
+  int grid, mp, R;
+  size_t pf, cb;
+  ta::decode_tc_plan(s, ta::num_sms(), &grid, &mp, &R, &pf, &cb);
+  TORCH_CHECK(R <= 16, "mx fp8 tensor-core decode packs at most 16 query rows per KV head");
+  TORCH_CHECK((size_t)part.numel() >= pf && tickets.numel() >= s.B * s.Hkv + 2, "workspace too small");
+  float* lse_p = lse.has_value() ? lse->data_ptr<float>() : nullptr;
+  CommCtxHost c;
+  if (!comm.is_none()) c = comm.cast<Comm&>().h;
+  ta::decode_swap_launch(s, q.data_ptr(), k8.data_ptr(), v8.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
+                         reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream(),
+                         nullptr, nullptr, reinterpret_cast<const uint32_t*>(k_sf.data_ptr()),
+                         reinterpret_cast<const uint32_t*>(v_sf.data_ptr()));
+}
+
 // per-channel-scaled fp8 KV cache on the tensor cores: k8/v8 uint8 (B, Hkv, S, 128) e4m3, ksc/vsc fp32 (B, Hkv, 128)
 void decode_tc_fwd8(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& ksc,
                     const at::Tensor& vsc, at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part,
@@ -364,7 +404,8 @@ void umma_probe(const at::Tensor& a, const at::Tensor& b, at::Tensor& c, bool b_
                         at::cuda::getCurrentCUDAStream());
 }
 
-void umma_bs_probe(const at::Tensor& a8, const at::Tensor& b8, const at::Tensor& sfa, const at::Tensor& sfb, at::Tensor& c) {
+void umma_bs_probe(const at::Tensor& a8, const at::Tensor& b8, const at::Tensor& sfa, const at::Tensor& sfb, at::Tensor& c,
+                   bool a_mn_major) {
   c10::cuda::CUDAGuard guard(a8.device());
   TORCH_CHECK(a8.scalar_type() == at::kByte && b8.scalar_type() == at::kByte && sfa.scalar_type() == at::kByte &&
               sfb.scalar_type() == at::kByte && c.scalar_type() == at::kFloat);
@@ -372,7 +413,7 @@ void umma_bs_probe(const at::Tensor& a8, const at::Tensor& b8, const at::Tensor&
   TORCH_CHECK(a8.size(0) == 128 && a8.size(1) == 128 && b8.size(1) == 128 && sfa.numel() == 128 * 4 && sfb.numel() == b8.size(0) * 4);
   TORCH_CHECK(c.size(0) == 128 && c.size(1) == b8.size(0));
   ta::umma_bs_probe_launch(a8.data_ptr(), b8.data_ptr(), sfa.data_ptr(), sfb.data_ptr(), c.data_ptr<float>(), (int)b8.size(0),
-                           at::cuda::getCurrentCUDAStream());
+                           at::cuda::getCurrentCUDAStream(), a_mn_major ? 1 : 0);
 }
 
 }  // namespace
@@ -398,6 +439,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_tc_plan", &decode_tc_plan);
   m.def("decode_tc_fwd", &decode_tc_fwd);
   m.def("decode_tc_fwd8", &decode_tc_fwd8);
+  m.def("decode_mx_tc_fwd", &decode_mx_tc_fwd);
   m.def("quant_mxfp8", &quant_mxfp8);
   m.def("dequant_mxfp8", &dequant_mxfp8);
   m.def("attn_fwd", &attn_fwd);
@@ -407,6 +449,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("symm_allreduce_sizes", &symm_allreduce_sizes);
   m.def("combine", &combine);
   m.def("umma_probe", &umma_probe);
-  m.def("umma_bs_probe", &umma_bs_probe);
+  m.def("umma_bs_probe", &umma_bs_probe, py::arg("a8"), py::arg("b8"), py::arg("sfa"), py::arg("sfb"), py::arg("c"),
+        py::arg("a_mn_major") = false);
   m.def("num_sms", []() { return ta::num_sms(); });
 }

@@ -25,6 +25,12 @@ constexpr int kSwThreads = 192;
 constexpr int kSmx = 128;
 constexpr int kSwMaxPending = 32;
 constexpr float kSwRescale = 8.0f;
+// MX mode: scale-factor columns in TMEM (4 columns per 128-row operand, see umma_probe.cu)
+constexpr uint32_t kSfK = 96;    // + 4 * (tile & 1): K tile scales (A of S^T = K Q^T)
+constexpr uint32_t kSfV = 104;   // + 4 * (tile & 1): V tile scales (A of O^T += V^T P^T)
+constexpr uint32_t kSfQ = 112;   // packed query rows (B of S^T)
+constexpr uint32_t kSfP = 116;   // P^T (B of O^T): constant 2^0
+constexpr uint32_t kSfOne = 0x7f7f7f7fu;
 
 struct DecodeSwParams {
   const void* q;
@@ -34,6 +40,8 @@ struct DecodeSwParams {
   uint32_t* tickets;
   const float* kscale;  // KV8: per-channel fp32 scales (B, Hkv, D) of the e4m3 K / V shards
   const float* vscale;
+  const uint32_t* k_sf;   // MX: one word per key = the 4 UE8M0 scales of its 4 blocks of 32 channels, (B, Hkv, S)
+  const uint32_t* v_sf;   // MX: one word per (128-key tile, channel) = the scales of its 4 blocks of 32 keys, (B, Hkv, tiles, D)
   int B, Hq, Hkv, G, Sq, S, R;
   float scale_log2;
   int causal;
@@ -72,7 +80,7 @@ __device__ __forceinline__ uint16_t sw_to16(float f) {
 __device__ __forceinline__ int sw_f2ord(float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); }
 __device__ __forceinline__ float sw_ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
 
-template <bool BF16, bool KV8>
+template <bool BF16, bool KV8, bool MX>
 __global__ void __launch_bounds__(kSwThreads, 1)
 decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
                    const DecodeSwParams p) {
@@ -188,7 +196,10 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
           for (int kk = 0; kk < D / KSTEP; ++kk) {
             const uint64_t ad = k_desc + (((kk / 4) * SM::kAtomBytes + (kk % 4) * 32) >> 4);
             const uint64_t bd = q_desc + (((kk / 4) * SM::kQAtomBytes + (kk % 4) * 32) >> 4);
-            if constexpr (KV8) umma_ss_f8(d_tmem, ad, bd, idesc_qk, kk > 0 ? 1u : 0u);
+            if constexpr (MX)
+              umma_ss_mxf8_block_scale(d_tmem, ad, bd, umma_idesc_block_scaled(0, 0, kSwKV, kSwN, 0, 0, kk, kk),
+                                       tmem + kSfK + 4 * (i & 1), tmem + kSfQ, kk > 0 ? 1u : 0u);
+            else if constexpr (KV8) umma_ss_f8(d_tmem, ad, bd, idesc_qk, kk > 0 ? 1u : 0u);
             else umma_ss_f16(d_tmem, ad, bd, idesc_qk, kk > 0 ? 1u : 0u);
           }
           umma_commit(&k_empty[st]);
@@ -219,7 +230,10 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
               for (int kk = 0; kk < kSwKV / KSTEP; ++kk) {
                 const uint64_t ad = v_desc + ((kk * (KSTEP * 128)) >> 4);
                 const uint64_t bd = pt_desc + (((kk / 4) * SM::kQAtomBytes + (kk % 4) * 32) >> 4);
-                if constexpr (KV8) umma_ss_f8(tmem_o, ad, bd, idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
+                if constexpr (MX)
+                  umma_ss_mxf8_block_scale(tmem_o, ad, bd, umma_idesc_block_scaled(0, 0, D, kSwN, 1, 0, kk, kk),
+                                           tmem + kSfV + 4 * (i & 1), tmem + kSfP, (jj > 0 || kk > 0) ? 1u : 0u);
+                else if constexpr (KV8) umma_ss_f8(tmem_o, ad, bd, idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
                 else umma_ss_f16(tmem_o, ad, bd, idesc_pv, (jj > 0 || kk > 0) ? 1u : 0u);
               }
               umma_commit(&v_empty[st]);
@@ -315,6 +329,24 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
 
 
     const uint32_t xch_a = smem_u32(xch), pt_a = smem_u32(p_s);
+    [[maybe_unused]] uint32_t* sfq_s = reinterpret_cast<uint32_t*>(ch_scale);   // MX: the 16 query-row scale words
+    // MX: scale words of K tile j (one per key) / V tile j (one per channel) for the 4 rows 32 c + lane this lane
+    // stages into its lane quarter of the scale-factor columns
+    [[maybe_unused]] auto load_ksf = [&](int x, int j, uint32_t (&w)[4]) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int key = j * kSwKV + 32 * c + lane;
+        w[c] = key < p.S ? __ldg(p.k_sf + (long long)x * p.S + key) : kSfOne;
+      }
+    };
+    [[maybe_unused]] auto load_vsf = [&](int x, int j, uint32_t (&w)[4]) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) w[c] = __ldg(p.v_sf + ((long long)x * p.tph + j) * D + 32 * c + lane);
+    };
+    if constexpr (MX) {
+      tmem_st_32x32b_x4(tmem + lane_addr + kSfP, kSfOne, kSfOne, kSfOne, kSfOne);   // P <= 2^8 fits e4m3 unscaled
+      tmem_st_wait();
+    }
     int it = 0;
     for (int t = t_lo; t < t_hi;) {
       int x, j0, n, tn;
@@ -322,7 +354,7 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       const int b = x / p.Hkv, h = x - b * p.Hkv;
       // ---- stage the packed query rows (B operand, K-major): thread -> (row = tid / 8, 2 chunks of 16 bytes)
       [[maybe_unused]] float q_scale_mine = 1.f;
-      if constexpr (KV8) {
+      if constexpr (KV8 && !MX) {
         if (tid < D) { ch_scale[tid] = __ldg(p.kscale + (long long)x * D + tid); ch_scale[D + tid] = __ldg(p.vscale + (long long)x * D + tid); }
         named_bar_sync(1, kSmx);
       }
@@ -341,6 +373,32 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
               *reinterpret_cast<uint4*>(q_s + (ch >> 3) * SM::kQAtomBytes + qr * 128 + (((ch & 7) ^ (qr & 7)) << 4)) = w;
             }
           }
+        } else if constexpr (MX) {
+          // MX-quantise the row: one power-of-two scale per 32 channels (two neighbouring threads share a block)
+          float qf[16];
+          float amax = 0.f;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            float v = 0.f;
+            if (qv) { if constexpr (BF16) v = __uint_as_float(uint32_t(src[u]) << 16); else v = __half2float(__ushort_as_half(src[u])); }
+            qf[u] = v;
+            amax = fmaxf(amax, fabsf(v));
+          }
+          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+          int e = 0;
+          if (amax > 0.f) e = max(-126, min(126, (int)ceilf(log2f(amax * (1.f / 448.f)))));
+          const float inv = __int_as_float((127 - e) << 23);   // 2^-e
+          uint4 w;
+          w.x = pack_e4m3x4(qf[0] * inv, qf[1] * inv, qf[2] * inv, qf[3] * inv);
+          w.y = pack_e4m3x4(qf[4] * inv, qf[5] * inv, qf[6] * inv, qf[7] * inv);
+          w.z = pack_e4m3x4(qf[8] * inv, qf[9] * inv, qf[10] * inv, qf[11] * inv);
+          w.w = pack_e4m3x4(qf[12] * inv, qf[13] * inv, qf[14] * inv, qf[15] * inv);
+          if (qv) *reinterpret_cast<uint4*>(q_s + qr * 128 + ((part8 ^ (qr & 7)) << 4)) = w;
+          const uint32_t eb = uint32_t(e + 127);
+          const int l0 = lane & ~7;
+          const uint32_t word = __shfl_sync(0xffffffffu, eb, l0) | (__shfl_sync(0xffffffffu, eb, l0 + 2) << 8) |
+                                (__shfl_sync(0xffffffffu, eb, l0 + 4) << 16) | (__shfl_sync(0xffffffffu, eb, l0 + 6) << 24);
+          if (part8 == 0) sfq_s[qr] = word;
         } else {
           // fold K's channel scales into q, quantise the row to e4m3 with one scale per row (8 threads cooperate)
           float qf[16];
@@ -369,10 +427,25 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
           if (part8 == 0) red_s[qr] = qs;  // per-query scale, read by every softmax thread below
         }
       }
+      if constexpr (MX) {
+        // scale factors of the query rows and of the first two K tiles of this head -> TMEM, before the MMA warp starts
+        named_bar_sync(1, kSmx);
+        tmem_st_32x32b_x4(tmem + lane_addr + kSfQ, lane < kSwN ? sfq_s[lane] : kSfOne, kSfOne, kSfOne, kSfOne);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u < n) {
+            uint32_t w[4];
+            load_ksf(x, j0 + u, w);
+            tmem_st_32x32b_x4(tmem + lane_addr + kSfK + 4 * ((it + u) & 1), w[0], w[1], w[2], w[3]);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      }
       fence_proxy_async_smem();
       mbar_arrive(q_ready);
       float sc_q[kSwN];
-      if constexpr (KV8) {
+      if constexpr (KV8 && !MX) {
         named_bar_sync(1, kSmx);
 #pragma unroll
         for (int qn = 0; qn < kSwN; ++qn) sc_q[qn] = p.scale_log2 * red_s[qn];
@@ -403,6 +476,11 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         tc_fence_after();
         uint32_t sr[16];
         tmem_ld_32x32b_x16(tmem + (i & 1) * 32 + lane_addr, sr);
+        [[maybe_unused]] uint32_t ksf_n[4], vsf_c[4];
+        if constexpr (MX) {   // in flight during the softmax: K scales of tile i + 2 (same buffer as tile i), V scales of tile i
+          if (jj + 2 < n) load_ksf(x, j0 + jj + 2, ksf_n);
+          load_vsf(x, j0 + jj, vsf_c);
+        }
         tmem_ld_wait();
         float sv[kSwN];
 #pragma unroll
@@ -479,6 +557,12 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
             st_shared_u8(pt + pa[qn & 7] + qn * 128, e2);
           }
         }
+        if constexpr (MX) {
+          // QK(i) has completed (s_full) and PV(i - 2) too (pv_done above): both scale buffers of parity i & 1 are free
+          if (jj + 2 < n) tmem_st_32x32b_x4(tmem + lane_addr + kSfK + 4 * (i & 1), ksf_n[0], ksf_n[1], ksf_n[2], ksf_n[3]);
+          tmem_st_32x32b_x4(tmem + lane_addr + kSfV + 4 * (i & 1), vsf_c[0], vsf_c[1], vsf_c[2], vsf_c[3]);
+          tmem_st_wait();
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
@@ -514,7 +598,7 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
           for (int qn = 0; qn < kSwN; ++qn) orow[qn] = 0u;
         }
         float vs_d = 1.f;
-        if constexpr (KV8) vs_d = ch_scale[D + row];
+        if constexpr (KV8 && !MX) vs_d = ch_scale[D + row];
 #pragma unroll
         for (int qn = 0; qn < kSwN; ++qn)
           if (qn < R) __stcg(my_part + qn * (D + 4) + row, __uint_as_float(orow[qn]) * vs_d);   // thread = channel d
@@ -614,9 +698,9 @@ inline CommCtx sw_device_ctx(const CommCtxHost& h) {
   return c;
 }
 
-template <bool BF16, bool KV8>
+template <bool BF16, bool KV8, bool MX = false>
 void launch_sw(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeSwParams& p, int grid, cudaStream_t stream) {
-  auto kern = decode_swap_kernel<BF16, KV8>;
+  auto kern = decode_swap_kernel<BF16, KV8, MX>;
   static bool configured = false;
   if (!configured) {
     TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SwSmem<KV8>::kTotal));
@@ -630,8 +714,9 @@ void launch_sw(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeSwP
 
 void decode_swap_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
                         uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream, const float* kscale,
-                        const float* vscale) {
-  const bool kv8 = kscale != nullptr;
+                        const float* vscale, const uint32_t* k_sf, const uint32_t* v_sf) {
+  const bool mx = k_sf != nullptr;
+  const bool kv8 = kscale != nullptr || mx;
   if (s.D != 128) throw std::runtime_error("decode_swap: head_dim must be 128");
   if (s.Hq % s.Hkv != 0) throw std::runtime_error("decode_swap: Hq must be a multiple of Hkv");
   const int G = s.Hq / s.Hkv;
@@ -649,7 +734,7 @@ void decode_swap_launch(const AttnShape& s, const void* q, const void* k, const 
   CUtensorMap kmap = make_tmap_bhsd(k, eb, s.B, s.Hkv, s.S, s.D, s.k_sb, s.k_sh, s.k_ss, 128 / eb, kSwKV, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap vmap = make_tmap_bhsd(v, eb, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 128 / eb, kSwKV, CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeSwParams p;
-  p.kscale = kscale; p.vscale = vscale;
+  p.kscale = kscale; p.vscale = vscale; p.k_sf = k_sf; p.v_sf = v_sf;
   p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S; p.R = R;
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
@@ -666,7 +751,8 @@ void decode_swap_launch(const AttnShape& s, const void* q, const void* k, const 
     p.jvis = (int)std::max<long long>(0, std::min<long long>(p.tph, last < 0 ? 0 : last / kSwKV + 1));
   }
   p.comm = sw_device_ctx(comm);
-  if (kv8) { if (s.is_bf16) launch_sw<true, true>(kmap, vmap, p, grid, stream); else launch_sw<false, true>(kmap, vmap, p, grid, stream); }
+  if (mx) { if (s.is_bf16) launch_sw<true, true, true>(kmap, vmap, p, grid, stream); else launch_sw<false, true, true>(kmap, vmap, p, grid, stream); }
+  else if (kv8) { if (s.is_bf16) launch_sw<true, true>(kmap, vmap, p, grid, stream); else launch_sw<false, true>(kmap, vmap, p, grid, stream); }
   else { if (s.is_bf16) launch_sw<true, false>(kmap, vmap, p, grid, stream); else launch_sw<false, false>(kmap, vmap, p, grid, stream); }
 }
 

@@ -60,7 +60,8 @@ void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const vo
 // ---- swap-AB tensor-core decode (keys on the TMEM lanes, <= 16 packed query columns); head_dim 128 ----
 void decode_swap_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
                         uint32_t* tickets, const CommCtxHost& comm, int num_sms, cudaStream_t stream,
-                        const float* kscale = nullptr, const float* vscale = nullptr);
+                        const float* kscale = nullptr, const float* vscale = nullptr, const uint32_t* k_sf = nullptr,
+                        const uint32_t* v_sf = nullptr);
 
 // ---- stand-alone combine of W per-rank partials (o fp32 normalised, lse natural log) ----
 // local: o_part (rows, D) fp32 + lse_part (rows); result written to out (dtype of `is_bf16`/fp16/fp32)
@@ -78,7 +79,7 @@ void umma_probe_launch(const void* a, const void* b, float* c, int N, int K, int
 // block-scaled fp8 probe: C[128, N] fp32 = (A8 o SFA)(128 x 128) x (B8 o SFB)(N x 128)^T, e4m3 + UE8M0 per 32 of K,
 // through tcgen05.mma.kind::mxf8f6f4.block_scale with the scale factors staged in TMEM.
 void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const void* sfb, float* c, int N,
-                          cudaStream_t stream);
+                          cudaStream_t stream, int a_mn_major = 0);
 
 // ---- tcgen05 flash-attention forward: shard-local partial (o normalised, lse natural log) ----
 // comm.world > 1: fused mode -- compute CTAs push their partial tiles to every peer, merge CTAs in the same

@@ -107,6 +107,7 @@ struct BsProbeParams {
   const uint32_t* sfb;  // [N] words
   float* c;
   int N;
+  int a_mn_major;   // A is stored transposed ([K][M], the layout of a [key][channel] tile consumed along the keys)
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -148,8 +149,11 @@ umma_bs_probe_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
     tc_fence_after();
     if (elect_one()) {
       for (int kk = 0; kk < 4; ++kk) {  // K = 32 per instruction; scale byte kk of the column words
-        const uint32_t idesc = umma_idesc_block_scaled(0, 0, 128, N, 0, 0, kk, kk);
-        umma_ss_mxf8_block_scale(tmem, umma_smem_desc_sw128(smem_u32(a_s) + kk * 32, 0, 1024),
+        const uint32_t idesc = umma_idesc_block_scaled(0, 0, 128, N, p.a_mn_major ? 1 : 0, 0, kk, kk);
+        // K-major A: 32 bytes further along the row; MN-major A: 32 rows (K) further down the [K][M] tile
+        const uint64_t a_desc = p.a_mn_major ? umma_smem_desc_sw128(smem_u32(a_s) + kk * 32 * 128, 128 * 128, 1024)
+                                             : umma_smem_desc_sw128(smem_u32(a_s) + kk * 32, 0, 1024);
+        umma_ss_mxf8_block_scale(tmem, a_desc,
                                  umma_smem_desc_sw128(smem_u32(b_s) + kk * 32, 0, 1024), idesc, tmem + 256, tmem + 264,
                                  kk > 0 ? 1u : 0u);
       }
@@ -174,7 +178,7 @@ umma_bs_probe_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
 }  // namespace
 
 void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const void* sfb, float* c, int N,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int a_mn_major) {
   if (N % 16 != 0 || N < 16 || N > 128) throw std::runtime_error("umma_bs_probe: bad N");
   auto enc = get_encode_tiled();
   auto mk = [&](const void* base, uint64_t rows) {
@@ -190,7 +194,7 @@ void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const
     return m;
   };
   CUtensorMap amap = mk(a8, 128), bmap = mk(b8, N);
-  BsProbeParams p{reinterpret_cast<const uint32_t*>(sfa), reinterpret_cast<const uint32_t*>(sfb), c, N};
+  BsProbeParams p{reinterpret_cast<const uint32_t*>(sfa), reinterpret_cast<const uint32_t*>(sfb), c, N, a_mn_major};
   const size_t smem = 1024 + 128 * 128 + (size_t)N * 128;
   TA_CUDA_CHECK(cudaFuncSetAttribute(umma_bs_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   umma_bs_probe_kernel<<<1, 128, smem, stream>>>(amap, bmap, p);

@@ -168,6 +168,36 @@ def decode_attention_fp8(
     return out, lse
 
 
+def decode_attention_mx_tc(
+    q: torch.Tensor,
+    k,
+    v,
+    softmax_scale: float,
+    causal: bool = False,
+    q_pos0: int = 0,
+    kv_pos0: int = 0,
+    comm=None,
+    return_lse: bool = True,
+) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Block-scaled fp8 KV cache on the tensor cores: ``k`` is an ``MXFP8Tensor`` (scales per 32 channels), ``v`` an
+    ``MXFP8SeqTensor`` (scales per 32 keys); both GEMMs of the swap-AB decode kernel are
+    ``tcgen05.mma.kind::mxf8f6f4.block_scale`` with the scale factors staged in TMEM.  head_dim 128, at most 16 packed
+    query rows per KV head; with ``comm`` the kernel also performs the cross-GPU tree combine."""
+    C = _build.load()
+    q = _as_bhsd(q)
+    b, hq, sq, d = q.shape
+    hkv, s = k.data.shape[1], k.data.shape[2]
+    if q.stride(2) % 8 != 0 and sq > 1:
+        q = q.contiguous()
+    grid, max_parts, rows, part_floats, _ = C.decode_tc_plan(b, hq, hkv, sq, s, d)
+    ws = _workspace(q.device, "decode_tc", part_floats, b * hkv + 2)
+    out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
+    lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device) if return_lse else None
+    C.decode_mx_tc_fwd(q, k.data, v.data, k.scales.contiguous(), v.scales.contiguous(), out, lse, ws["part"], ws["tickets"],
+                       comm, float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0))
+    return out, lse
+
+
 def decode_comm_bytes(b: int, hq: int, hkv: int, sq: int, s: int, d: int, world: int) -> Tuple[int, int]:
     """(data_bytes, flag_bytes) the decode family needs in symmetric memory (covers both decode kernels)."""
     rows = max(4, (hq // hkv) * sq)

@@ -71,6 +71,60 @@ class MXFP8Tensor:
         return dequantize_mxfp8(self.data, self.scales).to(dtype)
 
 
+SEQ_TILE = 128
+
+
+@dataclass
+class MXFP8SeqTensor:
+    """Block-scaled fp8 with the 32-element blocks running along the SEQUENCE: ``data`` uint8 (B, H, S, D) e4m3,
+    ``scales`` uint8 (B, H, ceil(S/128), D, 4) UE8M0 -- byte k of entry (tile, d) scales keys
+    ``[128 tile + 32 k, 128 tile + 32 k + 32)`` of channel d.
+
+    This is the V-cache format of the block-scaled tensor-core decode (``tcgen05.mma.kind::mxf8f6f4.block_scale`` in
+    ``csrc/decode_swap_sm100.cu``): ``O^T += V^T P^T`` contracts over the keys, and MX scale factors apply per 32
+    elements of the contraction, so V's blocks must run along the keys (K keeps the standard layout: ``S^T = K Q^T``
+    contracts over the channels).  The four scale bytes of a (128-key tile, channel) pair form one 32-bit word, which is
+    exactly one scale-factor entry of the MMA's A operand."""
+
+    data: torch.Tensor
+    scales: torch.Tensor
+
+    @classmethod
+    def from_float(cls, x: torch.Tensor) -> "MXFP8SeqTensor":
+        b, h, s, d = x.shape
+        t = (s + SEQ_TILE - 1) // SEQ_TILE
+        xf = x.float()
+        if t * SEQ_TILE != s:
+            xf = torch.nn.functional.pad(xf, (0, 0, 0, t * SEQ_TILE - s))
+        xb = xf.reshape(b, h, t, SEQ_TILE // BLOCK, BLOCK, d)
+        amax = xb.abs().amax(dim=4)                                    # (B, H, T, 4, D)
+        e = torch.ceil(torch.log2(torch.clamp(amax, min=1e-38) / E4M3_MAX))
+        e = torch.where(amax > 0, e, torch.zeros_like(e)).clamp(-127, 127)
+        q = (xb * torch.exp2(-e)[:, :, :, :, None, :]).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+        data = q.view(torch.uint8).reshape(b, h, t * SEQ_TILE, d)[:, :, :s].contiguous()
+        scales = (e + 127).to(torch.uint8).permute(0, 1, 2, 4, 3).contiguous()   # (B, H, T, D, 4)
+        return cls(data, scales)
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    @property
+    def is_cuda(self):
+        return self.data.is_cuda
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def dequantize(self, dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        b, h, s, d = self.data.shape
+        t = self.scales.shape[2]
+        sc = torch.exp2(self.scales.float() - 127.0).permute(0, 1, 2, 4, 3)        # (B, H, T, 4, D)
+        sc = sc[:, :, :, :, None, :].expand(b, h, t, SEQ_TILE // BLOCK, BLOCK, d).reshape(b, h, t * SEQ_TILE, d)[:, :, :s]
+        return (self.data.view(torch.float8_e4m3fn).float() * sc).to(dtype)
+
+
 # ------------------------------------------------------------------------------------------------
 # per-channel-scaled fp8 (the tensor-core decode format)
 # ------------------------------------------------------------------------------------------------

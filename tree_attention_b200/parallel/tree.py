@@ -284,18 +284,20 @@ def _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset,
     kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
     q_pos0 = (world * s_local - q.shape[2]) if q_offset is None else int(q_offset)
     g = q.shape[1] // k.shape[1]
-    from ..ops.quant import FP8ChannelTensor
+    from ..ops.quant import FP8ChannelTensor, MXFP8SeqTensor
 
     per_channel = isinstance(k, FP8ChannelTensor)
+    mx_tc = isinstance(v, MXFP8SeqTensor)   # block-scaled tensor-core path: K blocks along channels, V blocks along keys
     max_rows = local_ops.DECODE_MAX_ROWS if per_channel else 16
     if (q.is_cuda and q.shape[-1] == 128 and q.shape[2] * g <= max_rows and backend in ("auto", "fused", "local")):
         comm = None
         if world > 1:
             b, hq, sq, d = q.shape
             data, flags = local_ops.decode_comm_bytes(b, hq, k.shape[1], sq, s_local, d, world)
-            fam = "decode_tc" if per_channel else "decode"
-            comm = symm.get_region(fam, data, flags, group, layout=("fp8", per_channel, b, hq, k.shape[1], sq, d)).comm
-        fn = local_ops.decode_attention_fp8 if per_channel else local_ops.decode_attention_mxfp8
+            fam = "decode_tc" if (per_channel or mx_tc) else "decode"
+            comm = symm.get_region(fam, data, flags, group, layout=("fp8", per_channel, mx_tc, b, hq, k.shape[1], sq, d)).comm
+        fn = (local_ops.decode_attention_fp8 if per_channel else
+              local_ops.decode_attention_mx_tc if mx_tc else local_ops.decode_attention_mxfp8)
         o, lse = fn(q, k, v, scale, causal, q_pos0, kv_pos0, comm=comm, return_lse=return_lse)
         return (o, lse) if return_lse else o
     dt = q.dtype if q.is_cuda else torch.float32
