@@ -413,6 +413,19 @@ def run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier):
         out["mxfp8_kv_max_abs_diff_vs_bf16"] = float((o8.float() - o16.float()).abs().max())
         out["mxfp8_kv_eager_ms_per_step"] = timeit(
             lambda i: ta.tree_attention(q, kq, vq, softmax_scale=scale, backend=args.backend), steps=200)
+        if q.shape[-1] == 128 and (q.shape[1] // kvs[0][0].shape[1]) * q.shape[2] <= 16:
+            # the same MX cache with V blocked along the keys: both GEMMs on tcgen05.mma.kind::mxf8f6f4.block_scale
+            from tree_attention_b200.ops.quant import FP8ChannelTensor, MXFP8SeqTensor
+
+            vs = MXFP8SeqTensor.from_float(kvs[0][1])
+            o8t = ta.tree_attention(q, kq, vs, softmax_scale=scale, backend=args.backend)
+            out["mxfp8_block_scaled_tcgen05_max_abs_diff_vs_bf16"] = float((o8t.float() - o16.float()).abs().max())
+            out["mxfp8_block_scaled_tcgen05_eager_ms_per_step"] = timeit(
+                lambda i: ta.tree_attention(q, kq, vs, softmax_scale=scale, backend=args.backend), steps=200)
+            kc, vc = FP8ChannelTensor.from_float(kvs[0][0]), FP8ChannelTensor.from_float(kvs[0][1])
+            out["fp8_per_channel_tcgen05_eager_ms_per_step"] = timeit(
+                lambda i: ta.tree_attention(q, kc, vc, softmax_scale=scale, backend=args.backend), steps=200)
+            del vs, kc, vc
         del kq, vq
         if world > 1:
             from tree_attention_b200.parallel import symm
