@@ -147,3 +147,35 @@ def test_public_api_with_mx_block_scaled_cache():
     out = ta.tree_attention(q, kq, vq)
     exp, _ = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize())
     assert (out.float() - exp).abs().max().item() < 6e-2
+
+
+@pytest.mark.parametrize("fmt", ["mx_tc", "channel"])
+def test_decode_session_with_quantised_cache_and_append(fmt):
+    """TreeDecodeSession over an fp8 KV cache: graph-captured step, KV append (quantised on the way in), step again."""
+    from tree_attention_b200.models.decoder import TreeDecodeSession
+
+    g = torch.Generator(device="cuda").manual_seed(31)
+    s, used = 4096, 4000
+    q = torch.randn(1, 8, 1, 128, device="cuda", generator=g).bfloat16()
+    k = torch.randn(1, 2, s, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(1, 2, s, 128, device="cuda", generator=g).bfloat16()
+    k[:, :, used:] = 0
+    v[:, :, used:] = 0
+    if fmt == "mx_tc":
+        kq, vq = quant.MXFP8Tensor.from_float(k), quant.MXFP8SeqTensor.from_float(v)
+    else:
+        kq, vq = quant.FP8ChannelTensor.from_float(k, headroom=4.0), quant.FP8ChannelTensor.from_float(v, headroom=4.0)
+    scale = 128 ** -0.5
+    sess = TreeDecodeSession([(kq, vq)], softmax_scale=scale, q_shape=(1, 8, 1, 128), dtype=torch.bfloat16)
+    out0 = sess.step_device(q, 0).clone()
+    exp0, _ = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize(), scale)
+    assert (out0.float() - exp0).abs().max().item() < 6e-2
+    k_new = torch.randn(1, 2, 2, 128, device="cuda", generator=g).bfloat16() * 2
+    v_new = torch.randn(1, 2, 2, 128, device="cuda", generator=g).bfloat16() * 2
+    sess.append_kv(0, k_new, v_new, used)
+    out1 = sess.step_device(q, 0).clone()
+    torch.cuda.synchronize()
+    exp1, _ = ref.attention_partial_ref(q, kq.dequantize(), vq.dequantize(), scale)
+    assert (out1.float() - exp1).abs().max().item() < 6e-2
+    assert (vq.dequantize()[:, :, used:used + 2] - v_new.float()).abs().max().item() < 0.3
+    assert (out1.float() - out0.float()).abs().max().item() > 1e-4   # the appended tokens are attended

@@ -54,3 +54,37 @@ def test_seq_blocked_mx_roundtrip_and_cpu_path():
     out = ta.tree_attention(q, kq, vq)
     exp, _ = ref.attention_partial_ref(q, kq.dequantize(), back)
     assert (out - exp).abs().max().item() < 1e-4
+
+
+def test_quantised_cache_append_rows():
+    """write_rows on the three fp8 cache formats == quantising the updated float cache (same blocks / scales)."""
+    g = torch.Generator().manual_seed(9)
+    base = torch.randn(1, 2, 200, 128, generator=g)
+    new = torch.randn(1, 2, 3, 128, generator=g) * 4.0
+    upd = base.clone()
+    upd[:, :, 70:73] = new
+    # K layout: per-row blocks
+    kq = quant.MXFP8Tensor.from_float(base)
+    kq.write_rows(70, new)
+    ref_k = quant.MXFP8Tensor.from_float(upd)
+    assert torch.equal(kq.data, ref_k.data) and torch.equal(kq.scales, ref_k.scales)
+    # V layout: 32-key blocks are re-quantised
+    vq = quant.MXFP8SeqTensor.from_float(base)
+    vq.write_rows(70, new)
+    ref_v = quant.MXFP8SeqTensor.from_float(upd)
+    assert (vq.dequantize() - ref_v.dequantize()).abs().max().item() <= 2 ** -3 * upd.abs().max().item()
+    rows = vq.dequantize()[:, :, 70:73]
+    assert (rows - new).abs().max().item() <= 2 ** -4 * new.abs().max().item() * 2
+    # a write that crosses a block and a tile boundary
+    vq2 = quant.MXFP8SeqTensor.from_float(base)
+    big = torch.randn(1, 2, 40, 128, generator=g)
+    vq2.write_rows(110, big)
+    upd2 = base.clone()
+    upd2[:, :, 110:150] = big
+    # (re-quantising already rounded values may pick a different but equally valid power-of-two scale)
+    assert (vq2.dequantize() - upd2).abs().max().item() <= 2 ** -3 * upd2.abs().max().item()
+    assert (vq2.dequantize()[:, :, :96] - quant.MXFP8SeqTensor.from_float(base).dequantize()[:, :, :96]).abs().max().item() == 0
+    # per-channel: saturating write with the cache's scales
+    cq = quant.FP8ChannelTensor.from_float(base, headroom=8.0)
+    cq.write_rows(70, new)
+    assert (cq.dequantize()[:, :, 70:73] - new).abs().max().item() <= 2 ** -4 * 8.0 * base.abs().max().item()

@@ -30,6 +30,7 @@ class TreeDecodeSession:
         group=None,
         q_shape: Optional[Tuple[int, int, int, int]] = None,
         pdl: bool = False,
+        dtype: Optional[torch.dtype] = None,
     ):
         """``pdl=True``: eager launches with programmatic dependent launch + K/V prefetch (the KV caches of this
         session are only written through ``append_kv``, never by the kernel that precedes a step) instead of CUDA
@@ -37,7 +38,9 @@ class TreeDecodeSession:
         self.kv = list(kv_layers)
         k0 = self.kv[0][0]
         self.device = k0.device
-        self.dtype = k0.dtype
+        # quantised caches (MXFP8Tensor / MXFP8SeqTensor / FP8ChannelTensor) carry no query dtype: pass ``dtype``
+        self.quantised = not isinstance(k0, torch.Tensor)
+        self.dtype = dtype if dtype is not None else (torch.bfloat16 if self.quantised else k0.dtype)
         self.scale = softmax_scale
         self.causal = causal
         self.backend = backend
@@ -52,7 +55,7 @@ class TreeDecodeSession:
         self.graphs: List[torch.cuda.CUDAGraph] = []
         g = self.q_shape[1] // hkv
         rows = g * self.q_shape[2]
-        self.launches_per_step = max(1, -(-rows // 4)) if local_ops.decode_eligible(self.q_static, k0) else 1
+        self.launches_per_step = 1
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         graphable = self.device.type == "cuda" and (world == 1 or backend in ("fused", "symm", "auto"))
         self._use_graph = bool(use_graph and graphable)
@@ -121,8 +124,11 @@ class TreeDecodeSession:
         global position calls this; shards are preallocated)."""
         k, v = self.kv[layer]
         self._kv_dirty = True
-        k[:, :, position : position + k_new.shape[2]].copy_(k_new, non_blocking=True)
-        v[:, :, position : position + v_new.shape[2]].copy_(v_new, non_blocking=True)
+        for cache, new in ((k, k_new), (v, v_new)):
+            if hasattr(cache, "write_rows"):      # quantised cache: quantise on the way in
+                cache.write_rows(position, new)
+            else:
+                cache[:, :, position : position + new.shape[2]].copy_(new, non_blocking=True)
 
     def run_e2e(self, q: torch.Tensor, steps: int, barrier) -> dict:
         self._prepare()

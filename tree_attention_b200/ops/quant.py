@@ -70,6 +70,14 @@ class MXFP8Tensor:
     def dequantize(self, dtype: torch.dtype = torch.float32) -> torch.Tensor:
         return dequantize_mxfp8(self.data, self.scales).to(dtype)
 
+    def write_rows(self, position: int, x: torch.Tensor) -> None:
+        """KV append: quantise the new rows ``x`` (B, H, n, D) into ``[position, position + n)`` along the sequence
+        (blocks run along the channels, so every row carries its own scales)."""
+        q, sc = quantize_mxfp8(x.contiguous())
+        n = x.shape[2]
+        self.data[:, :, position:position + n].copy_(q, non_blocking=True)
+        self.scales[:, :, position:position + n].copy_(sc, non_blocking=True)
+
 
 SEQ_TILE = 128
 
@@ -117,6 +125,39 @@ class MXFP8SeqTensor:
     def device(self):
         return self.data.device
 
+    def write_rows(self, position: int, x: torch.Tensor) -> None:
+        """KV append: rows ``[position, position + n)``.  A 32-key block shares one scale per channel, so the blocks the
+        new rows touch are de-quantised, updated and re-quantised (at most 32 + n rows of work per call)."""
+        n = x.shape[2]
+        b, h, s, d = self.data.shape
+        lo = (position // BLOCK) * BLOCK
+        hi = min(s, ((position + n + BLOCK - 1) // BLOCK) * BLOCK)
+        blk = self.dequantize_rows(lo, hi)
+        blk[:, :, position - lo:position - lo + n] = x.float()
+        pad = (-(hi - lo)) % BLOCK
+        if pad:
+            blk = torch.nn.functional.pad(blk, (0, 0, 0, pad))
+        xb = blk.reshape(b, h, -1, BLOCK, d)
+        amax = xb.abs().amax(dim=3)                                    # (B, H, nblk, D)
+        e = torch.ceil(torch.log2(torch.clamp(amax, min=1e-38) / E4M3_MAX))
+        e = torch.where(amax > 0, e, torch.zeros_like(e)).clamp(-127, 127)
+        q = (xb * torch.exp2(-e)[:, :, :, None, :]).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+        self.data[:, :, lo:hi].copy_(q.view(torch.uint8).reshape(b, h, -1, d)[:, :, :hi - lo], non_blocking=True)
+        sc = (e + 127).to(torch.uint8)
+        for bi in range(sc.shape[2]):                                   # scale byte (tile, channel, block-in-tile)
+            g = lo // BLOCK + bi
+            self.scales[:, :, g // (SEQ_TILE // BLOCK), :, g % (SEQ_TILE // BLOCK)].copy_(sc[:, :, bi], non_blocking=True)
+
+    def dequantize_rows(self, lo: int, hi: int) -> torch.Tensor:
+        """fp32 rows ``[lo, hi)`` (``lo`` a multiple of 32)."""
+        b, h, s, d = self.data.shape
+        out = self.data[:, :, lo:hi].view(torch.float8_e4m3fn).float()
+        for g in range(lo // BLOCK, (hi + BLOCK - 1) // BLOCK):
+            sc = torch.exp2(self.scales[:, :, g // (SEQ_TILE // BLOCK), :, g % (SEQ_TILE // BLOCK)].float() - 127.0)
+            r0, r1 = g * BLOCK - lo, min(hi, (g + 1) * BLOCK) - lo
+            out[:, :, r0:r1] *= sc[:, :, None, :]
+        return out
+
     def dequantize(self, dtype: torch.dtype = torch.float32) -> torch.Tensor:
         b, h, s, d = self.data.shape
         t = self.scales.shape[2]
@@ -160,3 +201,9 @@ class FP8ChannelTensor:
 
     def dequantize(self, dtype: torch.dtype = torch.float32) -> torch.Tensor:
         return (self.data.view(torch.float8_e4m3fn).float() * self.scales[:, :, None, :]).to(dtype)
+
+    def write_rows(self, position: int, x: torch.Tensor) -> None:
+        """KV append with the cache's channel scales (values beyond the scale's range saturate: build the cache with
+        ``headroom`` > 1 when later tokens may be larger)."""
+        q = (x.float() / self.scales[:, :, None, :]).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn)
+        self.data[:, :, position:position + x.shape[2]].copy_(q.view(torch.uint8), non_blocking=True)
