@@ -179,3 +179,14 @@ def test_decode_session_with_quantised_cache_and_append(fmt):
     assert (out1.float() - exp1).abs().max().item() < 6e-2
     assert (vq.dequantize()[:, :, used:used + 2] - v_new.float()).abs().max().item() < 0.3
     assert (out1.float() - out0.float()).abs().max().item() > 1e-4   # the appended tokens are attended
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("s", [128, 300, 4097])
+def test_seq_blocked_quantiser_kernel_matches_oracle(s, dtype):
+    g = torch.Generator(device="cuda").manual_seed(s)
+    x = (torch.randn(2, 3, s, 128, device="cuda", generator=g) * torch.logspace(-2, 2, s, device="cuda")[:, None]).to(dtype)
+    a = quant.MXFP8SeqTensor.from_float(x)
+    b = quant.MXFP8SeqTensor.from_float_ref(x)
+    assert a.scales.shape == b.scales.shape and torch.equal(a.scales, b.scales)
+    assert torch.equal(a.data, b.data)

@@ -329,6 +329,20 @@ py::tuple quant_mxfp8(const at::Tensor& x) {
   return py::make_tuple(q, sc);
 }
 
+// sequence-blocked MX quantiser: x (B, H, S, D) -> (uint8 e4m3 (B, H, S, D), uint8 UE8M0 (B, H, ceil(S/128), D, 4))
+py::tuple quant_mxfp8_seq(const at::Tensor& x) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.is_cuda() && x.is_contiguous() && x.dim() == 4 && x.size(3) % 32 == 0, "x must be contiguous (B, H, S, D), D % 32 == 0");
+  int dt = x.scalar_type() == at::kBFloat16 ? 0 : x.scalar_type() == at::kHalf ? 1 : 2;
+  TORCH_CHECK(dt != 2 || x.scalar_type() == at::kFloat, "x must be bf16, fp16 or fp32");
+  const int64_t B = x.size(0), H = x.size(1), S = x.size(2), D = x.size(3), T = (S + 127) / 128;
+  auto q = at::empty(x.sizes(), x.options().dtype(at::kByte));
+  auto sc = at::empty({B, H, T, D, 4}, x.options().dtype(at::kByte));
+  ta::quant_mxfp8_seq_launch(x.data_ptr(), dt, q.data_ptr<uint8_t>(), sc.data_ptr<uint8_t>(), B * H, (int)S, (int)D,
+                             at::cuda::getCurrentCUDAStream());
+  return py::make_tuple(q, sc);
+}
+
 at::Tensor dequant_mxfp8(const at::Tensor& q, const at::Tensor& sc) {
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(q.is_cuda() && q.is_contiguous() && sc.is_contiguous() && q.scalar_type() == at::kByte &&
@@ -441,6 +455,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_tc_fwd8", &decode_tc_fwd8);
   m.def("decode_mx_tc_fwd", &decode_mx_tc_fwd);
   m.def("quant_mxfp8", &quant_mxfp8);
+  m.def("quant_mxfp8_seq", &quant_mxfp8_seq);
   m.def("dequant_mxfp8", &dequant_mxfp8);
   m.def("attn_fwd", &attn_fwd);
   m.def("attn_fwd_comm_bytes", &attn_fwd_comm_bytes);

@@ -114,6 +114,8 @@ void symm_allreduce_launch(const float* x, float* y, int64_t n, const CommCtxHos
 // ---- block-scaled fp8 (MX): e4m3 + one UE8M0 scale per 32 elements of the innermost dimension ----
 void quant_mxfp8_launch(const void* x, int in_dtype /*0 bf16, 1 fp16, 2 fp32*/, uint8_t* q, uint8_t* scales,
                         int64_t nblocks, cudaStream_t stream);
+void quant_mxfp8_seq_launch(const void* x, int in_dtype, uint8_t* q, uint8_t* scales, int64_t bh, int S, int D,
+                            cudaStream_t stream);
 void dequant_mxfp8_launch(const uint8_t* q, const uint8_t* scales, float* y, int64_t nblocks, cudaStream_t stream);
 
 }  // namespace ta

@@ -47,6 +47,43 @@ __global__ void quant_mxfp8_kernel(const void* __restrict__ x, uint8_t* __restri
   qp[1] = make_uint4(out[4], out[5], out[6], out[7]);
 }
 
+// Sequence-blocked MX (the V-cache layout of the block-scaled tensor-core decode): one scale per 32 KEYS per channel;
+// the four scale bytes of a (128-key tile, channel) pair are stored as one word.  x / q: (BH, S, D), sc: (BH, T, D, 4).
+// One CTA per (bh, 32-key block), one thread per channel: loads and stores are coalesced across the channels.
+template <int IN>
+__global__ void quant_mxfp8_seq_kernel(const void* __restrict__ x, uint8_t* __restrict__ q, uint8_t* __restrict__ sc,
+                                       int S, int D, int T) {
+  const int g = blockIdx.x % (T * 4);          // 32-key block within the (padded) sequence
+  const long long bh = blockIdx.x / (T * 4);
+  const int d = threadIdx.x;
+  float v[32];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int key = g * 32 + i;
+    v[i] = key < S ? load_in<IN>(x, (bh * S + key) * D + d) : 0.f;
+    amax = fmaxf(amax, fabsf(v[i]));
+  }
+  int e = 0;
+  if (amax > 0.f && isfinite(amax)) {
+    int ex;
+    const float m = frexpf(amax / 448.f, &ex);
+    e = (m == 0.5f) ? ex - 1 : ex;  // ceil(log2(amax / 448))
+    e = max(-127, min(127, e));
+  }
+  const float inv = exp2f((float)-e);
+  sc[((bh * T + g / 4) * D + d) * 4 + (g & 3)] = (uint8_t)(e + 127);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int key = g * 32 + i;
+    if (key < S) {
+      uint16_t b2;
+      asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(b2) : "f"(0.f), "f"(v[i] * inv));
+      q[(bh * S + key) * D + d] = (uint8_t)(b2 & 0xff);
+    }
+  }
+}
+
 __global__ void dequant_mxfp8_kernel(const uint8_t* __restrict__ q, const uint8_t* __restrict__ sc, float* __restrict__ y,
                                      long long nblocks) {
   const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,6 +107,17 @@ void quant_mxfp8_launch(const void* x, int in_dtype, uint8_t* q, uint8_t* scales
   if (in_dtype == 0) quant_mxfp8_kernel<0><<<grid, threads, 0, stream>>>(x, q, scales, nblocks);
   else if (in_dtype == 1) quant_mxfp8_kernel<1><<<grid, threads, 0, stream>>>(x, q, scales, nblocks);
   else quant_mxfp8_kernel<2><<<grid, threads, 0, stream>>>(x, q, scales, nblocks);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
+
+void quant_mxfp8_seq_launch(const void* x, int in_dtype, uint8_t* q, uint8_t* scales, int64_t bh, int S, int D,
+                            cudaStream_t stream) {
+  if (D % 32 != 0 || D > 1024) throw std::runtime_error("quant_mxfp8_seq: head_dim must be a multiple of 32, <= 1024");
+  const int T = (S + 127) / 128;
+  const unsigned grid = (unsigned)(bh * T * 4);
+  if (in_dtype == 0) quant_mxfp8_seq_kernel<0><<<grid, D, 0, stream>>>(x, q, scales, S, D, T);
+  else if (in_dtype == 1) quant_mxfp8_seq_kernel<1><<<grid, D, 0, stream>>>(x, q, scales, S, D, T);
+  else quant_mxfp8_seq_kernel<2><<<grid, D, 0, stream>>>(x, q, scales, S, D, T);
   TA_CUDA_CHECK(cudaGetLastError());
 }
 

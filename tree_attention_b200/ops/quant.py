@@ -99,6 +99,13 @@ class MXFP8SeqTensor:
 
     @classmethod
     def from_float(cls, x: torch.Tensor) -> "MXFP8SeqTensor":
+        if x.is_cuda and x.dtype in (torch.bfloat16, torch.float16, torch.float32):
+            return cls(*_build.load().quant_mxfp8_seq(x.contiguous()))   # csrc/quant.cu
+        return cls.from_float_ref(x)
+
+    @classmethod
+    def from_float_ref(cls, x: torch.Tensor) -> "MXFP8SeqTensor":
+        """PyTorch oracle / CPU path of the quantiser."""
         b, h, s, d = x.shape
         t = (s + SEQ_TILE - 1) // SEQ_TILE
         xf = x.float()
