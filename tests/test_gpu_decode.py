@@ -130,3 +130,24 @@ def test_pdl_back_to_back_steps_match_and_stay_ordered():
     for qi, o in outs[::5]:
         exp, _ = ref.attention_partial_ref(qi, k, v, 0.088, block=16384)
         assert (o.float() - exp).abs().max().item() < 1.5e-2
+
+
+def test_session_end_to_end_step_single_graph():
+    """TreeDecodeSession.step: pinned-host query -> [H2D | fused attention | D2H] replayed as one CUDA graph -> pinned
+    host result; a new query every step, results equal the eager device path."""
+    from tree_attention_b200.models.decoder import TreeDecodeSession
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    k = torch.randn(1, 4, 3000, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(1, 4, 3000, 128, device="cuda", generator=g).bfloat16()
+    sess = TreeDecodeSession([(k, v), (v, k)], softmax_scale=0.09, q_shape=(1, 8, 1, 128))
+    oh = torch.empty(1, 8, 1, 128, dtype=torch.bfloat16).pin_memory()
+    for it in range(4):
+        q = torch.randn(1, 8, 1, 128, generator=torch.Generator().manual_seed(it)).bfloat16()
+        qh = q.pin_memory()
+        layer = it % 2
+        got = sess.step(qh, oh, layer).clone()
+        kk, vv = (k, v) if layer == 0 else (v, k)
+        exp, _ = ref.attention_partial_ref(q.cuda(), kk, vv, 0.09)
+        assert (got.float().cuda() - exp).abs().max().item() < 2e-2
+    assert len(sess.e2e_graphs) == 2
