@@ -226,73 +226,118 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
         const int n0 = j * kBlockN;
         mbar_wait(&s_full[t], j & 1);
         tc_fence_after();
-        int limc = 127;
-        if ((n0 + kBlockN > p.S) || (p.causal && (p.kv_pos0 + n0 + kBlockN - 1 > p.q_pos0 + m0t))) {
-          long long lim = (long long)p.S - n0 - 1;
-          if (p.causal) lim = min(lim, q_pos - p.kv_pos0 - n0);
-          limc = (int)max(-1LL, min(lim, 127LL));
+        const bool need_mask = (n0 + kBlockN > p.S) || (p.causal && (p.kv_pos0 + n0 + kBlockN - 1 > p.q_pos0 + m0t));
+        uint32_t pk[64];
+        bool done = false;
+        // ---- fast path (interior tiles): exponentiate against the CURRENT reference maximum while the tile maximum is
+        // computed in the same loop (MUFU and FMNMX overlap instead of running as two serial phases).  If some row's
+        // maximum turns out to have grown past the lazy-rescale threshold, nothing has been committed yet: the scores are
+        // still in TMEM and the tile is redone on the exact path below.
+        if (!need_mask && !__any_sync(0xffffffffu, m_used == neg_inf_f())) {
+          // TMEM reads run at 64 B/clk per SM: the 64 KB score tile alone costs 1024 cycles, as much as the tile's MMAs
+          // or its 16K ex2.  The row is therefore consumed in four 32-column chunks, the tcgen05.ld of chunk c + 1 in
+          // flight while chunk c is exponentiated.
+          const float neg_m = -m_used;
+          const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
+          uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
+          float mx4[4] = {neg_inf_f(), neg_inf_f(), neg_inf_f(), neg_inf_f()};
+          uint32_t cb[2][32];
+          tmem_ld_32x32b_x32(s_tmem, cb[0]);
+          tmem_ld_wait_on(cb[0]);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            if (cc < 3) tmem_ld_32x32b_x32(s_tmem + 32 * (cc + 1), cb[(cc + 1) & 1]);
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float s0 = __uint_as_float(cb[cc & 1][i]), s1 = __uint_as_float(cb[cc & 1][i + 1]);
+              float x0, x1;
+              unpack_f32x2(fma2_f32x2(pack_f32x2(s0, s1), sc2, nm2), x0, x1);
+              const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+              ls2[(i >> 1) & 3] = add2_f32x2(ls2[(i >> 1) & 3], pack_f32x2(p0, p1));
+              pk[cc * 16 + (i >> 1)] = pack2<BF16>(p0, p1);
+              mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(s0, s1));
+            }
+            if (cc < 3) tmem_ld_wait_on(cb[(cc + 1) & 1]);
+          }
+          const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+          const bool grow = fmaxf(m_used, mx * p.scale_log2) - m_used > kRescaleThreshold;
+          if (!__any_sync(0xffffffffu, grow)) {
+            float a0, a1, b0, b1, c0, c1, d0, d1;
+            unpack_f32x2(ls2[0], a0, a1); unpack_f32x2(ls2[1], b0, b1); unpack_f32x2(ls2[2], c0, c1); unpack_f32x2(ls2[3], d0, d1);
+            l_sum += ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
+            done = true;
+          }
         }
-        uint32_t sr[128];
-        tmem_ld_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
-        tmem_ld_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
-        tmem_ld_32x32b_x32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
-        tmem_ld_32x32b_x32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
-        tmem_ld_wait();
-        if (limc < 127) {  // diagonal tiles and the ragged last tile only
+        if (!done) {
+          // ---- exact path: all 128 scores, mask (diagonal tiles and the ragged last tile only), row maximum, refresh,
+          // exponentiate
+          uint32_t sr[128];
+          tmem_ld_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+          tmem_ld_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+          tmem_ld_32x32b_x32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
+          tmem_ld_32x32b_x32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
+          tmem_ld_wait();
+          if (need_mask) {
+            long long lim = (long long)p.S - n0 - 1;
+            if (p.causal) lim = min(lim, q_pos - p.kv_pos0 - n0);
+            const int limc = (int)max(-1LL, min(lim, 127LL));
 #pragma unroll
-          for (int c = 0; c < 128; ++c)
-            if (c > limc) sr[c] = 0xff800000u;
-        }
-        float mx8[8];
+            for (int c = 0; c < 128; ++c)
+              if (c > limc) sr[c] = 0xff800000u;
+          }
+          float mx8[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
+          for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
 #pragma unroll
-        for (int c = 8; c < 128; c += 8) {
+          for (int c = 8; c < 128; c += 8) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(mx8[i], __uint_as_float(sr[c + i]));
-        }
-        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-        const float m_new = fmaxf(m_used, mx * p.scale_log2);
-        const bool refresh = (m_new - m_used > kRescaleThreshold) || (m_used == neg_inf_f() && m_new != neg_inf_f());
-        if (__any_sync(0xffffffffu, refresh)) {
-          const float alpha = refresh ? fast_exp2(m_used - m_new) : 1.f;
-          if (refresh) { l_sum *= alpha; m_used = m_new; }
-          if (j > 0) {
-            mbar_wait(&pv_done[t], (j - 1) & 1);
-            tc_fence_after();
+            for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(mx8[i], __uint_as_float(sr[c + i]));
+          }
+          const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+          const float m_new = fmaxf(m_used, mx * p.scale_log2);
+          // lazy rescale: refresh the reference max only when it moved by more than the threshold
+          const bool refresh = (m_new - m_used > kRescaleThreshold) || (m_used == neg_inf_f() && m_new != neg_inf_f());
+          if (__any_sync(0xffffffffu, refresh) ) {
+            const float alpha = refresh ? fast_exp2(m_used - m_new) : 1.f;  // m_used=-inf -> 0
+            if (refresh) { l_sum *= alpha; m_used = m_new; }
+            if (j > 0) {
+              mbar_wait(&pv_done[t], (j - 1) & 1);
+              tc_fence_after();
 #pragma unroll
-            for (int c0 = 0; c0 < D; c0 += 32) {
-              uint32_t orow[32];
-              tmem_ld_32x32b_x32(o_tmem + c0, orow);
-              tmem_ld_wait();
+              for (int c0 = 0; c0 < D; c0 += 32) {
+                uint32_t orow[32];
+                tmem_ld_32x32b_x32(o_tmem + c0, orow);
+                tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
-              tmem_st_32x32b_x32(o_tmem + c0, orow);
+                for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
+                tmem_st_32x32b_x32(o_tmem + c0, orow);
+              }
             }
           }
-        }
-        const float neg_m = (m_used == neg_inf_f()) ? 0.f : -m_used;
-        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
-        uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
-        uint32_t pk[64];
+          const float m_sub = (m_used == neg_inf_f()) ? 0.f : m_used;
+          const float neg_m = -m_sub;
+          // exp2(s * c - m) with packed f32x2 scale-subtract and row-sum (FFMA2 / FADD2: half the issue slots)
+          const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
+          uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-        for (int c = 0; c < 128; c += 8) {
+          for (int c = 0; c < 128; c += 8) {
 #pragma unroll
-          for (int i = 0; i < 8; i += 2) {
-            float x0, x1;
-            unpack_f32x2(fma2_f32x2(pack_f32x2(__uint_as_float(sr[c + i]), __uint_as_float(sr[c + i + 1])), sc2, nm2), x0, x1);
-            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-            ls2[i >> 1] = add2_f32x2(ls2[i >> 1], pack_f32x2(p0, p1));
-            pk[(c + i) >> 1] = pack2<BF16>(p0, p1);
+            for (int i = 0; i < 8; i += 2) {
+              float x0, x1;
+              unpack_f32x2(fma2_f32x2(pack_f32x2(__uint_as_float(sr[c + i]), __uint_as_float(sr[c + i + 1])), sc2, nm2), x0, x1);
+              const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+              ls2[i >> 1] = add2_f32x2(ls2[i >> 1], pack_f32x2(p0, p1));
+              pk[(c + i) >> 1] = pack2<BF16>(p0, p1);
+            }
           }
-          if (c == 56) tmem_st_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
+          {
+            float a0, a1, b0, b1, c0, c1, d0, d1;
+            unpack_f32x2(ls2[0], a0, a1); unpack_f32x2(ls2[1], b0, b1); unpack_f32x2(ls2[2], c0, c1); unpack_f32x2(ls2[3], d0, d1);
+            l_sum += ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
+          }
         }
+        tmem_st_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
         tmem_st_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
-        {
-          float a0, a1, b0, b1, c0, c1, d0, d1;
-          unpack_f32x2(ls2[0], a0, a1); unpack_f32x2(ls2[1], b0, b1); unpack_f32x2(ls2[2], c0, c1); unpack_f32x2(ls2[3], d0, d1);
-          l_sum += ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
-        }
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

@@ -20,6 +20,9 @@ namespace ta {
 namespace {
 using namespace fwd_detail;
 
+// profiling aid: cycles spent by softmax thread 0 of CTA 0 in {waiting for S, fast path, exact path, P store + signal}, tiles
+__device__ unsigned long long g_fwd_phase_cycles[5];
+
 template <int D, bool BF16, bool kComm>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant__ CUtensorMap kmap,
@@ -234,84 +237,138 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(qt_ready);
     }
+    const bool prof = (blockIdx.x == 0 && tid == 0);
+    long long c_wait = 0, c_fast = 0, c_exact = 0, c_store = 0;
     for (int j = 0; j < n_tiles; ++j) {
       const int n0 = j * kBlockN;
+      const long long tp0 = clock64();
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
+      const long long tp1 = clock64();
       const uint32_t s_tmem = tmem + (j & 1) * 128 + lane_addr;
-      uint32_t sr[128];
-      tmem_ld_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
-      tmem_ld_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
-      tmem_ld_32x32b_x32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
-      tmem_ld_32x32b_x32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
-      tmem_ld_wait();
-      // mask (diagonal tiles and the ragged last tile only)
       const bool need_mask = (n0 + kBlockN > p.S) || (p.causal && (p.kv_pos0 + n0 + kBlockN - 1 > p.q_pos0 + m0));
-      if (need_mask) {
-        long long lim = (long long)p.S - n0 - 1;
-        if (p.causal) lim = min(lim, q_pos - p.kv_pos0 - n0);
-        const int limc = (int)max(-1LL, min(lim, 127LL));
+      uint32_t pk[64];
+      bool done = false;
+      // ---- fast path (interior tiles): exponentiate against the CURRENT reference maximum while the tile maximum is
+      // computed in the same loop (MUFU and FMNMX overlap instead of running as two serial phases).  If some row's
+      // maximum turns out to have grown past the lazy-rescale threshold, nothing has been committed yet: the scores are
+      // still in TMEM and the tile is redone on the exact path below.
+      if (!need_mask && !__any_sync(0xffffffffu, m_used == neg_inf_f())) {
+        // TMEM reads run at 64 B/clk per SM: the 64 KB score tile alone costs 1024 cycles, as much as the tile's MMAs
+        // or its 16K ex2.  The row is therefore consumed in four 32-column chunks, the tcgen05.ld of chunk c + 1 in
+        // flight while chunk c is exponentiated.
+        const float neg_m = -m_used;
+        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
+        uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
+        float mx4[4] = {neg_inf_f(), neg_inf_f(), neg_inf_f(), neg_inf_f()};
+        uint32_t cb[2][32];
+        tmem_ld_32x32b_x32(s_tmem, cb[0]);
+        tmem_ld_wait_on(cb[0]);
 #pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if (c > limc) sr[c] = 0xff800000u;
+        for (int cc = 0; cc < 4; ++cc) {
+          if (cc < 3) tmem_ld_32x32b_x32(s_tmem + 32 * (cc + 1), cb[(cc + 1) & 1]);
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float s0 = __uint_as_float(cb[cc & 1][i]), s1 = __uint_as_float(cb[cc & 1][i + 1]);
+            float x0, x1;
+            unpack_f32x2(fma2_f32x2(pack_f32x2(s0, s1), sc2, nm2), x0, x1);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+            ls2[(i >> 1) & 3] = add2_f32x2(ls2[(i >> 1) & 3], pack_f32x2(p0, p1));
+            pk[cc * 16 + (i >> 1)] = pack2<BF16>(p0, p1);
+            mx4[(i >> 1) & 3] = fmaxf(mx4[(i >> 1) & 3], fmaxf(s0, s1));
+          }
+          if (cc < 3) tmem_ld_wait_on(cb[(cc + 1) & 1]);
+        }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        const bool grow = fmaxf(m_used, mx * p.scale_log2) - m_used > kRescaleThreshold;
+        if (!__any_sync(0xffffffffu, grow)) {
+          float a0, a1, b0, b1, c0, c1, d0, d1;
+          unpack_f32x2(ls2[0], a0, a1); unpack_f32x2(ls2[1], b0, b1); unpack_f32x2(ls2[2], c0, c1); unpack_f32x2(ls2[3], d0, d1);
+          l_sum += ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
+          done = true;
+        }
       }
-      float mx8[8];
+      const long long tp2 = clock64();
+      if (!done) {
+        // ---- exact path: all 128 scores, mask (diagonal tiles and the ragged last tile only), row maximum, refresh,
+        // exponentiate
+        uint32_t sr[128];
+        tmem_ld_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&sr[0]));
+        tmem_ld_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&sr[32]));
+        tmem_ld_32x32b_x32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
+        tmem_ld_32x32b_x32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
+        tmem_ld_wait();
+        if (need_mask) {
+          long long lim = (long long)p.S - n0 - 1;
+          if (p.causal) lim = min(lim, q_pos - p.kv_pos0 - n0);
+          const int limc = (int)max(-1LL, min(lim, 127LL));
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
+          for (int c = 0; c < 128; ++c)
+            if (c > limc) sr[c] = 0xff800000u;
+        }
+        float mx8[8];
 #pragma unroll
-      for (int c = 8; c < 128; c += 8) {
+        for (int i = 0; i < 8; ++i) mx8[i] = __uint_as_float(sr[i]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(mx8[i], __uint_as_float(sr[c + i]));
-      }
-      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-      const float m_new = fmaxf(m_used, mx * p.scale_log2);
-      // lazy rescale: refresh the reference max only when it moved by more than the threshold
-      const bool refresh = (m_new - m_used > kRescaleThreshold) || (m_used == neg_inf_f() && m_new != neg_inf_f());
-      if (__any_sync(0xffffffffu, refresh) ) {
-        const float alpha = refresh ? fast_exp2(m_used - m_new) : 1.f;  // m_used=-inf -> 0
-        if (refresh) { l_sum *= alpha; m_used = m_new; }
-        if (j > 0) {
-          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          tc_fence_after();
+        for (int c = 8; c < 128; c += 8) {
 #pragma unroll
-          for (int c0 = 0; c0 < D; c0 += 32) {
-            uint32_t orow[32];
-            tmem_ld_32x32b_x32(tmem_o + lane_addr + c0, orow);
-            tmem_ld_wait();
+          for (int i = 0; i < 8; ++i) mx8[i] = fmaxf(mx8[i], __uint_as_float(sr[c + i]));
+        }
+        const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
+        const float m_new = fmaxf(m_used, mx * p.scale_log2);
+        // lazy rescale: refresh the reference max only when it moved by more than the threshold
+        const bool refresh = (m_new - m_used > kRescaleThreshold) || (m_used == neg_inf_f() && m_new != neg_inf_f());
+        if (__any_sync(0xffffffffu, refresh) ) {
+          const float alpha = refresh ? fast_exp2(m_used - m_new) : 1.f;  // m_used=-inf -> 0
+          if (refresh) { l_sum *= alpha; m_used = m_new; }
+          if (j > 0) {
+            mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+            tc_fence_after();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
-            tmem_st_32x32b_x32(tmem_o + lane_addr + c0, orow);
+            for (int c0 = 0; c0 < D; c0 += 32) {
+              uint32_t orow[32];
+              tmem_ld_32x32b_x32(tmem_o + lane_addr + c0, orow);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
+              tmem_st_32x32b_x32(tmem_o + lane_addr + c0, orow);
+            }
           }
         }
-      }
-      const float m_sub = (m_used == neg_inf_f()) ? 0.f : m_used;
-      const float neg_m = -m_sub;
-      // exp2(s * c - m) with packed f32x2 scale-subtract and row-sum (FFMA2 / FADD2: half the issue slots)
-      const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
-      uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
-      uint32_t pk[64];
+        const float m_sub = (m_used == neg_inf_f()) ? 0.f : m_used;
+        const float neg_m = -m_sub;
+        // exp2(s * c - m) with packed f32x2 scale-subtract and row-sum (FFMA2 / FADD2: half the issue slots)
+        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2), nm2 = pack_f32x2(neg_m, neg_m);
+        uint64_t ls2[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-      for (int c = 0; c < 128; c += 8) {
+        for (int c = 0; c < 128; c += 8) {
 #pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          float x0, x1;
-          unpack_f32x2(fma2_f32x2(pack_f32x2(__uint_as_float(sr[c + i]), __uint_as_float(sr[c + i + 1])), sc2, nm2), x0, x1);
-          const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
-          ls2[i >> 1] = add2_f32x2(ls2[i >> 1], pack_f32x2(p0, p1));
-          pk[(c + i) >> 1] = pack2<BF16>(p0, p1);
+          for (int i = 0; i < 8; i += 2) {
+            float x0, x1;
+            unpack_f32x2(fma2_f32x2(pack_f32x2(__uint_as_float(sr[c + i]), __uint_as_float(sr[c + i + 1])), sc2, nm2), x0, x1);
+            const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+            ls2[i >> 1] = add2_f32x2(ls2[i >> 1], pack_f32x2(p0, p1));
+            pk[(c + i) >> 1] = pack2<BF16>(p0, p1);
+          }
+        }
+        {
+          float a0, a1, b0, b1, c0, c1, d0, d1;
+          unpack_f32x2(ls2[0], a0, a1); unpack_f32x2(ls2[1], b0, b1); unpack_f32x2(ls2[2], c0, c1); unpack_f32x2(ls2[3], d0, d1);
+          l_sum += ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
         }
       }
-      {
-        float a0, a1, b0, b1, c0, c1, d0, d1;
-        unpack_f32x2(ls2[0], a0, a1); unpack_f32x2(ls2[1], b0, b1); unpack_f32x2(ls2[2], c0, c1); unpack_f32x2(ls2[3], d0, d1);
-        l_sum += ((a0 + a1) + (b0 + b1)) + ((c0 + c1) + (d0 + d1));
-      }
+      const long long tp3 = clock64();
       tmem_st_32x32b_x32(s_tmem + 0, *reinterpret_cast<uint32_t(*)[32]>(&pk[0]));
       tmem_st_32x32b_x32(s_tmem + 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[32]));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      c_wait += tp1 - tp0; c_fast += tp2 - tp1; c_exact += tp3 - tp2; c_store += clock64() - tp3;
+    }
+    if (prof) {
+      g_fwd_phase_cycles[0] = c_wait; g_fwd_phase_cycles[1] = c_fast; g_fwd_phase_cycles[2] = c_exact; g_fwd_phase_cycles[3] = c_store;
+      g_fwd_phase_cycles[4] = n_tiles;
     }
     // ------------------------------- epilogue --------------------------------------------------
     const int jl = n_tiles - 1;
@@ -417,6 +474,10 @@ void launch_fwd(const AttnShape& s, const void* q, const void* k, const void* v,
 }
 
 }  // namespace
+
+void attn_fwd_phase_cycles(unsigned long long* out5) {
+  TA_CUDA_CHECK(cudaMemcpyFromSymbol(out5, g_fwd_phase_cycles, 5 * sizeof(unsigned long long)));
+}
 
 size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes) {
   const size_t n_items = (size_t)((s.Sq + kBlockM - 1) / kBlockM) * s.Hq * s.B;

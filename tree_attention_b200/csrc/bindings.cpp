@@ -459,6 +459,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dequant_mxfp8", &dequant_mxfp8);
   m.def("attn_fwd", &attn_fwd);
   m.def("attn_fwd_comm_bytes", &attn_fwd_comm_bytes);
+  m.def("attn_fwd_phase_cycles", []() { unsigned long long c[5]; ta::attn_fwd_phase_cycles(c); return py::make_tuple(c[0], c[1], c[2], c[3], c[4]); });
   m.def("attn_bwd", &attn_bwd);
   m.def("symm_allreduce", &symm_allreduce);
   m.def("symm_allreduce_sizes", &symm_allreduce_sizes);
@@ -467,4 +468,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("umma_bs_probe", &umma_bs_probe, py::arg("a8"), py::arg("b8"), py::arg("sfa"), py::arg("sfb"), py::arg("c"),
         py::arg("a_mn_major") = false);
   m.def("num_sms", []() { return ta::num_sms(); });
+  m.def("tmem_ld_bw_probe", [](int warps, int iters) { return ta::tmem_ld_bw_probe(warps, iters, at::cuda::getCurrentCUDAStream()); });
 }

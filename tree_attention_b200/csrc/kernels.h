@@ -78,6 +78,7 @@ void umma_probe_launch(const void* a, const void* b, float* c, int N, int K, int
 
 // block-scaled fp8 probe: C[128, N] fp32 = (A8 o SFA)(128 x 128) x (B8 o SFB)(N x 128)^T, e4m3 + UE8M0 per 32 of K,
 // through tcgen05.mma.kind::mxf8f6f4.block_scale with the scale factors staged in TMEM.
+long long tmem_ld_bw_probe(int warps, int iters, cudaStream_t stream);   // cycles for iters x (warps x 16 KB) of tcgen05.ld
 void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const void* sfb, float* c, int N,
                           cudaStream_t stream, int a_mn_major = 0);
 
@@ -86,6 +87,7 @@ void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const
 // launch produce the final (replicated) output; no NCCL.
 void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                      const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem = 0);
+void attn_fwd_phase_cycles(unsigned long long* out5);   // profiling aid, see attn_fwd_sm100.cu
 size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
 // M = 128 with two softmax warpgroups splitting the score columns (two resident softmax warps per SM sub-partition)
 void attn_fwd3_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,

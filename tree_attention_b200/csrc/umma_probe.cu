@@ -175,7 +175,51 @@ umma_bs_probe_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// TMEM read bandwidth probe: `warps` warps (4 or 8) of one CTA each read 128 fp32 columns of their 32-lane quarter
+// (4 x tcgen05.ld.32x32b.x32 + wait) `iters` times; out[0] = cycles, out[1] = checksum.
+__global__ void __launch_bounds__(256, 1) tmem_ld_bw_kernel(long long* out, int iters) {
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc<128>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t taddr = tmem_base_s + (uint32_t((warp & 3) * 32) << 16);
+  uint32_t acc = 0;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+    uint32_t r[128];
+    tmem_ld_32x32b_x32(taddr + 0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+    tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+    tmem_ld_32x32b_x32(taddr + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+    tmem_ld_32x32b_x32(taddr + 96, *reinterpret_cast<uint32_t(*)[32]>(&r[96]));
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 128; i += 16) acc ^= r[i];
+  }
+  const long long t1 = clock64();
+  __syncthreads();
+  if (threadIdx.x == 0) out[0] = t1 - t0;
+  if (acc == 0x12345u) out[1] = acc;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<128>(tmem_base_s); }
+}
+
 }  // namespace
+
+long long tmem_ld_bw_probe(int warps, int iters, cudaStream_t stream) {
+  long long* d;
+  TA_CUDA_CHECK(cudaMalloc(&d, 2 * sizeof(long long)));
+  tmem_ld_bw_kernel<<<1, warps * 32, 0, stream>>>(d, iters);
+  TA_CUDA_CHECK(cudaGetLastError());
+  long long h[2] = {0, 0};
+  TA_CUDA_CHECK(cudaMemcpyAsync(h, d, sizeof(long long), cudaMemcpyDeviceToHost, stream));
+  TA_CUDA_CHECK(cudaStreamSynchronize(stream));
+  TA_CUDA_CHECK(cudaFree(d));
+  return h[0];
+}
 
 void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const void* sfb, float* c, int N,
                           cudaStream_t stream, int a_mn_major) {
