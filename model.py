@@ -67,6 +67,21 @@ def main(rank: int, world_size: int) -> None:
                               num_kv_heads=cfg.num_kv_heads, seed=cfg.seed)
     logger.info(f"Rank {rank}: Starting computation with seq_len: {cfg.seq_len}, hid_dim: {cfg.num_heads * cfg.head_dim}")
     scale = 1.0 if cfg.softmax_scale is None else cfg.softmax_scale  # the reference's default (model.py:60,100)
+    k_ref, v_ref = kfl, vfl
+    if cfg.kv_format != "native":   # quantised KV cache; the oracle check runs on the de-quantised cache
+        from tree_attention_b200.ops.quant import FP8ChannelTensor, MXFP8SeqTensor, MXFP8Tensor
+
+        if cfg.layout != "bhsd":
+            raise SystemExit("--kv-format needs --layout bhsd")
+        if cfg.kv_format == "fp8":
+            kfl, vfl = FP8ChannelTensor.from_float(kfl), FP8ChannelTensor.from_float(vfl)
+        elif cfg.kv_format == "mxfp8":
+            kfl, vfl = MXFP8Tensor.from_float(kfl), MXFP8SeqTensor.from_float(vfl)
+        elif cfg.kv_format == "mxfp8-simt":
+            kfl, vfl = MXFP8Tensor.from_float(kfl), MXFP8Tensor.from_float(vfl)
+        else:
+            raise SystemExit(f"unknown --kv-format {cfg.kv_format}")
+        k_ref, v_ref = kfl.dequantize(dtype), vfl.dequantize(dtype)
 
     def step():
         return tree_attention(qfl, kfl, vfl, causal=cfg.causal, softmax_scale=scale, backend=cfg.backend,
@@ -83,8 +98,10 @@ def main(rank: int, world_size: int) -> None:
     logger.info(f"Rank {rank}: Computation completed in {seconds}s")
     err = None
     if cfg.check:
-        err = _oracle_check(cfg, qfl, kfl, vfl, output, rank, world_size)
+        err = _oracle_check(cfg, qfl, k_ref, v_ref, output, rank, world_size)
         tol = 2e-2 if dtype in (torch.float16, torch.bfloat16) else 1e-4
+        if cfg.kv_format != "native":
+            tol = 8e-2   # q and P are rounded to e4m3 inside the fp8 kernels
         status = "OK" if err < tol else "MISMATCH"
         logger.info(f"Rank {rank}: max |out - oracle| = {err:.3e} [{status}]")
         if err >= tol:
@@ -98,7 +115,7 @@ def main(rank: int, world_size: int) -> None:
                       "S_per_rank": cfg.seq_len, "S_global": s_global, "D": cfg.head_dim},
             "latency_us": seconds * 1e6, "decode_tokens_per_s": cfg.batch * cfg.q_len / seconds,
             "kv_tokens_per_s": cfg.batch * s_global / seconds, "max_abs_err": err,
-            "backend": cfg.backend, "schedule": cfg.schedule,
+            "backend": cfg.backend, "schedule": cfg.schedule, "kv_format": cfg.kv_format,
         }))
     cleanup()
 

@@ -28,6 +28,7 @@ class TreeAttentionConfig:
     head_dim: int = 128
     q_len: int = 1                  # decode; the reference's only mode
     dtype: str = "fp16"             # model.py:51-53
+    kv_format: str = "native"       # native | fp8 (per-channel e4m3) | mxfp8 (block-scaled, tcgen05) | mxfp8-simt
     layout: str = "bhsd"
     causal: bool = False
     softmax_scale: Optional[float] = None
