@@ -150,38 +150,49 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
     }
   } else if (warp == 9) {
     // =============================== MMA issuer =================================================
-    if (lane == 0) {
+    {
+      // whole warp convergent (descriptors in uniform registers, no per-MMA R2UR waterfall); one elected lane issues
+      const bool leader = elect_one();
       constexpr uint32_t fmt = BF16 ? 1u : 0u;
       constexpr uint32_t idesc_qk = umma_idesc(fmt, fmt, kBlockM, kBlockN, 0, 0);
       constexpr uint32_t idesc_pv = umma_idesc(fmt, fmt, kBlockM, D, 0, 1);
+      const uint64_t q_desc0 = umma_smem_desc_sw128(smem_u32(q_s), 0, 1024);
       auto issue_qk = [&](int t, int j) {
-        const uint32_t q_addr = smem_u32(q_s + t * SM::kTileBytes);
-        const uint32_t k_addr = smem_u32(k_s + (j % NS) * SM::kTileBytes);
+        const uint64_t q_desc = q_desc0 + ((t * SM::kTileBytes) >> 4);
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(k_s + (j % NS) * SM::kTileBytes), 0, 1024);
         const uint32_t d_tmem = tmem + t * 128;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk / 4) * SM::kAtomBytes + (kk % 4) * 32;
-          umma_ss_f16(d_tmem, umma_smem_desc_sw128(q_addr + off, 0, 1024), umma_smem_desc_sw128(k_addr + off, 0, 1024),
-                      idesc_qk, kk > 0 ? 1u : 0u);
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = ((kk / 4) * SM::kAtomBytes + (kk % 4) * 32) >> 4;
+            umma_ss_f16(d_tmem, q_desc + off, k_desc + off, idesc_qk, kk > 0 ? 1u : 0u);
+          }
+          umma_commit(&s_full[t]);
         }
-        umma_commit(&s_full[t]);
+        __syncwarp();
       };
       auto issue_pv = [&](int t, int j) {
-        const uint32_t v_addr = smem_u32(v_s + (j % NS) * SM::kTileBytes);
+        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(v_s + (j % NS) * SM::kTileBytes), kBlockN * 128, 1024);
         const uint32_t p_tmem = tmem + t * 128;
         const uint32_t o_tmem = tmem + 256 + t * 128;
+        if (leader) {
 #pragma unroll
-        for (int kk = 0; kk < kBlockN / 16; ++kk)
-          umma_ts_f16(o_tmem, p_tmem + kk * 8, umma_smem_desc_sw128(v_addr + kk * 2048, kBlockN * 128, 1024), idesc_pv,
-                      (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&pv_done[t]);
+          for (int kk = 0; kk < kBlockN / 16; ++kk)
+            umma_ts_f16(o_tmem, p_tmem + kk * 8, v_desc + ((kk * 2048) >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(&pv_done[t]);
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (leader) umma_commit(bar);
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_qk(0, 0);
       if (has_b) issue_qk(1, 0);
-      umma_commit(&k_empty[0]);
+      commit(&k_empty[0]);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % NS;
         const uint32_t ph = (j / NS) & 1;
@@ -199,10 +210,10 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant
           tc_fence_after();
           issue_pv(1, j);
         }
-        umma_commit(&v_empty[st]);
+        commit(&v_empty[st]);
         if (j + 1 < n_tiles) {
           if (has_b) issue_qk(1, j + 1);
-          umma_commit(&k_empty[(j + 1) % NS]);
+          commit(&k_empty[(j + 1) % NS]);
         }
       }
     }
