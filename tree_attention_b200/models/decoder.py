@@ -81,7 +81,8 @@ class TreeDecodeSession:
             return
         for i in range(len(self.kv)):  # allocates workspaces and (collectively) the symmetric region
             self.out_static[i] = self._eager(self.q_static, i)
-        torch.cuda.synchronize()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
         if self._use_graph:
             side = torch.cuda.Stream()
             for i in range(len(self.kv)):
@@ -143,7 +144,8 @@ class TreeDecodeSession:
         else:
             out = self._eager(self.q_static, layer)
         out_host.copy_(out, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        if self.device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
         return out_host
 
     def append_kv(self, layer: int, k_new: torch.Tensor, v_new: torch.Tensor, position: int) -> None:
