@@ -413,7 +413,8 @@ def run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier):
         out["mxfp8_kv_max_abs_diff_vs_bf16"] = float((o8.float() - o16.float()).abs().max())
         out["mxfp8_kv_eager_ms_per_step"] = timeit(
             lambda i: ta.tree_attention(q, kq, vq, softmax_scale=scale, backend=args.backend), steps=200)
-        if q.shape[-1] == 128 and (q.shape[1] // kvs[0][0].shape[1]) * q.shape[2] <= 16:
+        if world == 1 and q.shape[-1] == 128 and (q.shape[1] // kvs[0][0].shape[1]) * q.shape[2] <= 16:
+            # (single-GPU extra; the multi-GPU fused fp8 paths are covered by tests/test_gpu_multi.py)
             # the same MX cache with V blocked along the keys: both GEMMs on tcgen05.mma.kind::mxf8f6f4.block_scale
             from tree_attention_b200.ops.quant import FP8ChannelTensor, MXFP8SeqTensor
 
