@@ -26,7 +26,6 @@ def test_single_rank_matches_autograd_of_oracle():
 
 
 def _worker(rank, world):
-    import torch.distributed as dist
     from tree_attention_b200.ops import reference as ref
     from tree_attention_b200.ops.autograd import tree_attention_func
 

@@ -1,6 +1,5 @@
 """The (o, lse) combine is an associative, commutative monoid with identity (0, -inf)."""
 import itertools
-import math
 
 import pytest
 import torch

@@ -14,7 +14,6 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-from ..ops import local as local_ops
 from ..parallel.tree import tree_attention
 
 

@@ -10,7 +10,6 @@ switching frameworks still needs the op as a layer, so:
 """
 from __future__ import annotations
 
-import math
 from typing import Optional
 
 import torch

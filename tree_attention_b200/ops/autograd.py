@@ -13,7 +13,6 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
-import torch.distributed as dist
 
 from ..parallel.tree import _world, tree_attention
 from . import reference as ref

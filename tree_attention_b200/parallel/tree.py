@@ -27,7 +27,6 @@ import torch.distributed as dist
 from ..ops import local as local_ops
 from ..ops import reference as ref
 from . import symm
-from .runtime import get_runtime
 
 import contextlib
 import os as _os

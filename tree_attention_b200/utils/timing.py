@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import statistics
 import time
-from typing import Callable, List, Optional
+from typing import Callable, List
 
 import torch
 import torch.distributed as dist
