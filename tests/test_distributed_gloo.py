@@ -71,3 +71,28 @@ def _worker_unequal(rank, world):
 
 def test_unequal_shards_and_masked_rank(port):
     run_distributed(_worker_unequal, 3, port)
+
+
+def _worker_quantised(rank, world):
+    """fp8 KV caches through the distributed API on CPU (de-quantising path): every format, every rank agrees."""
+    import tree_attention_b200 as ta
+    from tree_attention_b200.ops import quant, reference as ref
+
+    q, k, v = ta.make_data((1, 4, 160, 128), rank, "cpu", dtype=torch.float32, sq=2, num_kv_heads=2, log=False)
+    for name, kq, vq in (
+        ("channel", quant.FP8ChannelTensor.from_float(k), quant.FP8ChannelTensor.from_float(v)),
+        ("mx", quant.MXFP8Tensor.from_float(k), quant.MXFP8Tensor.from_float(v)),
+        ("mx_seq", quant.MXFP8Tensor.from_float(k), quant.MXFP8SeqTensor.from_float(v)),
+    ):
+        kf, vf = _gather_kv(kq.dequantize(), vq.dequantize(), world)
+        o_ref, _ = ref.attention_ref(q, kf, vf, causal=True)
+        out = ta.tree_attention(q, kq, vq, causal=True)
+        assert torch.allclose(out.double(), o_ref, atol=1e-5), (name, (out.double() - o_ref).abs().max())
+        outs = [torch.empty_like(out) for _ in range(world)]
+        dist.all_gather(outs, out.contiguous())
+        for o in outs:
+            assert torch.allclose(o, outs[0], atol=1e-6), name
+
+
+def test_quantised_kv_caches_gloo(port):
+    run_distributed(_worker_quantised, 2, port)
