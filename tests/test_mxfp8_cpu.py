@@ -88,3 +88,25 @@ def test_quantised_cache_append_rows():
     cq = quant.FP8ChannelTensor.from_float(base, headroom=8.0)
     cq.write_rows(70, new)
     assert (cq.dequantize()[:, :, 70:73] - new).abs().max().item() <= 2 ** -4 * 8.0 * base.abs().max().item()
+
+
+def test_quantiser_properties_hypothesis():
+    """For both MX layouts: bounded relative error per block, no saturation, and re-quantising a de-quantised tensor is
+    lossless in value (idempotence)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(s=st.integers(1, 300), log_scale=st.floats(-20, 20), seed=st.integers(0, 10_000))
+    def prop(s, log_scale, seed):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(1, 2, s, 64, generator=g) * (2.0 ** log_scale)
+        for cls in (quant.MXFP8Tensor, quant.MXFP8SeqTensor):
+            t = cls.from_float(x)
+            y = t.dequantize()
+            assert torch.isfinite(y).all()
+            assert (y - x).abs().max().item() <= 2 ** -4 * x.abs().max().item() + 1e-30
+            assert (t.data.view(torch.float8_e4m3fn).float().abs() <= 448).all()
+            y2 = cls.from_float(y).dequantize()
+            assert torch.equal(y2, y)
+
+    prop()
