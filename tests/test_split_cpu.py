@@ -1,0 +1,37 @@
+"""The decode kernels' stream-K split (host code in csrc/decode_tc_sm100.cu, shared by all three decode kernels):
+every 128-key tile is owned by exactly one CTA, CTA loads differ by at most one tile, and ``max_parts`` -- which sizes the
+split-merge workspace -- really bounds the number of CTAs that touch one KV head (a violation would be a buffer overflow
+in the kernel).  Pure host code: runs without a GPU."""
+import pytest
+
+from tree_attention_b200 import _build
+
+hypothesis = pytest.importorskip("hypothesis")
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+def _ranges(total, grid):
+    q, rem = divmod(total, grid)
+    lo = [c * q + min(c, rem) for c in range(grid + 1)]
+    return lo
+
+
+@settings(max_examples=300, deadline=None)
+@given(b=st.integers(1, 4), hkv=st.integers(1, 64), s=st.integers(1, 300_000), ncta=st.sampled_from([1, 8, 132, 148, 296]))
+def test_split_covers_every_tile_once_and_max_parts_bounds_sharing(b, hkv, s, ncta):
+    C = _build.load()
+    grid, max_parts = C.decode_split_for(b, hkv, s, ncta)
+    tph = (s + 127) // 128
+    total = b * hkv * tph
+    assert 1 <= grid <= min(ncta, total)
+    lo = _ranges(total, grid)
+    assert lo[0] == 0 and lo[-1] == total
+    sizes = [lo[c + 1] - lo[c] for c in range(grid)]
+    assert min(sizes) >= 1 and max(sizes) - min(sizes) <= 1
+    # CTAs touching head x = those whose [lo, hi) intersects [x * tph, (x + 1) * tph)
+    worst = 0
+    for x in range(b * hkv):
+        first = next(c for c in range(grid) if lo[c + 1] > x * tph)
+        last = next(c for c in range(grid - 1, -1, -1) if lo[c] < (x + 1) * tph)
+        worst = max(worst, last - first + 1)
+    assert worst <= max_parts, (worst, max_parts, b, hkv, s, ncta)

@@ -468,5 +468,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("umma_bs_probe", &umma_bs_probe, py::arg("a8"), py::arg("b8"), py::arg("sfa"), py::arg("sfb"), py::arg("c"),
         py::arg("a_mn_major") = false);
   m.def("num_sms", []() { return ta::num_sms(); });
+  // host-only: the stream-K split of (B x Hkv x ceil(S / 128)) tiles over `ncta` persistent CTAs -> (grid, max_parts).
+  // Needs no device; tests/test_split_cpu.py checks that max_parts really bounds the CTAs sharing one KV head.
+  m.def("decode_split_for", [](int B, int Hkv, int S, int ncta) {
+    AttnShape s{};
+    s.B = B; s.Hkv = Hkv; s.Hq = Hkv; s.Sq = 1; s.S = S; s.D = 128;
+    int g = 0, mp = 0;
+    ta::decode_tc_split(s, ncta, &g, &mp);
+    return py::make_tuple(g, mp);
+  });
   m.def("tmem_ld_bw_probe", [](int warps, int iters) { return ta::tmem_ld_bw_probe(warps, iters, at::cuda::getCurrentCUDAStream()); });
 }
