@@ -5,6 +5,8 @@
   ``csrc/build/_C.so`` in the tree, so the binary travels to the GPU box with the repo snapshot.
 * ``load()`` imports that ``.so`` directly (no ninja, no JIT cache) when its recorded source hash
   matches; otherwise it rebuilds if ``nvcc`` is present and fails loudly if not.
+
+The reference (``/root/reference/model.py``) has no native code to build.
 """
 from __future__ import annotations
 

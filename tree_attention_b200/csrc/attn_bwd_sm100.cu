@@ -13,6 +13,8 @@
 // with S/dP double-buffered in TMEM (64-column tiles) so that the tensor pipe works on tile j+1 while the
 // SIMT pipes work on tile j.  The same swizzled smem tile is consumed K-major by one MMA and MN-major by
 // another (Q and dO in bwd_dkv, K in bwd_dq) -- only the descriptor differs.
+// Reference: none -- /root/reference/model.py has no backward; this differentiates the op it defines at model.py:74-80 (local
+// attention) and model.py:103-124 (combine).
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"

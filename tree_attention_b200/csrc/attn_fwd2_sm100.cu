@@ -10,6 +10,7 @@
 //   * the softmax is two-pass over TMEM in 32-column chunks (max, then exp/pack), so a row needs ~40
 //     registers instead of 128 and the CTA runs 12 warps without spills.
 // TMEM: S_A [0,128) | S_B [128,256) | O_A [256,384) | O_B [384,512);  P_t aliases S_t[0,64).
+// Reference: replaces /root/reference/model.py:74-80 (matmul -> softmax -> matmul -> logsumexp), like attn_fwd_sm100.cu.
 #include "attn_fwd_common.cuh"
 
 namespace ta {

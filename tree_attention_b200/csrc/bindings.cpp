@@ -1,4 +1,5 @@
 // Python bindings (torch extension) for the sm_100a kernels and the symmetric-memory runtime.
+// Reference: the Python <-> native boundary; /root/reference/model.py calls stock torch ops instead (model.py:74-80, 108-115).
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <pybind11/stl.h>

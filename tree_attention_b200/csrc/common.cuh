@@ -1,5 +1,6 @@
 // Shared device helpers for the sm_100a kernels: mbarrier, TMA, tcgen05/TMEM, sys-scope
 // acquire/release, bounded spins.  Everything here is inline PTX; no CUTLASS dependency.
+// Reference: none -- /root/reference/model.py contains no device code.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>

@@ -11,6 +11,8 @@
 // P^T is written to shared memory by the softmax threads (B operands cannot come from TMEM) in the 128B-swizzled
 // K-major layout and made visible with fence.proxy.async.  Split-KV scheduling, workspace, tickets and the LL-tagged
 // cross-GPU combine are those of decode_simt.cu / decode_tc_sm100.cu.  R = (Hq/Hkv) x Sq <= 16, head_dim = 128.
+// Reference: replaces flash_res_lse (/root/reference/model.py:60-83) and the combine of tree_decode (model.py:85-124) for <= 16
+// packed query rows per KV head.
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"

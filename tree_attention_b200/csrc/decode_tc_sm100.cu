@@ -12,6 +12,8 @@
 //     attn_fwd_sm100.cu (double-buffered S, lazy rescale), only warps that own valid rows do softmax work;
 //   * epilogue: (O, m, l) of the valid rows -> workspace -> atomic ticket -> the last CTA of the head merges the
 //     splits in part order -> output, or LL-tagged 8-byte words to every peer + deferred cross-GPU merge.
+// Reference: replaces flash_res_lse (/root/reference/model.py:60-83) and the combine of tree_decode (model.py:85-124) for up to
+// 128 packed query rows per KV head.
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"

@@ -1,6 +1,7 @@
 // Host helpers shared by the kernel launchers: CUDA error checks and TMA tensor-map creation
 // (cuTensorMapEncodeTiled is fetched through the runtime's driver entry point, so nothing links
 // against libcuda directly).
+// Reference: none (host helpers of the native layer; /root/reference/model.py has no native code).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>

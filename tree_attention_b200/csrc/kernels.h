@@ -1,4 +1,5 @@
 // Plain-C++ launcher interface between the CUDA translation units and the torch bindings.
+// Reference: none (launcher declarations of the native layer; the reference is a single Python file, /root/reference/model.py).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -2,6 +2,7 @@
 // consecutive elements of the innermost (head) dimension.  Used for the block-scaled-fp8 KV cache
 // (BASELINE.json config "256K, block-scaled fp8 forward").  The scale is the smallest power of two that maps
 // the block's amax into the e4m3 range (|x| <= 448), so quantisation never saturates.
+// Reference: none -- /root/reference/model.py is fp16 only (model.py:51-53); fp8 KV caches are BASELINE.json's fp8 config.
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"

@@ -10,6 +10,7 @@
 //   phase C  every rank acquires the result flags of all chunks, so that when the kernel retires the
 //            replicated sum is complete in local memory.
 // Per rank NVLink traffic: (W-1)/W * n in + (W-1)/W * n out.  Slots are double-buffered by epoch parity.
+// Reference: the reference sums across ranks with blocking ncclAllReduce (/root/reference/model.py:108-115); it has no backward.
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"

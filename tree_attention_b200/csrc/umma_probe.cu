@@ -6,6 +6,7 @@
 //     b_mn_major = 0 : B is (N, K) row-major  ("K-major", like K in Q K^T)
 //     b_mn_major = 1 : B is (K, N) row-major  ("MN-major", like V in P V)
 //     a_from_tmem = 1: A is written to TMEM with tcgen05.st and consumed by the .ts MMA form (like P)
+// Reference: none (hardware layout probes for the tcgen05 kernels).
 #include "common.cuh"
 #include "host_utils.h"
 #include "kernels.h"

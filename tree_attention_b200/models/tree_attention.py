@@ -1,6 +1,7 @@
 """``nn.Module`` front-ends.
 
-The reference has no modules or parameters ("no nn.Module, no requires_grad").  A user
+The reference has no modules or parameters ("no nn.Module, no requires_grad"; the op itself is
+``/root/reference/model.py:85-124``).  A user
 switching frameworks still needs the op as a layer, so:
 
 * ``TreeAttention``      -- the bare op as a module (replicated q, sequence-sharded k/v).

@@ -1,4 +1,4 @@
-"""Autograd for tree attention (the reference has no backward at all -- SURVEY.md 5.7 / 7.4).
+"""Autograd for tree attention (the reference, ``/root/reference/model.py``, has no backward at all -- SURVEY.md 5.7 / 7.4).
 
 Forward leaves the GLOBAL ``o`` and ``lse`` on every rank.  Backward on rank r:
 

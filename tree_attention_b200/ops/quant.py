@@ -1,7 +1,8 @@
 """Block-scaled fp8 (OCP MX style): e4m3 elements + one UE8M0 power-of-two scale per 32 elements of the
 innermost dimension.  ``csrc/quant.cu`` holds the CUDA kernels; the PyTorch implementation below is the
 oracle and the CPU path.  Used for the mxfp8 KV cache of the streaming decode kernel (half the HBM bytes of
-bf16: decode is bandwidth bound, so this is up to 2x on the headline op)."""
+bf16: decode is bandwidth bound, so this is up to 2x on the headline op).  The reference is fp16 only
+(``/root/reference/model.py:51-53``)."""
 from __future__ import annotations
 
 from dataclasses import dataclass
