@@ -96,3 +96,35 @@ def _worker_quantised(rank, world):
 
 def test_quantised_kv_caches_gloo(port):
     run_distributed(_worker_quantised, 2, port)
+
+
+def _worker_session(rank, world):
+    """TreeDecodeSession on CPU ranks: step, append on the owner rank, step again -- against the gathered oracle."""
+    import tree_attention_b200 as ta
+    from tree_attention_b200.models.decoder import TreeDecodeSession
+    from tree_attention_b200.ops import reference as ref
+
+    cap, used = 96, 90
+    q, k, v = ta.make_data((1, 4, cap, 32), rank, "cpu", dtype=torch.float32, num_kv_heads=2, log=False)
+    k[:, :, used:] = 0
+    v[:, :, used:] = 0
+    sess = TreeDecodeSession([(k, v)], softmax_scale=0.2, q_shape=(1, 4, 1, 32), backend="auto")
+    oh = torch.empty(1, 4, 1, 32)
+
+    def oracle():
+        kf, vf = _gather_kv(k, v, world)
+        return ref.attention_ref(q, kf, vf, softmax_scale=0.2)[0]
+
+    out0 = sess.step(q, oh, 0).clone()
+    assert torch.allclose(out0.double(), oracle(), atol=1e-5)
+    g = torch.Generator().manual_seed(7)
+    k_new, v_new = torch.randn(1, 2, 1, 32, generator=g) * 3, torch.randn(1, 2, 1, 32, generator=g) * 3
+    if rank == world - 1:                      # the owner of the new position appends
+        sess.append_kv(0, k_new, v_new, used)
+    out1 = sess.step(q, oh, 0).clone()
+    assert torch.allclose(out1.double(), oracle(), atol=1e-5)
+    assert (out1 - out0).abs().max() > 1e-6
+
+
+def test_decode_session_gloo(port):
+    run_distributed(_worker_session, 2, port)
