@@ -45,3 +45,18 @@ def test_umma_block_scaled_probe(n, a_mn_major):
     exp = quant.dequantize_mxfp8(a8, sfa) @ quant.dequantize_mxfp8(b8, sfb).t()
     err = (c - exp).abs().max().item() / exp.abs().max().item()
     assert err < 1e-5, err
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("TREE_ATTN_EXPERIMENTAL"),
+                    reason="cta_group::2 probe is compile-checked only so far (docs/NEXT.md); set TREE_ATTN_EXPERIMENTAL=1 to run it")
+def test_umma_2cta_probe():
+    """One tcgen05.mma.cta_group::2 GEMM (M = 256 over a CTA pair, each CTA holding half of B's rows)."""
+    C = _build.load()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.randn(256, 64, device="cuda", generator=g).bfloat16()
+    b = torch.randn(128, 64, device="cuda", generator=g).bfloat16()
+    c = torch.zeros(256, 128, device="cuda", dtype=torch.float32)
+    C.umma_2cta_probe(a, b, c)
+    torch.cuda.synchronize()
+    exp = a.float() @ b.float().t()
+    assert (c - exp).abs().max().item() < 1e-2

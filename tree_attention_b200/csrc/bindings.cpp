@@ -468,6 +468,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("umma_probe", &umma_probe);
   m.def("umma_bs_probe", &umma_bs_probe, py::arg("a8"), py::arg("b8"), py::arg("sfa"), py::arg("sfb"), py::arg("c"),
         py::arg("a_mn_major") = false);
+  m.def("umma_2cta_probe", [](const at::Tensor& a, const at::Tensor& b, at::Tensor& c) {   // EXPERIMENTAL, see umma_probe.cu
+    c10::cuda::CUDAGuard guard(a.device());
+    TORCH_CHECK(a.scalar_type() == at::kBFloat16 && b.scalar_type() == at::kBFloat16 && c.scalar_type() == at::kFloat);
+    TORCH_CHECK(a.is_contiguous() && b.is_contiguous() && c.is_contiguous() && a.size(0) == 256 && a.size(1) == 64 &&
+                b.size(0) == 128 && b.size(1) == 64 && c.size(0) == 256 && c.size(1) == 128);
+    ta::umma_2cta_probe_launch(a.data_ptr(), b.data_ptr(), c.data_ptr<float>(), 128, at::cuda::getCurrentCUDAStream());
+  });
   m.def("num_sms", []() { return ta::num_sms(); });
   // host-only: the stream-K split of (B x Hkv x ceil(S / 128)) tiles over `ncta` persistent CTAs -> (grid, max_parts).
   // Needs no device; tests/test_split_cpu.py checks that max_parts really bounds the CTAs sharing one KV head.

@@ -80,6 +80,8 @@ void umma_probe_launch(const void* a, const void* b, float* c, int N, int K, int
 // block-scaled fp8 probe: C[128, N] fp32 = (A8 o SFA)(128 x 128) x (B8 o SFB)(N x 128)^T, e4m3 + UE8M0 per 32 of K,
 // through tcgen05.mma.kind::mxf8f6f4.block_scale with the scale factors staged in TMEM.
 long long tmem_ld_bw_probe(int warps, int iters, cudaStream_t stream);   // cycles for iters x (warps x 16 KB) of tcgen05.ld
+// EXPERIMENTAL (compile-checked only): C[256, 128] = A[256, 64] B[128, 64]^T with one cta_group::2 MMA over a CTA pair
+void umma_2cta_probe_launch(const void* a, const void* b, float* c, int N, cudaStream_t stream);
 void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const void* sfb, float* c, int N,
                           cudaStream_t stream, int a_mn_major = 0);
 

@@ -176,6 +176,83 @@ umma_bs_probe_kernel(const __grid_constant__ CUtensorMap amap, const __grid_cons
   if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
+// ---- 2-CTA probe (EXPERIMENTAL: compile-checked only, not yet run on hardware -- docs/NEXT.md) ---------------------------
+// One tcgen05.mma.cta_group::2 GEMM, M = 256 over a CTA pair: CTA r holds rows [128 r, +128) of A and HALF of B's N rows
+// (rows [N/2 r, +N/2)) in its own shared memory at identical offsets; each CTA's TMEM receives its 128 rows of C.
+// C[256, N] = A[256, 64] * B[N, 64]^T, bf16 inputs, N = 128.  The leader CTA issues the MMAs and signals both CTAs with a
+// multicast commit.  PTX forms follow cute/arch/mma_sm100_umma.hpp and cutlass/arch/barrier.h.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+umma_2cta_probe_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap, float* c, int N) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  uint8_t* a_s = smem;                 // [128 rows][64 bf16] = one 128B-swizzled atom column
+  uint8_t* b_s = smem + 128 * 128;     // [N / 2 rows][64 bf16]
+  if (tid == 0) { mbar_init(&bar_load, 1); mbar_init(&bar_mma, 1); fence_mbar_init(); }
+  if (warp == 0) {   // the same warp id in both CTAs allocates the same columns in both TMEMs
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  if (tid == 0) {    // every CTA loads its own operand halves into its own shared memory
+    mbar_arrive_expect_tx(&bar_load, 128 * 128 + (N / 2) * 128);
+    tma_load_2d(a_s, &amap, &bar_load, 0, (int)rank * 128);
+    tma_load_2d(b_s, &bmap, &bar_load, 0, (int)rank * (N / 2));
+  }
+  mbar_wait(&bar_load, 0);
+  cluster_sync_all();   // both CTAs' operands are in place before the leader issues
+  if (rank == 0 && warp == 1) {
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc(1, 1, 256, N, 0, 0);
+      const uint32_t zero = 0;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t ad = umma_smem_desc_sw128(smem_u32(a_s) + kk * 32, 0, 1024);
+        const uint64_t bd = umma_smem_desc_sw128(smem_u32(b_s) + kk * 32, 0, 1024);
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+            ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(kk > 0 ? 1u : 0u), "r"(zero)
+            : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                   ::"r"(smem_u32(&bar_mma)), "h"((uint16_t)3) : "memory");
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(tmem + (uint32_t(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) c[((size_t)rank * 128 + tid) * N + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+  }
+}
+
 // TMEM read bandwidth probe: `warps` warps (4 or 8) of one CTA each read 128 fp32 columns of their 32-lane quarter
 // (4 x tcgen05.ld.32x32b.x32 + wait) `iters` times; out[0] = cycles, out[1] = checksum.
 __global__ void __launch_bounds__(256, 1) tmem_ld_bw_kernel(long long* out, int iters) {
@@ -220,6 +297,28 @@ long long tmem_ld_bw_probe(int warps, int iters, cudaStream_t stream) {
   TA_CUDA_CHECK(cudaStreamSynchronize(stream));
   TA_CUDA_CHECK(cudaFree(d));
   return h[0];
+}
+
+void umma_2cta_probe_launch(const void* a, const void* b, float* c, int N, cudaStream_t stream) {
+  if (N != 128) throw std::runtime_error("umma_2cta_probe: N must be 128");
+  auto enc = get_encode_tiled();
+  auto mk = [&](const void* base, uint64_t rows, uint32_t box_rows) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {64, rows};
+    cuuint64_t strides[1] = {64 * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("umma_2cta_probe: cuTensorMapEncodeTiled failed " + std::to_string((int)r));
+    return m;
+  };
+  CUtensorMap amap = mk(a, 256, 128), bmap = mk(b, N, N / 2);
+  const size_t smem = 1024 + 128 * 128 + (size_t)(N / 2) * 128;
+  TA_CUDA_CHECK(cudaFuncSetAttribute(umma_2cta_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_2cta_probe_kernel<<<2, 128, smem, stream>>>(amap, bmap, c, N);
+  TA_CUDA_CHECK(cudaGetLastError());
 }
 
 void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const void* sfb, float* c, int N,
