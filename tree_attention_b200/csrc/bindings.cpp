@@ -149,7 +149,10 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at:
   // variant 0 = auto = 1: the M=128 kernel with double-buffered S.  The M=256 ping-pong kernel (variant 2) is kept
   // selectable; it measured slower on B200 (single-buffered S per tile exposes softmax + 2 GEMMs per step).
   const bool use2 = variant == 2;
-  if (variant == 5)
+  if (variant == 7)   // EXPERIMENTAL 2-CTA forward: compile-checked only (docs/NEXT.md)
+    ta::attn_fwd7_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
+                         at::cuda::getCurrentCUDAStream());
+  else if (variant == 5)
     ta::attn_fwd5_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
                          at::cuda::getCurrentCUDAStream());
   else if (variant == 4)

@@ -95,6 +95,9 @@ size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
 // M = 128 with two softmax warpgroups splitting the score columns (two resident softmax warps per SM sub-partition)
 void attn_fwd3_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                       const CommCtxHost& comm, cudaStream_t stream);
+// EXPERIMENTAL (compile-checked only): cluster of two CTAs, tcgen05.mma.cta_group::2 with M = 256, half of each B operand per CTA
+void attn_fwd7_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                      const CommCtxHost& comm, cudaStream_t stream);
 // M = 256 (two query tiles), BLOCK_N = 64, scores double-buffered per tile
 void attn_fwd5_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                       const CommCtxHost& comm, cudaStream_t stream);
