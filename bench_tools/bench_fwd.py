@@ -62,14 +62,6 @@ def main():
             res["tcgen05_own"] = t["median_ms"]
             res["tcgen05_own_sustained"] = t["sustained_ms"]
             own_clocks = t["clocks"]
-            t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=1), a.steps, a.warmup)
-            res["tcgen05_own_v1_m128"] = t["median_ms"]
-            t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=3), a.steps, a.warmup)
-            res["tcgen05_own_v3_colsplit"] = t["median_ms"]
-            t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=4), a.steps, a.warmup)
-            res["tcgen05_own_v4_m256"] = t["median_ms"]
-            t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=5), a.steps, a.warmup)
-            res["tcgen05_own_v5_m256_n64"] = t["median_ms"]
             t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=6), a.steps, a.warmup)
             res["tcgen05_own_v6_q_in_tmem"] = t["median_ms"]
             if a.libs:

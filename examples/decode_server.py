@@ -33,8 +33,8 @@ def worker(rank: int, world: int, a) -> None:
     for layer in range(a.layers):
         _, k, v = ta.make_data((1, a.heads, cap, a.head_dim), rank, dev, dtype=dtype, num_kv_heads=a.kv_heads,
                                seed=layer, log=False)
-        k[:, :, a.tokens_per_rank:] = 0         # unused tail of the preallocated shard
-        v[:, :, a.tokens_per_rank:] = 0
+        k[:, :, a.tokens_per_rank:] = 0         # unwritten tail of the preallocated shard: excluded by the fill level
+        v[:, :, a.tokens_per_rank:] = 0         # (kept finite: the tensor-core kernels multiply it by exact zeros)
         if a.kv_format == "fp8":
             k, v = FP8ChannelTensor.from_float(k, headroom=2.0), FP8ChannelTensor.from_float(v, headroom=2.0)
         elif a.kv_format == "mxfp8":
@@ -42,11 +42,10 @@ def worker(rank: int, world: int, a) -> None:
         layers.append((k, v))
     scale = a.head_dim ** -0.5
     sess = TreeDecodeSession(layers, softmax_scale=scale, q_shape=(1, a.heads, 1, a.head_dim), dtype=dtype,
-                             backend="auto")
+                             backend="auto", kv_lens=[a.tokens_per_rank] * a.layers)
     g = torch.Generator().manual_seed(1234)    # the same queries / new tokens on every rank
     oh = torch.empty(1, a.heads, 1, a.head_dim, dtype=dtype)
     oh = oh.pin_memory() if dev.type == "cuda" else oh
-    filled = a.tokens_per_rank
     t0 = time.perf_counter()
     for step in range(a.steps):
         for layer in range(a.layers):
@@ -55,10 +54,8 @@ def worker(rank: int, world: int, a) -> None:
             sess.step(q, oh, layer)
             k_new = torch.randn(1, a.kv_heads or a.heads, 1, a.head_dim, generator=g).to(dtype)
             v_new = torch.randn(1, a.kv_heads or a.heads, 1, a.head_dim, generator=g).to(dtype)
-            if step % world == rank:            # round-robin owner of the new position
-                sess.append_kv(layer, k_new.to(dev), v_new.to(dev), filled)
-        if step % world == rank:
-            filled += 1
+            if step % world == rank:            # round-robin owner of the new position: appends at its fill level
+                sess.append_kv(layer, k_new.to(dev), v_new.to(dev))
     if dev.type == "cuda":
         torch.cuda.synchronize()
     dt = time.perf_counter() - t0

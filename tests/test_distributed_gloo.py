@@ -99,31 +99,69 @@ def test_quantised_kv_caches_gloo(port):
 
 
 def _worker_session(rank, world):
-    """TreeDecodeSession on CPU ranks: step, append on the owner rank, step again -- against the gathered oracle."""
+    """TreeDecodeSession on CPU ranks with FILL LEVELS: the tail of the preallocated shard holds garbage and must not
+    take part in the softmax; step, append on the owner rank (which raises its level), step again -- against the oracle
+    over the filled rows only (the old test zero-filled the tail and encoded the dilution)."""
     import tree_attention_b200 as ta
     from tree_attention_b200.models.decoder import TreeDecodeSession
     from tree_attention_b200.ops import reference as ref
 
-    cap, used = 96, 90
+    cap = 96
+    used = 90 if rank == world - 1 else cap     # the last rank's shard is still filling up
     q, k, v = ta.make_data((1, 4, cap, 32), rank, "cpu", dtype=torch.float32, num_kv_heads=2, log=False)
-    k[:, :, used:] = 0
-    v[:, :, used:] = 0
-    sess = TreeDecodeSession([(k, v)], softmax_scale=0.2, q_shape=(1, 4, 1, 32), backend="auto")
+    k[:, :, used:] = 1e3                        # garbage in the unwritten tail: must be ignored
+    v[:, :, used:] = -1e3
+    sess = TreeDecodeSession([(k, v)], softmax_scale=0.2, q_shape=(1, 4, 1, 32), backend="auto", kv_lens=[used])
     oh = torch.empty(1, 4, 1, 32)
 
     def oracle():
-        kf, vf = _gather_kv(k, v, world)
+        n = sess.kv_len_host[0]
+        lens = [None] * world
+        dist.all_gather_object(lens, n)
+        ks, vs = [None] * world, [None] * world
+        dist.all_gather_object(ks, k)
+        dist.all_gather_object(vs, v)
+        kf = torch.cat([ks[r][:, :, : lens[r]] for r in range(world)], 2)
+        vf = torch.cat([vs[r][:, :, : lens[r]] for r in range(world)], 2)
         return ref.attention_ref(q, kf, vf, softmax_scale=0.2)[0]
 
     out0 = sess.step(q, oh, 0).clone()
     assert torch.allclose(out0.double(), oracle(), atol=1e-5)
     g = torch.Generator().manual_seed(7)
     k_new, v_new = torch.randn(1, 2, 1, 32, generator=g) * 3, torch.randn(1, 2, 1, 32, generator=g) * 3
-    if rank == world - 1:                      # the owner of the new position appends
-        sess.append_kv(0, k_new, v_new, used)
+    if rank == world - 1:                      # the owner of the new position appends at its fill level
+        sess.append_kv(0, k_new, v_new)
+        assert sess.kv_len_host[0] == used + 1
     out1 = sess.step(q, oh, 0).clone()
     assert torch.allclose(out1.double(), oracle(), atol=1e-5)
     assert (out1 - out0).abs().max() > 1e-6
+
+
+def _worker_kv_len(rank, world):
+    """tree_attention(kv_len=...): ragged fill levels, including an EMPTY shard, on every collective schedule."""
+    import tree_attention_b200 as ta
+    from tree_attention_b200.ops import reference as ref
+
+    cap = 64
+    lens = [cap, 17, 0, 40][:world]
+    q, k, v = ta.make_data((2, 4, cap, 32), rank, "cpu", dtype=torch.float32, num_kv_heads=2, log=False)
+    k[:, :, lens[rank]:] = float("nan")        # unwritten rows hold anything
+    v[:, :, lens[rank]:] = float("nan")
+    ks, vs = [None] * world, [None] * world
+    dist.all_gather_object(ks, k)
+    dist.all_gather_object(vs, v)
+    kf = torch.cat([ks[r][:, :, : lens[r]] for r in range(world)], 2)
+    vf = torch.cat([vs[r][:, :, : lens[r]] for r in range(world)], 2)
+    o_ref, l_ref = ref.attention_ref(q, kf, vf, softmax_scale=0.3)
+    for sched in ("allgather", "allreduce3", "butterfly"):
+        o, l = ta.tree_attention(q, k, v, softmax_scale=0.3, backend="gloo", schedule=sched, return_lse=True,
+                                 kv_len=lens[rank])
+        assert torch.allclose(o.double(), o_ref, atol=1e-5), sched
+        assert torch.allclose(l.double(), l_ref, atol=1e-5), sched
+
+
+def test_kv_len_ragged_gloo(port):
+    run_distributed(_worker_kv_len, 4, port)
 
 
 def test_decode_session_gloo(port):

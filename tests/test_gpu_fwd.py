@@ -39,7 +39,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [1, 6])
 @pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
 def test_fwd_matches_oracle(case, variant):
     b, hq, hkv, sq, s, d, dtype, causal, q_pos0, kv_pos0, bshd = case

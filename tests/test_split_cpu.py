@@ -1,4 +1,5 @@
-"""The decode kernels' stream-K split (host code in csrc/decode_tc_sm100.cu, shared by all three decode kernels):
+"""The decode kernels' stream-K split (``decode_split`` in csrc/decode_simt.cu, shared by all three decode kernels; the
+device side is ``dcomm::make_geom`` in csrc/decode_comm.cuh):
 every 128-key tile is owned by exactly one CTA, CTA loads differ by at most one tile, and ``max_parts`` -- which sizes the
 split-merge workspace -- really bounds the number of CTAs that touch one KV head (a violation would be a buffer overflow
 in the kernel).  Pure host code: runs without a GPU."""
@@ -35,3 +36,23 @@ def test_split_covers_every_tile_once_and_max_parts_bounds_sharing(b, hkv, s, nc
         last = next(c for c in range(grid - 1, -1, -1) if lo[c] < (x + 1) * tph)
         worst = max(worst, last - first + 1)
     assert worst <= max_parts, (worst, max_parts, b, hkv, s, ncta)
+
+
+@settings(max_examples=200, deadline=None)
+@given(b=st.integers(1, 3), hkv=st.integers(1, 40), cap=st.integers(1, 40_000), frac=st.floats(0.0, 1.0),
+       ncta=st.sampled_from([4, 132, 148]))
+def test_max_parts_bounds_sharing_for_every_fill_level(b, hkv, cap, frac, ncta):
+    """The kernels re-derive the split on the device from the run-time fill level ``kv_len <= capacity`` but keep the grid
+    and the workspace sized for the capacity: ``max_parts`` must bound the CTAs per head for EVERY fill level (an empty
+    shard still runs one masked tile per head)."""
+    C = _build.load()
+    grid, max_parts = C.decode_split_for(b, hkv, cap, ncta)
+    s_eff = int(cap * frac)
+    tph = max(1, (s_eff + 127) // 128)
+    total = b * hkv * tph
+    lo = _ranges(total, grid)                    # dcomm::cta_lo with tiles_q = total // grid (possibly 0)
+    assert lo[-1] == total
+    for x in range(b * hkv):
+        owners = [c for c in range(grid) if lo[c + 1] > x * tph and lo[c] < (x + 1) * tph]
+        assert owners and owners == list(range(owners[0], owners[-1] + 1))
+        assert len(owners) <= max_parts, (len(owners), max_parts, b, hkv, cap, s_eff, ncta)

@@ -25,7 +25,7 @@ BUILD_DIR = CSRC / "build"
 SO_PATH = BUILD_DIR / "_C.so"
 HASH_PATH = BUILD_DIR / "_C.hash"
 
-CUDA_SOURCES = ["decode_simt.cu", "decode_tc_sm100.cu", "decode_swap_sm100.cu", "combine.cu", "umma_probe.cu", "attn_fwd_sm100.cu", "attn_fwd2_sm100.cu", "attn_fwd3_sm100.cu", "attn_fwd4_sm100.cu", "attn_fwd5_sm100.cu", "attn_fwd7_sm100.cu", "attn_bwd_sm100.cu",
+CUDA_SOURCES = ["decode_simt.cu", "decode_tc_sm100.cu", "decode_swap_sm100.cu", "combine.cu", "umma_probe.cu", "attn_fwd_sm100.cu", "attn_fwd7_sm100.cu", "attn_bwd_sm100.cu",
                 "quant.cu", "reduce.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 NVCC_FLAGS = [
@@ -101,6 +101,12 @@ def load(required: bool = True) -> Optional[ModuleType]:
     have_so = SO_PATH.exists()
     fresh = have_so and HASH_PATH.exists() and HASH_PATH.read_text().strip() == source_hash()
     if have_so and (fresh or shutil.which("nvcc") is None or os.environ.get("TREE_ATTN_NO_REBUILD")):
+        if not fresh:
+            import warnings
+
+            warnings.warn(
+                f"{SO_PATH} was built from different sources than the ones in {CSRC} and cannot be rebuilt here "
+                "(nvcc missing or TREE_ATTN_NO_REBUILD set): loading the STALE binary", RuntimeWarning, stacklevel=2)
         _module = _import_so()
         return _module
     if shutil.which("nvcc") is not None:

@@ -97,6 +97,14 @@ AttnShape make_shape(const at::Tensor& q, const at::Tensor& k, const at::Tensor&
   return s;
 }
 
+// optional device scalar with the number of valid KV rows (int32, 1 element); nullptr when absent
+const int* kv_len_ptr(const c10::optional<at::Tensor>& kv_len, const at::Tensor& like) {
+  if (!kv_len.has_value()) return nullptr;
+  TORCH_CHECK(kv_len->is_cuda() && kv_len->device() == like.device() && kv_len->scalar_type() == at::kInt && kv_len->numel() == 1,
+              "kv_len must be a 1-element int32 CUDA tensor on the KV cache's device");
+  return kv_len->data_ptr<int>();
+}
+
 py::tuple decode_plan(int B, int Hq, int Hkv, int Sq, int S, int D) {
   AttnShape s;
   s.B = B; s.Hq = Hq; s.Hkv = Hkv; s.Sq = Sq; s.S = S; s.D = D;
@@ -108,7 +116,7 @@ py::tuple decode_plan(int B, int Hq, int Hkv, int Sq, int S, int D) {
 
 void decode_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out,
                 c10::optional<at::Tensor> lse, at::Tensor& part, at::Tensor& tickets, py::object comm, double scale,
-                bool causal, int64_t q_pos0, int64_t kv_pos0, int pdl) {
+                bool causal, int64_t q_pos0, int64_t kv_pos0, int pdl, c10::optional<at::Tensor> kv_len) {
   c10::cuda::CUDAGuard guard(q.device());
   AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
   TORCH_CHECK(part.scalar_type() == at::kFloat && part.is_contiguous(), "part must be contiguous fp32");
@@ -127,7 +135,7 @@ void decode_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, a
   if (!comm.is_none()) c = comm.cast<Comm&>().h;
   ta::decode_simt_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
                          reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(),
-                         at::cuda::getCurrentCUDAStream(), nullptr, nullptr, pdl);
+                         at::cuda::getCurrentCUDAStream(), nullptr, nullptr, pdl, kv_len_ptr(kv_len, k));
 }
 
 py::tuple attn_fwd_comm_bytes(int B, int Hq, int Sq, int D, int world) {
@@ -146,23 +154,12 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at:
               "lse must be contiguous fp32 (B, Hq, Sq)");
   CommCtxHost c;
   if (!comm.is_none()) c = comm.cast<Comm&>().h;
-  // variant 0 = auto = 1: the M=128 kernel with double-buffered S.  The M=256 ping-pong kernel (variant 2) is kept
-  // selectable; it measured slower on B200 (single-buffered S per tile exposes softmax + 2 GEMMs per step).
-  const bool use2 = variant == 2;
-  if (variant == 7)   // EXPERIMENTAL 2-CTA forward: compile-checked only (docs/NEXT.md)
+  // variant 0 / 1: the M = 128 kernel with double-buffered S; 6: the same kernel with the query tile kept in TMEM;
+  // 7: EXPERIMENTAL 2-CTA kernel (csrc/attn_fwd7_sm100.cu).  The M = 256 / split-softmax pipelines of round 1
+  // (variants 2-5) measured within +-4 % of variant 1 and were removed (DESIGN.md section 5b keeps the numbers).
+  TORCH_CHECK(variant == 0 || variant == 1 || variant == 6 || variant == 7, "attn_fwd: unknown variant ", variant);
+  if (variant == 7)
     ta::attn_fwd7_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
-                         at::cuda::getCurrentCUDAStream());
-  else if (variant == 5)
-    ta::attn_fwd5_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
-                         at::cuda::getCurrentCUDAStream());
-  else if (variant == 4)
-    ta::attn_fwd4_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
-                         at::cuda::getCurrentCUDAStream());
-  else if (variant == 3)
-    ta::attn_fwd3_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
-                         at::cuda::getCurrentCUDAStream());
-  else if (use2)
-    ta::attn_fwd2_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
                          at::cuda::getCurrentCUDAStream());
   else
     ta::attn_fwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
@@ -180,7 +177,7 @@ py::tuple decode_tc_plan(int B, int Hq, int Hkv, int Sq, int S, int D) {
 
 void decode_tc_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out,
                    c10::optional<at::Tensor> lse, at::Tensor& part, at::Tensor& tickets, py::object comm, double scale,
-                   bool causal, int64_t q_pos0, int64_t kv_pos0, bool swap) {
+                   bool causal, int64_t q_pos0, int64_t kv_pos0, bool swap, c10::optional<at::Tensor> kv_len) {
   c10::cuda::CUDAGuard guard(q.device());
   AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
   TORCH_CHECK(part.scalar_type() == at::kFloat && part.is_contiguous(), "part must be contiguous fp32");
@@ -199,10 +196,12 @@ void decode_tc_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
   if (!comm.is_none()) c = comm.cast<Comm&>().h;
   if (swap)
     ta::decode_swap_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
-                           reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream());
+                           reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream(),
+                           nullptr, nullptr, nullptr, nullptr, kv_len_ptr(kv_len, k));
   else
     ta::decode_tc_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
-                         reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream());
+                         reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream(),
+                         nullptr, nullptr, kv_len_ptr(kv_len, k));
 }
 
 // block-scaled (MX) fp8 KV cache on the tensor cores (tcgen05.mma.kind::mxf8f6f4.block_scale, swap-AB decode kernel):
@@ -210,7 +209,8 @@ void decode_tc_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v
 //   v_sf uint8 (B, Hkv, ceil(S / 128), 128, 4): V's UE8M0 scales per 32 KEYS, grouped per 128-key tile and channel.
 void decode_mx_tc_fwd(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& k_sf,
                       const at::Tensor& v_sf, at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part,
-                      at::Tensor& tickets, py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
+                      at::Tensor& tickets, py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0,
+                      c10::optional<at::Tensor> kv_len) {
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(q.dim() == 4 && k8.dim() == 4 && v8.dim() == 4 && out.sizes() == q.sizes(), "expected (B, H, S, D) tensors");
   TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
@@ -242,14 +242,14 @@ void decode_mx_tc_fwd(const at::Tensor& q, const at::Tensor& k8, const at::Tenso
   ta::decode_swap_launch(s, q.data_ptr(), k8.data_ptr(), v8.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
                          reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream(),
                          nullptr, nullptr, reinterpret_cast<const uint32_t*>(k_sf.data_ptr()),
-                         reinterpret_cast<const uint32_t*>(v_sf.data_ptr()));
+                         reinterpret_cast<const uint32_t*>(v_sf.data_ptr()), kv_len_ptr(kv_len, k8));
 }
 
 // per-channel-scaled fp8 KV cache on the tensor cores: k8/v8 uint8 (B, Hkv, S, 128) e4m3, ksc/vsc fp32 (B, Hkv, 128)
 void decode_tc_fwd8(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& ksc,
                     const at::Tensor& vsc, at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part,
                     at::Tensor& tickets, py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0,
-                    bool swap) {
+                    bool swap, c10::optional<at::Tensor> kv_len) {
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(q.dim() == 4 && k8.dim() == 4 && v8.dim() == 4 && out.sizes() == q.sizes(), "expected (B, H, S, D) tensors");
   TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
@@ -278,17 +278,18 @@ void decode_tc_fwd8(const at::Tensor& q, const at::Tensor& k8, const at::Tensor&
   if (swap)
     ta::decode_swap_launch(s, q.data_ptr(), k8.data_ptr(), v8.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
                            reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream(),
-                           ksc.data_ptr<float>(), vsc.data_ptr<float>());
+                           ksc.data_ptr<float>(), vsc.data_ptr<float>(), nullptr, nullptr, kv_len_ptr(kv_len, k8));
   else
     ta::decode_tc_launch(s, q.data_ptr(), k8.data_ptr(), v8.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
                          reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(), at::cuda::getCurrentCUDAStream(),
-                         ksc.data_ptr<float>(), vsc.data_ptr<float>());
+                         ksc.data_ptr<float>(), vsc.data_ptr<float>(), kv_len_ptr(kv_len, k8));
 }
 
 // block-scaled fp8 KV cache decode: k8/v8 uint8 (B, Hkv, S, 128) e4m3, ks/vs uint8 (B, Hkv, S, 4) UE8M0
 void decode_fwd_mx(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& v8, const at::Tensor& ks,
                    const at::Tensor& vs, at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part,
-                   at::Tensor& tickets, py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
+                   at::Tensor& tickets, py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0,
+                   c10::optional<at::Tensor> kv_len) {
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(q.dim() == 4 && k8.dim() == 4 && v8.dim() == 4 && out.sizes() == q.sizes(), "expected (B, H, S, D) tensors");
   TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
@@ -316,7 +317,84 @@ void decode_fwd_mx(const at::Tensor& q, const at::Tensor& k8, const at::Tensor& 
   ta::decode_simt_launch(s, q.data_ptr(), k8.data_ptr(), v8.data_ptr(), out.data_ptr(), lse_p, part.data_ptr<float>(),
                          reinterpret_cast<uint32_t*>(tickets.data_ptr<int>()), c, ta::num_sms(),
                          at::cuda::getCurrentCUDAStream(), reinterpret_cast<const uint32_t*>(ks.data_ptr()),
-                         reinterpret_cast<const uint32_t*>(vs.data_ptr()));
+                         reinterpret_cast<const uint32_t*>(vs.data_ptr()), 0, kv_len_ptr(kv_len, k8));
+}
+
+// ---------------------------------------------------------------------------------------------
+// DecodeStep: a decode-attention step prepared ONCE (tensor maps encoded, parameter block filled, workspace and
+// symmetric region bound) and re-launched with a single runtime call -- the host path of a serving loop.  It holds
+// references to every tensor the kernel touches, so the memory a captured CUDA graph or an in-flight launch points
+// at cannot be freed or re-used while the step object is alive (workspace / region lifetime).
+// ---------------------------------------------------------------------------------------------
+struct DecodeStep {
+  ta::PreparedLaunch launches[3];   // indexed by pdl level (0 plain, 1 dependent launch, 2 + K/V prefetch)
+  bool has[3] = {false, false, false};
+  std::vector<at::Tensor> keep;
+  py::object comm_keep;
+  c10::Device device;
+  int kernels_per_step = 1;
+  std::string impl;
+
+  explicit DecodeStep(c10::Device d) : device(d) {}
+
+  void launch(int pdl) {
+    c10::cuda::CUDAGuard guard(device);
+    if (pdl < 0 || pdl > 2 || !has[pdl]) pdl = 0;
+    launches[pdl].run(at::cuda::getCurrentCUDAStream());
+  }
+};
+
+std::shared_ptr<DecodeStep> decode_step(const std::string& impl, const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
+                                        at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part, at::Tensor& tickets,
+                                        py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0,
+                                        c10::optional<at::Tensor> kv_len) {
+  c10::cuda::CUDAGuard guard(q.device());
+  AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
+  TORCH_CHECK(part.scalar_type() == at::kFloat && part.is_contiguous(), "part must be contiguous fp32");
+  TORCH_CHECK(tickets.scalar_type() == at::kInt && tickets.numel() >= s.B * s.Hkv + 2, "tickets too small");
+  float* lse_p = nullptr;
+  if (lse.has_value()) {
+    TORCH_CHECK(lse->scalar_type() == at::kFloat && lse->is_contiguous() && lse->numel() == (int64_t)s.B * s.Hq * s.Sq,
+                "lse must be contiguous fp32 (B, Hq, Sq)");
+    lse_p = lse->data_ptr<float>();
+  }
+  CommCtxHost c;
+  if (!comm.is_none()) c = comm.cast<Comm&>().h;
+  auto st = std::make_shared<DecodeStep>(q.device());
+  st->impl = impl;
+  st->comm_keep = comm;
+  st->keep = {q, k, v, out, part, tickets};
+  if (lse.has_value()) st->keep.push_back(*lse);
+  if (kv_len.has_value()) st->keep.push_back(*kv_len);
+  const int* kvl = kv_len_ptr(kv_len, k);
+  uint32_t* tk = reinterpret_cast<uint32_t*>(tickets.data_ptr<int>());
+  if (impl == "simt") {
+    int grid, mp, R;
+    size_t pf, cf, cfl;
+    ta::decode_simt_plan(s, ta::num_sms(), &grid, &mp, &R, &pf, &cf, &cfl);
+    TORCH_CHECK((size_t)part.numel() >= pf, "part workspace too small: need ", pf, " floats");
+    for (int pdl = 0; pdl < 3; ++pdl) {
+      st->launches[pdl] = ta::decode_simt_prepare(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p,
+                                                  part.data_ptr<float>(), tk, c, ta::num_sms(), nullptr, nullptr, pdl, kvl);
+      st->has[pdl] = true;
+    }
+    st->kernels_per_step = (int)st->launches[0].passes.size();
+  } else if (impl == "swap" || impl == "tc") {
+    int grid, mp, R;
+    size_t pf, cb;
+    ta::decode_tc_plan(s, ta::num_sms(), &grid, &mp, &R, &pf, &cb);
+    TORCH_CHECK((size_t)part.numel() >= pf, "part workspace too small: need ", pf, " floats");
+    TORCH_CHECK(q.stride(2) % 8 == 0 || q.size(2) == 1, "q rows must be 16-byte aligned");
+    st->launches[0] = impl == "swap"
+                          ? ta::decode_swap_prepare(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p,
+                                                    part.data_ptr<float>(), tk, c, ta::num_sms(), nullptr, nullptr, nullptr, nullptr, kvl)
+                          : ta::decode_tc_prepare(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p,
+                                                  part.data_ptr<float>(), tk, c, ta::num_sms(), nullptr, nullptr, kvl);
+    st->has[0] = true;
+  } else {
+    TORCH_CHECK(false, "decode_step: impl must be 'simt', 'swap' or 'tc'");
+  }
+  return st;
 }
 
 py::tuple quant_mxfp8(const at::Tensor& x) {
@@ -452,12 +530,29 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_property_readonly("rank", [](Comm& c) { return c.h.rank; })
       .def_property_readonly("world", [](Comm& c) { return c.h.world; });
   m.def("decode_plan", &decode_plan);
-  m.def("decode_fwd", &decode_fwd);
-  m.def("decode_fwd_mx", &decode_fwd_mx);
+  m.def("decode_fwd", &decode_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("lse"), py::arg("part"),
+        py::arg("tickets"), py::arg("comm"), py::arg("scale"), py::arg("causal"), py::arg("q_pos0"), py::arg("kv_pos0"),
+        py::arg("pdl") = 0, py::arg("kv_len") = py::none());
+  m.def("decode_fwd_mx", &decode_fwd_mx, py::arg("q"), py::arg("k8"), py::arg("v8"), py::arg("ks"), py::arg("vs"), py::arg("out"),
+        py::arg("lse"), py::arg("part"), py::arg("tickets"), py::arg("comm"), py::arg("scale"), py::arg("causal"),
+        py::arg("q_pos0"), py::arg("kv_pos0"), py::arg("kv_len") = py::none());
   m.def("decode_tc_plan", &decode_tc_plan);
-  m.def("decode_tc_fwd", &decode_tc_fwd);
-  m.def("decode_tc_fwd8", &decode_tc_fwd8);
-  m.def("decode_mx_tc_fwd", &decode_mx_tc_fwd);
+  m.def("decode_tc_fwd", &decode_tc_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("lse"), py::arg("part"),
+        py::arg("tickets"), py::arg("comm"), py::arg("scale"), py::arg("causal"), py::arg("q_pos0"), py::arg("kv_pos0"),
+        py::arg("swap"), py::arg("kv_len") = py::none());
+  m.def("decode_tc_fwd8", &decode_tc_fwd8, py::arg("q"), py::arg("k8"), py::arg("v8"), py::arg("ksc"), py::arg("vsc"), py::arg("out"),
+        py::arg("lse"), py::arg("part"), py::arg("tickets"), py::arg("comm"), py::arg("scale"), py::arg("causal"),
+        py::arg("q_pos0"), py::arg("kv_pos0"), py::arg("swap"), py::arg("kv_len") = py::none());
+  m.def("decode_mx_tc_fwd", &decode_mx_tc_fwd, py::arg("q"), py::arg("k8"), py::arg("v8"), py::arg("k_sf"), py::arg("v_sf"),
+        py::arg("out"), py::arg("lse"), py::arg("part"), py::arg("tickets"), py::arg("comm"), py::arg("scale"), py::arg("causal"),
+        py::arg("q_pos0"), py::arg("kv_pos0"), py::arg("kv_len") = py::none());
+  py::class_<DecodeStep, std::shared_ptr<DecodeStep>>(m, "DecodeStep")
+      .def("launch", &DecodeStep::launch, py::arg("pdl") = 0)
+      .def_readonly("kernels_per_step", &DecodeStep::kernels_per_step)
+      .def_readonly("impl", &DecodeStep::impl);
+  m.def("decode_step", &decode_step, py::arg("impl"), py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("lse"),
+        py::arg("part"), py::arg("tickets"), py::arg("comm"), py::arg("scale"), py::arg("causal"), py::arg("q_pos0"),
+        py::arg("kv_pos0"), py::arg("kv_len") = py::none());
   m.def("quant_mxfp8", &quant_mxfp8);
   m.def("quant_mxfp8_seq", &quant_mxfp8_seq);
   m.def("dequant_mxfp8", &dequant_mxfp8);
@@ -485,7 +580,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     AttnShape s{};
     s.B = B; s.Hkv = Hkv; s.Hq = Hkv; s.Sq = 1; s.S = S; s.D = 128;
     int g = 0, mp = 0;
-    ta::decode_tc_split(s, ncta, &g, &mp);
+    ta::decode_split(B * Hkv, S, ncta, &g, &mp);
     return py::make_tuple(g, mp);
   });
   m.def("tmem_ld_bw_probe", [](int warps, int iters) { return ta::tmem_ld_bw_probe(warps, iters, at::cuda::getCurrentCUDAStream()); });

@@ -16,6 +16,7 @@
 // The math is CUDA-core (decode is a GEMV per head: ~1 FMA per byte of KV, HBM bound).  Query rows
 // R = (GQA group) x Sq <= 4 per pass; larger Sq goes to the tcgen05 kernel (attn_fwd_sm100.cu).
 #include "common.cuh"
+#include "decode_comm.cuh"
 #include "host_utils.h"
 #include "kernels.h"
 
@@ -38,17 +39,15 @@ struct DecodeParams {
   const uint32_t* vscale;
   float* part;
   uint32_t* tickets;  // [BH] tickets, [BH] = done-CTA counter
-  int B, Hq, Hkv, G, Sq, S;
+  const int* kv_len;  // optional device scalar: valid rows of this shard (<= S); read by the kernel => graph-replayable
+  int B, Hq, Hkv, G, Sq, S;   // S = capacity of the shard (rows covered by the tensor maps)
   int rows_valid;     // G * Sq - r_base, clipped to R
   int r_base;
   float scale_log2;
   int causal;
   long long q_pos0, kv_pos0;
   long long q_sb, q_sh, q_ss, o_sb, o_sh, o_ss;
-  int tph;            // tiles per head
-  int total_tiles;
-  int tiles_q, tiles_rem;  // stream-K split: first `rem` CTAs get q+1 tiles
-  int max_parts;
+  int max_parts;      // bound on the CTAs sharing one head, for ANY number of valid rows (decode_simt_plan)
   int pdl;  // 0: plain launch; 1: programmatic dependent launch; 2: + K/V prefetch before the dependency wait (static KV)
   CommCtx comm;
 };
@@ -69,15 +68,7 @@ constexpr size_t smem_bytes() {
   using L = SmemLayout<D, KV8>;
   return 1024 /*align slack*/ + size_t(L::kStages) * L::kStageBytes +
          sizeof(float) * (R * D + kConsumerWarps * L::kPsPerWarp * R * kRowsPerWarp + kConsumerWarps * R * (D + 4)) +
-         sizeof(int) * (kMaxPending + 8) + sizeof(uint64_t) * 2 * L::kStages;
-}
-
-__device__ __forceinline__ int cta_lo(const DecodeParams& p, int c) {
-  return c * p.tiles_q + min(c, p.tiles_rem);
-}
-__device__ __forceinline__ int cta_of_tile(const DecodeParams& p, int t) {
-  const int big = p.tiles_rem * (p.tiles_q + 1);
-  return t < big ? t / (p.tiles_q + 1) : p.tiles_rem + (t - big) / p.tiles_q;
+         sizeof(int) * (kMaxPending + 8) + sizeof(uint64_t) * (2 * L::kStages + 2);
 }
 
 template <bool BF16>
@@ -106,7 +97,7 @@ __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); 
 template <int D, int R, bool BF16, bool KV8>
 __global__ void __launch_bounds__(kThreads, 1)
 decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
-                   const DecodeParams p) {
+                   const __grid_constant__ DecodeParams p) {
   using L = SmemLayout<D, KV8>;
   constexpr int NS = L::kStages;
   constexpr int EPL = D / 32;  // output elements per lane in the PV phase
@@ -117,16 +108,15 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   float* p_s = q_s + R * D;                                                    // [warps][(blk)][R][16]
   float* merge_s = p_s + kConsumerWarps * L::kPsPerWarp * R * kRowsPerWarp;    // [warps][R][D+4]
   int* pending = reinterpret_cast<int*>(merge_s + kConsumerWarps * R * (D + 4));
-  int* s_misc = pending + kMaxPending;  // [0]=ticket, [1]=n_pending, [2]=combine ok
+  int* s_misc = pending + kMaxPending;  // [0]=ticket, [1]=n_pending, [2]=head+1 to combine inline
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_misc + 8);
   uint64_t* empty_bar = full_bar + NS;
+  uint64_t* stamps = empty_bar + NS;   // [0] CTA start, [1] last publish (globaltimer, thread 0)
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
   const int cta = blockIdx.x;
-  const int t_lo = cta_lo(p, cta);
-  const int t_hi = cta_lo(p, cta + 1);
   const int world = p.comm.world;
 
   if (tid == 0) {
@@ -135,7 +125,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       mbar_init(&empty_bar[i], kConsumerWarps);
     }
     fence_mbar_init();
-    s_misc[1] = 0;
+    s_misc[1] = 0; s_misc[2] = 0;
   }
   if (warp == kConsumerWarps && lane == 0) {
     tma_prefetch_desc(&kmap);
@@ -158,11 +148,15 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   if (warp == kConsumerWarps) {
     // ------------------------------- TMA producer --------------------------------------------
     if (lane == 0) {
+      // pdl == 2 streams K/V (and reads kv_len) BEFORE the dependency wait: only valid when neither was written by
+      // the kernel this launch depends on (the session downgrades to pdl = 1 for the step after an append)
       if (p.pdl == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
+      const dcomm::Geom geo = dcomm::make_geom(p.S, p.kv_len, BH, gridDim.x);
+      const int t_lo = dcomm::cta_lo(geo, cta), t_hi = dcomm::cta_lo(geo, cta + 1);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_lo; t < t_hi; ++t) {
-        const int x = t / p.tph, j = t - x * p.tph;
+        const int x = t / geo.tph, j = t - x * geo.tph;
         if (!tile_visible(j)) continue;
         const int b = x / p.Hkv, h = x - b * p.Hkv;
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -187,8 +181,18 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   // has completed (griddepcontrol.wait above).
   uint32_t epoch = 0;
   if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
-  const uint64_t t_cta0 = globaltimer_ns();
-  const int parity = epoch & 1;
+  const dcomm::Geom geo = dcomm::make_geom(p.S, p.kv_len, BH, gridDim.x);
+  const int t_lo = dcomm::cta_lo(geo, cta), t_hi = dcomm::cta_lo(geo, cta + 1);
+  constexpr int RB = R;  // rows of one output channel gathered per batch of the cross-GPU merge (R <= 4)
+  if (tid == 0) { stamps[0] = globaltimer_ns(); stamps[1] = 0; }
+  // built on demand (kept out of the streaming loop's live registers)
+  auto make_tail = [&]() {
+    dcomm::Tail tl;
+    tl.comm = &p.comm; tl.part = p.part; tl.tickets = p.tickets; tl.max_parts = p.max_parts; tl.BH = BH;
+    tl.R = R; tl.rows_valid = p.rows_valid; tl.epoch = epoch; tl.parity = epoch & 1;
+    tl.s_misc = s_misc; tl.pending = pending; tl.max_pending = kMaxPending; tl.stamps = stamps;
+    return tl;
+  };
   const int r16 = lane & 15;
   const int half = lane >> 4;
   float m_run[R], l_run[R], o_acc[R][EPL];
@@ -236,75 +240,8 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       p.lse[((long long)b * p.Hq + (h * p.G + g)) * p.Sq + i] = lse2 * 0.6931471805599453f;
   };
 
-  // ---- cross-GPU transport: NCCL-LL style words {fp32 value, epoch tag} (8-byte atomic granules).  Every word
-  // validates itself, so there is no separate flag, no fence and no second NVLink round trip: the combine
-  // costs one one-way store latency.  Slots are double-buffered by epoch parity.
-  auto word_ptr = [&](int dst, int src, int x) -> uint2* {
-    return reinterpret_cast<uint2*>(p.comm.data[dst]) + ((size_t)(parity * world + src) * BH + x) * (size_t)(R * (D + 2));
-  };
-  auto ll_store = [&](uint2* w, float v) {
-    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(w), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
-  };
-  auto ll_wait = [&](const uint2* w, bool& ok) -> float {
-    uint32_t v, tag;
-    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(w) : "memory");
-    if (tag != epoch) {
-      const uint64_t t0 = globaltimer_ns();
-      uint32_t it = 0;
-      do {
-        asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(w) : "memory");
-        if (tag == epoch) break;
-        if ((++it & 0x3fu) == 0 && globaltimer_ns() - t0 > p.comm.timeout_ns) { ok = false; break; }
-      } while (true);
-    }
-    return __uint_as_float(v);
-  };
-
-  // merge the W published partials of head x in rank order (each word is polled until its tag is this epoch)
-  uint64_t t_publish = 0;
-  auto combine_ranks = [&](int x) {
-    uint64_t t_got = 0;
-    for (int idx = tid; idx < p.rows_valid * D; idx += kConsumerThreads) {
-      const int r = idx / D, d = idx - r * D;
-      bool ok = true;
-      float lse_s[kMaxWorld];
-      float mx = neg_inf();
-      int bad_src = -1;
-      for (int s = 0; s < world; ++s) {
-        bool oks = true;
-        lse_s[s] = ll_wait(word_ptr(p.comm.rank, s, x) + r * (D + 2) + D, oks);
-        if (!oks) { ok = false; bad_src = s; }
-        mx = fmaxf(mx, lse_s[s]);
-      }
-      const float ms = (mx == neg_inf()) ? 0.f : mx;
-      float num = 0.f, den = 0.f;
-      for (int s = 0; s < world; ++s) {
-        bool oks = true;
-        const float val = ll_wait(word_ptr(p.comm.rank, s, x) + r * (D + 2) + d, oks);
-        if (!oks) { ok = false; bad_src = s; }
-        const float w = fast_exp2(lse_s[s] - ms);
-        num = fmaf(w, val, num);
-        den += w;
-      }
-      if (idx == 0) t_got = globaltimer_ns();
-      float o_norm = den > 0.f ? num / den : 0.f;
-      float lse2 = den > 0.f ? ms + fast_log2(den) : neg_inf();
-      if (!ok) {
-        o_norm = __int_as_float(0x7fc00000); lse2 = o_norm;
-        p.comm.status[0] = kCommTimeout; p.comm.status[1] = x; p.comm.status[2] = bad_src; p.comm.status[3] = epoch;
-      }
-      store_out(x, r, d, o_norm, lse2);
-    }
-    named_bar_sync(1, kConsumerThreads);
-    if (tid == 0 && t_publish != 0) {  // in-kernel stamps of the combine step
-      const uint64_t t_done = globaltimer_ns();
-      atomicMax(p.comm.status + 10, (uint32_t)min((unsigned long long)(t_got - t_publish), 0xffffffffull));
-      atomicMax(p.comm.status + 11, (uint32_t)min((unsigned long long)(t_done - t_publish), 0xffffffffull));
-      atomicMax(p.comm.status + 12, (uint32_t)min((unsigned long long)(t_publish - t_cta0), 0xffffffffull));
-    }
-  };
-
-  // per-CTA partial of head x is complete: merge warps, write partial, take a ticket, maybe finish the head
+  // per-CTA partial of head x is complete: merge warps, write the partial, then the shared tail (decode_comm.cuh):
+  // ticket -> last CTA merges the parts -> output (world == 1) or tagged 8-byte words to every rank + deferred merge
   auto finalize_segment = [&](int x) {
     // (a) warps -> smem
 #pragma unroll
@@ -321,8 +258,8 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     }
     named_bar_sync(1, kConsumerThreads);
     // (b) CTA partial -> global
-    const int first_cta = cta_of_tile(p, x * p.tph);
-    const int nparts = cta_of_tile(p, (x + 1) * p.tph - 1) - first_cta + 1;
+    const int first_cta = dcomm::cta_of_tile(geo, x * geo.tph);
+    const int nparts = dcomm::cta_of_tile(geo, (x + 1) * geo.tph - 1) - first_cta + 1;
     const int pidx = cta - first_cta;
     float* my_part = p.part + ((size_t)x * p.max_parts + pidx) * (size_t)(R * (D + 4));
     for (int idx = tid; idx < R * D; idx += kConsumerThreads) {
@@ -339,63 +276,12 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         acc = fmaf(ms[d], sc, acc);
         Lsum = fmaf(ms[D + 1], sc, Lsum);
       }
-      if (nparts == 1) {
-        // keep in smem-free registers: write straight to the part buffer anyway (uniform path)
-      }
       __stcg(my_part + r * (D + 4) + d, acc);
       if (d == 0) { __stcg(my_part + r * (D + 4) + D, M); __stcg(my_part + r * (D + 4) + D + 1, Lsum); }
     }
-    __threadfence();
-    named_bar_sync(1, kConsumerThreads);
-    if (tid == 0) s_misc[0] = (int)atomicAdd(&p.tickets[x], 1u);
-    named_bar_sync(1, kConsumerThreads);
-    const bool last = (s_misc[0] == nparts - 1);
-    if (!last) return;
-    __threadfence();
-    // (c) last arriver: merge all CTA partials of this head in part order (deterministic)
-    if (tid == 0) p.tickets[x] = 0;
-    const float* parts = p.part + (size_t)x * p.max_parts * (size_t)(R * (D + 4));
-    for (int idx = tid; idx < p.rows_valid * D; idx += kConsumerThreads) {
-      const int r = idx / D, d = idx - r * D;
-      float M = neg_inf();
-      for (int q = 0; q < nparts; ++q) M = fmaxf(M, __ldcg(parts + (size_t)q * (R * (D + 4)) + r * (D + 4) + D));
-      const float Ms = (M == neg_inf()) ? 0.f : M;
-      float acc = 0.f, Lsum = 0.f;
-      for (int q = 0; q < nparts; ++q) {
-        const float* pp = parts + (size_t)q * (R * (D + 4)) + r * (D + 4);
-        const float sc = fast_exp2(__ldcg(pp + D) - Ms);
-        acc = fmaf(__ldcg(pp + d), sc, acc);
-        Lsum = fmaf(__ldcg(pp + D + 1), sc, Lsum);
-      }
-      const float o_norm = Lsum > 0.f ? acc / Lsum : 0.f;
-      const float lse2 = Lsum > 0.f ? Ms + fast_log2(Lsum) : neg_inf();
-      if (world == 1) {
-        store_out(x, r, d, o_norm, lse2);
-      } else if (!p.comm.skip_publish) {
-        // (d) publish to every rank's slot [parity][my rank][x] (own slot included): tagged 8-byte words
-        for (int dst = 0; dst < world; ++dst) {
-          uint2* wp = word_ptr(dst, p.comm.rank, x) + r * (D + 2);
-          ll_store(wp + d, o_norm);
-          if (d == 0) ll_store(wp + D, lse2);
-        }
-      }
-    }
-    if (world > 1) {
-      if (tid == 0) {
-        t_publish = globaltimer_ns();
-        const int n = s_misc[1];
-        if (n < kMaxPending) { pending[n] = x; s_misc[1] = n + 1; }
-        else s_misc[3] = x + 1;  // list full: combine inline below
-      }
-      named_bar_sync(1, kConsumerThreads);
-      if (s_misc[3] != 0) {
-        if (tid == 0) s_misc[3] = 0;
-        combine_ranks(x);
-      }
-    }
+    const dcomm::Tail tail = make_tail();
+    dcomm::finish_head<D, kConsumerThreads, RB>(tail, x, nparts, tid, 1, store_out);
   };
-
-  if (tid == 0) { s_misc[2] = 1; s_misc[3] = 0; }
 
   // KV8: the block scales of the NEXT tile are prefetched into registers one iteration ahead, so that their
   // global-load latency hides behind the current tile's math and the mbarrier wait.
@@ -403,7 +289,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   [[maybe_unused]] auto fetch_scales = [&](int tt) {
     if constexpr (KV8) {
       if (tt < t_hi) {
-        const int xx = tt / p.tph, jj = tt - xx * p.tph;
+        const int xx = tt / geo.tph, jj = tt - xx * geo.tph;
         const long long srow = (long long)xx * p.S + min((long long)jj * kTileRows + warp * kRowsPerWarp + (lane & 15), (long long)p.S - 1);
         nxt_ksc = __ldg(p.kscale + srow);
         nxt_vsc = __ldg(p.vscale + srow);
@@ -413,7 +299,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   fetch_scales(t_lo);
 
   for (int t = t_lo; t < t_hi; ++t) {
-    const int x = t / p.tph, j = t - x * p.tph;
+    const int x = t / geo.tph, j = t - x * geo.tph;
     [[maybe_unused]] const uint32_t ksc_word = nxt_ksc;
     [[maybe_unused]] const uint32_t vsc_cur = nxt_vsc;
     fetch_scales(t + 1);
@@ -494,7 +380,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       }
     }
     const long long grow = (long long)j * kTileRows + row;
-    const bool inb = grow < p.S;
+    const bool inb = grow < geo.S;
     const long long kvpos = p.kv_pos0 + grow;
     float alpha[R];
 #pragma unroll
@@ -529,6 +415,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     __syncwarp();
 
     // ---------------- O += P . V : lane = EPL consecutive output columns ---------------------------
+    const int nv = geo.S - (j * kTileRows + warp * kRowsPerWarp);   // valid rows of this warp's 16 (>= 16: all)
     if constexpr (KV8) {
       // fp8: 4 output columns = 4 bytes; the P x scale coefficients of this lane's block come from smem
       const int blk = lane >> 3;
@@ -541,6 +428,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
           pr[r] = *reinterpret_cast<const float4*>(p_s + ((warp * 4 + blk) * R + r) * kRowsPerWarp + jj);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
+          if (jj + u >= nv) continue;   // rows past the valid length may hold anything (0 x NaN): skip, never multiply
           const int vrow = warp * kRowsPerWarp + jj + u;
           const uint32_t w = *reinterpret_cast<const uint32_t*>(vs + vrow * 128 + ((chunk ^ (vrow & 7)) << 4) + off);
           uint32_t h0, h1;
@@ -573,6 +461,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
           pr[r] = *reinterpret_cast<const float4*>(p_s + (warp * R + r) * kRowsPerWarp + jj);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
+          if (jj + u >= nv) continue;   // rows past the valid length may hold anything (0 x NaN): skip, never multiply
           const int vrow = warp * kRowsPerWarp + jj + u;
           const uint8_t* vp = vb + vrow * 128 + ((chunk ^ (vrow & 7)) << 4);
           float vf[EPL];
@@ -600,42 +489,13 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   }
   if (cur_x >= 0) finalize_segment(cur_x);
 
-  // ------------- deferred cross-GPU merges for the heads this CTA finished -----------------------
-  if (world > 1) {
-    named_bar_sync(1, kConsumerThreads);
-    const int n = s_misc[1];
-    for (int i = 0; i < n; ++i) combine_ranks(pending[i]);
-    // end-of-kernel arrival; the last CTA bumps the device-resident epoch for the next launch
-    if (tid == 0) {
-      __threadfence();
-      const uint32_t done = atomicAdd(&p.tickets[BH], 1u);
-      if (done == gridDim.x - 1) {
-        p.tickets[BH] = 0;
-        __threadfence();
-        *reinterpret_cast<volatile uint32_t*>(p.comm.epoch) = epoch;
-      }
-    }
-  }
-}
-
-inline CommCtx to_device_ctx(const CommCtxHost& h) {
-  CommCtx c;
-  c.rank = h.rank;
-  c.world = h.world;
-  for (int i = 0; i < kMaxWorld; ++i) {
-    c.data[i] = reinterpret_cast<float*>(h.data[i]);
-    c.flags[i] = reinterpret_cast<uint32_t*>(h.flags[i]);
-  }
-  c.epoch = reinterpret_cast<uint32_t*>(h.epoch);
-  c.status = reinterpret_cast<uint32_t*>(h.status);
-  c.timeout_ns = h.timeout_ns;
-  c.skip_publish = h.skip_publish;
-  return c;
+  // ------------- deferred cross-GPU merges for the heads this CTA finished, end-of-kernel arrival -----
+  const dcomm::Tail tail = make_tail();
+  dcomm::drain_and_exit<D, kConsumerThreads, RB>(tail, tid, 1, store_out);
 }
 
 template <int D, int R, bool BF16, bool KV8>
-void launch_one(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeParams& p, int grid,
-                cudaStream_t stream) {
+std::function<void(cudaStream_t)> make_pass(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeParams& p, int grid) {
   auto kern = decode_simt_kernel<D, R, BF16, KV8>;
   constexpr size_t smem = smem_bytes<D, R, KV8>();
   static bool configured = false;
@@ -643,54 +503,57 @@ void launch_one(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodePa
     TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  if (p.pdl) {
+  // the tensor maps and the parameter block are captured BY VALUE: a prepared pass re-launches with one runtime call
+  return [kern, kmap, vmap, p, grid](cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = smem_bytes<D, R, KV8>();
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = p.pdl ? 1 : 0;
     TA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, kmap, vmap, p));
-  } else {
-    kern<<<grid, kThreads, smem, stream>>>(kmap, vmap, p);
-  }
-  TA_CUDA_CHECK(cudaGetLastError());
+  };
 }
 
 int pick_rows(int total_rows) { return total_rows >= 4 ? 4 : (total_rows >= 2 ? 2 : 1); }
 
 }  // namespace
 
+void decode_split(int BH, int cap, int ncta, int* grid, int* max_parts) {
+  const int tph = std::max(1, (cap + kTileRows - 1) / kTileRows);
+  const long long total = (long long)BH * tph;
+  const int g = (int)std::min<long long>(ncta, total);
+  // The kernels split BH * max(1, ceil(s / 128)) tiles over the SAME g CTAs for whatever number s <= cap of rows is
+  // valid at run time (device-resident kv_len).  Every CTA then owns >= floor(BH * tph(s) / g) tiles, which bounds the
+  // CTAs that share one head by ceil(2 g / BH) + 1 for every s (tests/test_split_cpu.py checks this exhaustively).
+  const int mp = std::min<long long>(g, (2LL * g + BH - 1) / BH + 1);
+  *grid = g;
+  *max_parts = std::max(mp, 1);
+}
+
 void decode_simt_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, int* rows_per_pass,
                       size_t* part_floats, size_t* comm_floats, size_t* comm_flags) {
   const int BH = s.B * s.Hkv;
-  const int tph = (s.S + kTileRows - 1) / kTileRows;
-  const long long total = (long long)BH * tph;
-  int g = (int)std::min<long long>(nsm, std::max<long long>(total, 1));
-  const int q = (int)(total / g);
-  int mp = std::min(g, (tph + std::max(q, 1) - 1) / std::max(q, 1) + 1);
-  mp = std::max(mp, 1);
+  decode_split(BH, s.S, nsm, grid, max_parts);
   const int R = pick_rows((s.Hq / s.Hkv) * s.Sq);
-  *grid = g;
-  *max_parts = mp;
   *rows_per_pass = R;
-  *part_floats = (size_t)BH * mp * R * (s.D + 4);
+  *part_floats = (size_t)BH * *max_parts * R * (s.D + 4);
   *comm_floats = (size_t)2 * kMaxWorldHost * BH * R * (s.D + 2) * 2;
   *comm_flags = (size_t)2 * kMaxWorldHost * BH;
 }
 
-void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                        float* part, uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream,
-                        const uint32_t* kscale, const uint32_t* vscale, int pdl) {
+PreparedLaunch decode_simt_prepare(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                                   float* part, uint32_t* tickets, const CommCtxHost& comm, int nsm,
+                                   const uint32_t* kscale, const uint32_t* vscale, int pdl, const int* kv_len) {
   const bool kv8 = kscale != nullptr;
   if (s.D != 64 && s.D != 128) throw std::runtime_error("decode_simt: head_dim must be 64 or 128");
   if (kv8 && s.D != 128) throw std::runtime_error("decode_simt(mxfp8): head_dim must be 128");
   if (s.Hq % s.Hkv != 0) throw std::runtime_error("decode_simt: Hq must be a multiple of Hkv");
-  if (s.S <= 0) throw std::runtime_error("decode_simt: empty KV shard");
+  if (s.S <= 0) throw std::runtime_error("decode_simt: the KV shard must have capacity for at least one row");
   int grid, max_parts, R;
   size_t pf, cf, cfl;
   decode_simt_plan(s, nsm, &grid, &max_parts, &R, &pf, &cf, &cfl);
@@ -707,37 +570,37 @@ void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const 
   CUtensorMap vmap = make_tmap_bhsd(v, eb, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 128 / eb, kTileRows,
                                     CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeParams p;
-  p.kscale = kscale; p.vscale = vscale; p.pdl = pdl;
+  p.kscale = kscale; p.vscale = vscale; p.pdl = pdl; p.kv_len = kv_len;
   p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S;
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
   p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;
   p.q_sb = s.q_sb; p.q_sh = s.q_sh; p.q_ss = s.q_ss; p.o_sb = s.o_sb; p.o_sh = s.o_sh; p.o_ss = s.o_ss;
-  p.tph = (s.S + kTileRows - 1) / kTileRows;
-  p.total_tiles = s.B * s.Hkv * p.tph;
-  p.tiles_q = p.total_tiles / grid;
-  p.tiles_rem = p.total_tiles % grid;
   p.max_parts = max_parts;
-  p.comm = to_device_ctx(comm);
+  p.comm = dcomm::to_device_ctx(comm);
+  PreparedLaunch pl;
   for (int r_base = 0; r_base < total_rows; r_base += R) {
     p.r_base = r_base;
     p.rows_valid = std::min(R, total_rows - r_base);
-#define TA_LAUNCH(DD, RR)                                                              \
-  if (s.is_bf16) launch_one<DD, RR, true, false>(kmap, vmap, p, grid, stream);         \
-  else launch_one<DD, RR, false, false>(kmap, vmap, p, grid, stream);
-#define TA_LAUNCH8(RR)                                                                 \
-  if (s.is_bf16) launch_one<128, RR, true, true>(kmap, vmap, p, grid, stream);         \
-  else launch_one<128, RR, false, true>(kmap, vmap, p, grid, stream);
+#define TA_PASS(DD, RR, KV)                                                                       \
+  pl.passes.push_back(s.is_bf16 ? make_pass<DD, RR, true, KV>(kmap, vmap, p, grid)               \
+                                : make_pass<DD, RR, false, KV>(kmap, vmap, p, grid));
     if (kv8) {
-      if (R == 4) { TA_LAUNCH8(4) } else if (R == 2) { TA_LAUNCH8(2) } else { TA_LAUNCH8(1) }
+      if (R == 4) { TA_PASS(128, 4, true) } else if (R == 2) { TA_PASS(128, 2, true) } else { TA_PASS(128, 1, true) }
     } else if (s.D == 128) {
-      if (R == 4) { TA_LAUNCH(128, 4) } else if (R == 2) { TA_LAUNCH(128, 2) } else { TA_LAUNCH(128, 1) }
+      if (R == 4) { TA_PASS(128, 4, false) } else if (R == 2) { TA_PASS(128, 2, false) } else { TA_PASS(128, 1, false) }
     } else {
-      if (R == 4) { TA_LAUNCH(64, 4) } else if (R == 2) { TA_LAUNCH(64, 2) } else { TA_LAUNCH(64, 1) }
+      if (R == 4) { TA_PASS(64, 4, false) } else if (R == 2) { TA_PASS(64, 2, false) } else { TA_PASS(64, 1, false) }
     }
-#undef TA_LAUNCH
-#undef TA_LAUNCH8
+#undef TA_PASS
   }
+  return pl;
+}
+
+void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                        float* part, uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream,
+                        const uint32_t* kscale, const uint32_t* vscale, int pdl, const int* kv_len) {
+  decode_simt_prepare(s, q, k, v, out, lse, part, tickets, comm, nsm, kscale, vscale, pdl, kv_len).run(stream);
 }
 
 }  // namespace ta

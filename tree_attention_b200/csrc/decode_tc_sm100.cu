@@ -15,6 +15,7 @@
 // Reference: replaces flash_res_lse (/root/reference/model.py:60-83) and the combine of tree_decode (model.py:85-124) for up to
 // 128 packed query rows per KV head.
 #include "common.cuh"
+#include "decode_comm.cuh"
 #include "host_utils.h"
 #include "kernels.h"
 
@@ -37,12 +38,14 @@ struct DecodeTcParams {
   uint32_t* tickets;
   const float* kscale;  // KV8: per-channel scales (B, Hkv, D) of the e4m3 K / V shards
   const float* vscale;
-  int B, Hq, Hkv, G, Sq, S, R;
+  const int* kv_len;      // optional device scalar: valid rows of this shard (<= S); rows past it inside the last tile
+                          // must hold FINITE data (the tensor pipe multiplies them by exact zeros)
+  int B, Hq, Hkv, G, Sq, S, R;   // S = capacity of the shard (rows covered by the tensor maps)
   float scale_log2;
   int causal;
   long long q_pos0, kv_pos0;
   long long q_sb, q_sh, q_ss, o_sb, o_sh, o_ss;
-  int tph, total_tiles, tiles_q, tiles_rem, max_parts, jvis;
+  int max_parts;
   CommCtx comm;
 };
 
@@ -58,11 +61,6 @@ struct TcSmem {
 };
 
 __device__ __forceinline__ float tc_ninf() { return __int_as_float(0xff800000); }
-__device__ __forceinline__ int tc_cta_lo(const DecodeTcParams& p, int c) { return c * p.tiles_q + min(c, p.tiles_rem); }
-__device__ __forceinline__ int tc_cta_of_tile(const DecodeTcParams& p, int t) {
-  const int big = p.tiles_rem * (p.tiles_q + 1);
-  return t < big ? t / (p.tiles_q + 1) : p.tiles_rem + (t - big) / p.tiles_q;
-}
 template <bool BF16>
 __device__ __forceinline__ uint32_t tc_pack2(float lo, float hi) {
   if constexpr (BF16) return pack_bf16x2(lo, hi);
@@ -77,7 +75,7 @@ __device__ __forceinline__ uint16_t tc_to16(float f) {
 template <int D, bool BF16, bool KV8>
 __global__ void __launch_bounds__(kTcThreads, 1)
 decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant__ CUtensorMap vmap,
-                 const DecodeTcParams p) {
+                 const __grid_constant__ DecodeTcParams p) {
   using SM = TcSmem<D, KV8>;
   constexpr int NS = SM::kStages;
   constexpr int EPA = 128 / SM::kElem;  // elements per 128-byte atom row
@@ -95,17 +93,24 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
   uint64_t* s_full = v_empty + NS;     // 2
   uint64_t* p_full = s_full + 2;       // 2
   uint64_t* pv_done = p_full + 2;      // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* stamps = pv_done + 2;      // 2: globaltimer at CTA start / last publish (thread 0)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stamps + 2);
   int* s_misc = reinterpret_cast<int*>(tmem_slot + 2);  // [0] ticket, [1] n_pending, [2] inline-combine head+1
   int* pending = s_misc + 4;                            // [kTcMaxPending]
   [[maybe_unused]] float* ch_scale = reinterpret_cast<float*>(pending + kTcMaxPending);  // KV8: [2][D] K / V channel scales
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x;
-  const int t_lo = tc_cta_lo(p, cta), t_hi = tc_cta_lo(p, cta + 1);
   const int world = p.comm.world;
   const int BH = p.B * p.Hkv;
   const int R = p.R;
+  const dcomm::Geom geo = dcomm::make_geom(p.S, p.kv_len, BH, gridDim.x);
+  const int t_lo = dcomm::cta_lo(geo, cta), t_hi = dcomm::cta_lo(geo, cta + 1);
+  int jvis = geo.tph;   // tiles of a head that hold visible keys (causal prefix)
+  if (p.causal) {
+    const long long last = p.q_pos0 + p.Sq - 1 - p.kv_pos0;   // last visible local key index
+    jvis = (int)max(0LL, min((long long)geo.tph, last < 0 ? 0LL : last / kTN + 1));
+  }
   const int n_active_warps = (R + 31) / 32;
 
   if (tid == 0) {
@@ -129,16 +134,15 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
 
   uint32_t epoch = 0;
   if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
-  const int parity = epoch & 1;
-  const uint64_t t_cta0 = globaltimer_ns();
+  if (tid == 0) { stamps[0] = globaltimer_ns(); stamps[1] = 0; }
 
   // segment iteration shared by all roles: consecutive tiles of one head, clipped to the visible (causal) prefix
   auto next_segment = [&](int t, int& x, int& j0, int& n, int& t_next) {
-    x = t / p.tph;
-    const int seg_end = min(t_hi, (x + 1) * p.tph);
-    j0 = t - x * p.tph;
-    const int j1 = seg_end - x * p.tph;
-    n = max(0, min(j1, p.jvis) - j0);
+    x = t / geo.tph;
+    const int seg_end = min(t_hi, (x + 1) * geo.tph);
+    j0 = t - x * geo.tph;
+    const int j1 = seg_end - x * geo.tph;
+    n = max(0, min(j1, jvis) - j0);
     t_next = seg_end;
   };
 
@@ -248,68 +252,13 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
       *op = tc_to16<BF16>(o_norm);
       if (d == 0 && p.lse != nullptr) p.lse[((long long)b * p.Hq + (h * p.G + g)) * p.Sq + i] = lse2 * 0.6931471805599453f;
     };
-    // ---- LL transport (tagged 8-byte words), identical protocol to decode_simt.cu ----
-    auto word_ptr = [&](int dst, int src, int x) -> uint2* {
-      return reinterpret_cast<uint2*>(p.comm.data[dst]) + ((size_t)(parity * world + src) * BH + x) * (size_t)(R * (D + 2));
-    };
-    auto ll_store = [&](uint2* w, float v) {
-      asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(w), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
-    };
-    auto ll_wait = [&](const uint2* w, bool& ok) -> float {
-      uint32_t v, tag;
-      asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(w) : "memory");
-      if (tag != epoch) {
-        const uint64_t t0 = globaltimer_ns();
-        uint32_t itn = 0;
-        do {
-          asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(tag) : "l"(w) : "memory");
-          if (tag == epoch) break;
-          if ((++itn & 0x3fu) == 0 && globaltimer_ns() - t0 > p.comm.timeout_ns) { ok = false; break; }
-        } while (true);
-      }
-      return __uint_as_float(v);
-    };
-    uint64_t t_publish = 0;
-    auto combine_ranks = [&](int x) {
-      uint64_t t_got = 0;
-      for (int idx = tid; idx < R * D; idx += kSmx) {
-        const int r = idx / D, d = idx - r * D;
-        bool ok = true;
-        float lse_s[kMaxWorld];
-        float mx = tc_ninf();
-        int bad_src = -1;
-        for (int s = 0; s < world; ++s) {
-          bool oks = true;
-          lse_s[s] = ll_wait(word_ptr(p.comm.rank, s, x) + r * (D + 2) + D, oks);
-          if (!oks) { ok = false; bad_src = s; }
-          mx = fmaxf(mx, lse_s[s]);
-        }
-        const float ms = (mx == tc_ninf()) ? 0.f : mx;
-        float num = 0.f, den = 0.f;
-        for (int s = 0; s < world; ++s) {
-          bool oks = true;
-          const float val = ll_wait(word_ptr(p.comm.rank, s, x) + r * (D + 2) + d, oks);
-          if (!oks) { ok = false; bad_src = s; }
-          const float w = fast_exp2(lse_s[s] - ms);
-          num = fmaf(w, val, num);
-          den += w;
-        }
-        if (idx == 0) t_got = globaltimer_ns();
-        float o_norm = den > 0.f ? num / den : 0.f;
-        float lse2 = den > 0.f ? ms + fast_log2(den) : tc_ninf();
-        if (!ok) {
-          o_norm = __int_as_float(0x7fc00000); lse2 = o_norm;
-          p.comm.status[0] = kCommTimeout; p.comm.status[1] = x; p.comm.status[2] = bad_src; p.comm.status[3] = epoch;
-        }
-        store_out(x, r, d, o_norm, lse2);
-      }
-      named_bar_sync(1, kSmx);
-      if (tid == 0 && t_publish != 0) {
-        const uint64_t t_done = globaltimer_ns();
-        atomicMax(p.comm.status + 10, (uint32_t)min((unsigned long long)(t_got - t_publish), 0xffffffffull));
-        atomicMax(p.comm.status + 11, (uint32_t)min((unsigned long long)(t_done - t_publish), 0xffffffffull));
-        atomicMax(p.comm.status + 12, (uint32_t)min((unsigned long long)(t_publish - t_cta0), 0xffffffffull));
-      }
+    // split merge + LL-word cross-GPU combine: decode_comm.cuh (shared with decode_simt.cu / decode_swap_sm100.cu)
+    auto make_tail = [&]() {   // built on demand: keeps the tail's bookkeeping out of the tile loop's live registers
+      dcomm::Tail tl;
+      tl.comm = &p.comm; tl.part = p.part; tl.tickets = p.tickets; tl.max_parts = p.max_parts; tl.BH = BH;
+      tl.R = R; tl.rows_valid = R; tl.epoch = epoch; tl.parity = epoch & 1;
+      tl.s_misc = s_misc; tl.pending = pending; tl.max_pending = kTcMaxPending; tl.stamps = stamps;
+      return tl;
     };
 
     int it = 0;
@@ -381,9 +330,9 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
           tmem_ld_32x32b_x32(s_tmem + 64, *reinterpret_cast<uint32_t(*)[32]>(&sr[64]));
           tmem_ld_32x32b_x32(s_tmem + 96, *reinterpret_cast<uint32_t(*)[32]>(&sr[96]));
           tmem_ld_wait();
-          const bool need_mask = (n0 + kTN > p.S) || (p.causal && (p.kv_pos0 + n0 + kTN - 1 > p.q_pos0));
+          const bool need_mask = (n0 + kTN > geo.S) || (p.causal && (p.kv_pos0 + n0 + kTN - 1 > p.q_pos0));
           if (need_mask) {
-            long long lim = (long long)p.S - n0 - 1;
+            long long lim = (long long)geo.S - n0 - 1;
             if (p.causal) lim = min(lim, q_pos - p.kv_pos0 - n0);
             const int limc = (int)max(-1LL, min(lim, 127LL));
 #pragma unroll
@@ -455,8 +404,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
         }
       }
       // ---- segment epilogue: (O, m, l) of the valid rows -> CTA partial in the workspace
-      const int first_cta = tc_cta_of_tile(p, x * p.tph);
-      const int nparts = tc_cta_of_tile(p, (x + 1) * p.tph - 1) - first_cta + 1;
+      const int first_cta = dcomm::cta_of_tile(geo, x * geo.tph);
+      const int nparts = dcomm::cta_of_tile(geo, (x + 1) * geo.tph - 1) - first_cta + 1;
       float* my_part = p.part + ((size_t)x * p.max_parts + (cta - first_cta)) * (size_t)(R * (D + 4));
       if (warp_active) {
         if (n > 0) {
@@ -492,130 +441,55 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
         tc_fence_before();
       }
       it += n;
-      __threadfence();
-      named_bar_sync(1, kSmx);
-      if (tid == 0) s_misc[0] = (int)atomicAdd(&p.tickets[x], 1u);
-      named_bar_sync(1, kSmx);
-      if (s_misc[0] == nparts - 1) {
-        __threadfence();
-        if (tid == 0) p.tickets[x] = 0;
-        const float* parts = p.part + (size_t)x * p.max_parts * (size_t)(R * (D + 4));
-        for (int idx = tid; idx < R * D; idx += kSmx) {
-          const int r = idx / D, d = idx - r * D;
-          float M = tc_ninf();
-          for (int qi = 0; qi < nparts; ++qi) M = fmaxf(M, __ldcg(parts + (size_t)qi * (R * (D + 4)) + r * (D + 4) + D));
-          const float Ms = (M == tc_ninf()) ? 0.f : M;
-          float acc = 0.f, Lsum = 0.f;
-          for (int qi = 0; qi < nparts; ++qi) {
-            const float* pp = parts + (size_t)qi * (R * (D + 4)) + r * (D + 4);
-            const float sc = fast_exp2(__ldcg(pp + D) - Ms);
-            acc = fmaf(__ldcg(pp + d), sc, acc);
-            Lsum = fmaf(__ldcg(pp + D + 1), sc, Lsum);
-          }
-          const float o_norm = Lsum > 0.f ? acc / Lsum : 0.f;
-          const float lse2 = Lsum > 0.f ? Ms + fast_log2(Lsum) : tc_ninf();
-          if (world == 1) {
-            store_out(x, r, d, o_norm, lse2);
-          } else if (!p.comm.skip_publish) {
-            for (int dst = 0; dst < world; ++dst) {
-              uint2* wp = word_ptr(dst, p.comm.rank, x) + r * (D + 2);
-              ll_store(wp + d, o_norm);
-              if (d == 0) ll_store(wp + D, lse2);
-            }
-          }
-        }
-        if (world > 1) {
-          if (tid == 0) {
-            t_publish = globaltimer_ns();
-            const int np = s_misc[1];
-            if (np < kTcMaxPending) { pending[np] = x; s_misc[1] = np + 1; }
-            else s_misc[2] = x + 1;
-          }
-          named_bar_sync(1, kSmx);
-          if (s_misc[2] != 0) {
-            named_bar_sync(1, kSmx);
-            if (tid == 0) s_misc[2] = 0;
-            combine_ranks(x);
-          }
-        }
+      {
+        const dcomm::Tail tail = make_tail();
+        dcomm::finish_head<D, kSmx, 4>(tail, x, nparts, tid, 1, store_out);
       }
       named_bar_sync(1, kSmx);  // Q smem / s_misc reuse by the next segment
       t = tn;
     }
-    if (world > 1) {
-      named_bar_sync(1, kSmx);
-      const int np = s_misc[1];
-      for (int u = 0; u < np; ++u) combine_ranks(pending[u]);
-      if (tid == 0) {
-        __threadfence();
-        const uint32_t done = atomicAdd(&p.tickets[BH], 1u);
-        if (done == gridDim.x - 1) {
-          p.tickets[BH] = 0;
-          __threadfence();
-          *reinterpret_cast<volatile uint32_t*>(p.comm.epoch) = epoch;
-        }
-      }
-    }
+    const dcomm::Tail tail = make_tail();
+    dcomm::drain_and_exit<D, kSmx, 4>(tail, tid, 1, store_out);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) { tc_fence_after(); tmem_dealloc<512>(tmem); }
 }
 
-inline CommCtx tc_device_ctx(const CommCtxHost& h) {
-  CommCtx c;
-  c.rank = h.rank;
-  c.world = h.world;
-  for (int i = 0; i < kMaxWorld; ++i) {
-    c.data[i] = reinterpret_cast<float*>(h.data[i]);
-    c.flags[i] = reinterpret_cast<uint32_t*>(h.flags[i]);
-  }
-  c.epoch = reinterpret_cast<uint32_t*>(h.epoch);
-  c.status = reinterpret_cast<uint32_t*>(h.status);
-  c.timeout_ns = h.timeout_ns;
-  c.skip_publish = h.skip_publish;
-  return c;
-}
-
 template <int D, bool BF16, bool KV8>
-void launch_tc(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeTcParams& p, int grid, cudaStream_t stream) {
+std::function<void(cudaStream_t)> make_tc_pass(const CUtensorMap& kmap, const CUtensorMap& vmap, const DecodeTcParams& p, int grid) {
   auto kern = decode_tc_kernel<D, BF16, KV8>;
   static bool configured = false;
   if (!configured) {
     TA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcSmem<D, KV8>::kTotal));
     configured = true;
   }
-  kern<<<grid, kTcThreads, TcSmem<D, KV8>::kTotal, stream>>>(kmap, vmap, p);
-  TA_CUDA_CHECK(cudaGetLastError());
+  return [kern, kmap, vmap, p, grid](cudaStream_t stream) {
+    kern<<<grid, kTcThreads, TcSmem<D, KV8>::kTotal, stream>>>(kmap, vmap, p);
+    TA_CUDA_CHECK(cudaGetLastError());
+  };
 }
 
 }  // namespace
 
-// split of the (B x Hkv x tiles) work list over ncta persistent CTAs; max_parts bounds the CTAs sharing one KV head
+// kept for callers of the round-1 name: same split as decode_simt (decode_split, decode_simt.cu)
 void decode_tc_split(const AttnShape& s, int ncta, int* grid, int* max_parts) {
-  const int BH = s.B * s.Hkv;
-  const int tph = (s.S + kTN - 1) / kTN;
-  const long long total = (long long)BH * tph;
-  const int g = (int)std::min<long long>(ncta, std::max<long long>(total, 1));
-  const int q = (int)(total / g);
-  int mp = std::min(g, (tph + std::max(q, 1) - 1) / std::max(q, 1) + 1);
-  *grid = g;
-  *max_parts = std::max(mp, 1);
+  decode_split(s.B * s.Hkv, s.S, ncta, grid, max_parts);
 }
 
 void decode_tc_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, int* rows, size_t* part_floats,
                     size_t* comm_bytes) {
   const int BH = s.B * s.Hkv;
-  decode_tc_split(s, nsm, grid, max_parts);
+  decode_split(BH, s.S, nsm, grid, max_parts);
   const int R = (s.Hq / s.Hkv) * s.Sq;
   *rows = R;
   *part_floats = (size_t)BH * *max_parts * R * (s.D + 4);
   *comm_bytes = (size_t)2 * kMaxWorldHost * BH * R * (s.D + 2) * 8;
 }
 
-void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
-                      uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream, const float* kscale,
-                      const float* vscale) {
+PreparedLaunch decode_tc_prepare(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                                 float* part, uint32_t* tickets, const CommCtxHost& comm, int nsm, const float* kscale,
+                                 const float* vscale, const int* kv_len) {
   const bool kv8 = kscale != nullptr;
   if (s.D != 64 && s.D != 128) throw std::runtime_error("decode_tc: head_dim must be 64 or 128");
   if (kv8 && s.D != 128) throw std::runtime_error("decode_tc(fp8): head_dim must be 128");
@@ -623,7 +497,7 @@ void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const vo
   const int G = s.Hq / s.Hkv;
   const int R = G * s.Sq;
   if (R > kTM) throw std::runtime_error("decode_tc: (Hq / Hkv) * Sq must be <= 128");
-  if (s.S <= 0) throw std::runtime_error("decode_tc: empty KV shard");
+  if (s.S <= 0) throw std::runtime_error("decode_tc: the KV shard must have capacity for at least one row");
   int grid, max_parts, rows;
   size_t pf, cb;
   decode_tc_plan(s, nsm, &grid, &max_parts, &rows, &pf, &cb);
@@ -635,30 +509,25 @@ void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const vo
   CUtensorMap kmap = make_tmap_bhsd(k, eb, s.B, s.Hkv, s.S, s.D, s.k_sb, s.k_sh, s.k_ss, 128 / eb, kTN, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap vmap = make_tmap_bhsd(v, eb, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 128 / eb, kTN, CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeTcParams p;
-  p.kscale = kscale; p.vscale = vscale;
+  p.kscale = kscale; p.vscale = vscale; p.kv_len = kv_len;
   p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S; p.R = R;
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
   p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;
   p.q_sb = s.q_sb; p.q_sh = s.q_sh; p.q_ss = s.q_ss; p.o_sb = s.o_sb; p.o_sh = s.o_sh; p.o_ss = s.o_ss;
-  p.tph = (s.S + kTN - 1) / kTN;
-  p.total_tiles = s.B * s.Hkv * p.tph;
-  p.tiles_q = p.total_tiles / grid;
-  p.tiles_rem = p.total_tiles % grid;
   p.max_parts = max_parts;
-  p.jvis = p.tph;
-  if (s.causal) {
-    const long long last = s.q_pos0 + s.Sq - 1 - s.kv_pos0;  // last visible local key index
-    p.jvis = (int)std::max<long long>(0, std::min<long long>(p.tph, last < 0 ? 0 : last / kTN + 1));
-  }
-  p.comm = tc_device_ctx(comm);
-  if (kv8) {
-    if (s.is_bf16) launch_tc<128, true, true>(kmap, vmap, p, grid, stream); else launch_tc<128, false, true>(kmap, vmap, p, grid, stream);
-  } else if (s.D == 128) {
-    if (s.is_bf16) launch_tc<128, true, false>(kmap, vmap, p, grid, stream); else launch_tc<128, false, false>(kmap, vmap, p, grid, stream);
-  } else {
-    if (s.is_bf16) launch_tc<64, true, false>(kmap, vmap, p, grid, stream); else launch_tc<64, false, false>(kmap, vmap, p, grid, stream);
-  }
+  p.comm = dcomm::to_device_ctx(comm);
+  PreparedLaunch pl;
+  if (kv8) pl.passes.push_back(s.is_bf16 ? make_tc_pass<128, true, true>(kmap, vmap, p, grid) : make_tc_pass<128, false, true>(kmap, vmap, p, grid));
+  else if (s.D == 128) pl.passes.push_back(s.is_bf16 ? make_tc_pass<128, true, false>(kmap, vmap, p, grid) : make_tc_pass<128, false, false>(kmap, vmap, p, grid));
+  else pl.passes.push_back(s.is_bf16 ? make_tc_pass<64, true, false>(kmap, vmap, p, grid) : make_tc_pass<64, false, false>(kmap, vmap, p, grid));
+  return pl;
+}
+
+void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
+                      uint32_t* tickets, const CommCtxHost& comm, int nsm, cudaStream_t stream, const float* kscale,
+                      const float* vscale, const int* kv_len) {
+  decode_tc_prepare(s, q, k, v, out, lse, part, tickets, comm, nsm, kscale, vscale, kv_len).run(stream);
 }
 
 }  // namespace ta

@@ -4,7 +4,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <functional>
+#include <vector>
+
 namespace ta {
+
+// A kernel launch (or a short sequence of launches) whose tensor maps and parameter block were encoded once.
+// run() costs one cudaLaunchKernelEx per pass: the host path of a serving loop (models/decoder.py, bindings DecodeStep).
+struct PreparedLaunch {
+  std::vector<std::function<void(cudaStream_t)>> passes;
+  void run(cudaStream_t stream) const {
+    for (const auto& f : passes) f(stream);
+  }
+};
 
 constexpr int kMaxWorldHost = 16;
 
@@ -35,16 +47,26 @@ struct AttnShape {
   int64_t o_sb = 0, o_sh = 0, o_ss = 0;
 };
 
+// ---- stream-K split shared by the three decode kernels: BH x ceil(cap / 128) tiles over <= ncta persistent CTAs.
+// max_parts bounds the CTAs sharing one (batch, kv-head) for EVERY run-time number of valid rows <= cap.
+void decode_split(int BH, int cap, int ncta, int* grid, int* max_parts);
+
 // ---- split-KV streaming decode (CUDA-core math, TMA-fed), fused split merge + cross-GPU combine ----
 // workspace sizes for a given problem; `grid` is returned so that callers can cache it.
 void decode_simt_plan(const AttnShape& s, int num_sms, int* grid, int* max_parts, int* rows_per_pass,
                       size_t* part_floats, size_t* comm_floats, size_t* comm_flags);
 // out: same dtype as q.  lse: fp32 (B, Hq, Sq) natural log, may be null.
 // part: float workspace, tickets: uint32 [B*Hkv + 2] zero-initialised once.
+// kv_len: optional DEVICE scalar with the number of valid rows of the shard (<= S, the capacity the tensor maps
+// cover); the kernel reads it at run time, so a captured CUDA graph follows a growing KV cache.
 void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                         float* part, uint32_t* tickets, const CommCtxHost& comm, int num_sms,
                         cudaStream_t stream, const uint32_t* kscale = nullptr, const uint32_t* vscale = nullptr,
-                        int pdl = 0);
+                        int pdl = 0, const int* kv_len = nullptr);
+PreparedLaunch decode_simt_prepare(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                                   float* part, uint32_t* tickets, const CommCtxHost& comm, int num_sms,
+                                   const uint32_t* kscale = nullptr, const uint32_t* vscale = nullptr, int pdl = 0,
+                                   const int* kv_len = nullptr);
 // kscale/vscale != null: K/V are block-scaled fp8 (e4m3 bytes, D = 128) and the scales are (B, Hkv, S) words of
 // four UE8M0 exponents (one per 32 elements); strides in AttnShape are then in BYTES == elements.
 
@@ -56,13 +78,22 @@ void decode_tc_plan(const AttnShape& s, int num_sms, int* grid, int* max_parts, 
 // tcgen05 kind::f8f6f4 (q is quantised per row in the kernel, P per element, K's scales are folded into q).
 void decode_tc_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
                       uint32_t* tickets, const CommCtxHost& comm, int num_sms, cudaStream_t stream,
-                      const float* kscale = nullptr, const float* vscale = nullptr);
+                      const float* kscale = nullptr, const float* vscale = nullptr, const int* kv_len = nullptr);
+PreparedLaunch decode_tc_prepare(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                                 float* part, uint32_t* tickets, const CommCtxHost& comm, int num_sms,
+                                 const float* kscale = nullptr, const float* vscale = nullptr,
+                                 const int* kv_len = nullptr);
 
 // ---- swap-AB tensor-core decode (keys on the TMEM lanes, <= 16 packed query columns); head_dim 128 ----
 void decode_swap_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse, float* part,
                         uint32_t* tickets, const CommCtxHost& comm, int num_sms, cudaStream_t stream,
                         const float* kscale = nullptr, const float* vscale = nullptr, const uint32_t* k_sf = nullptr,
-                        const uint32_t* v_sf = nullptr);
+                        const uint32_t* v_sf = nullptr, const int* kv_len = nullptr);
+PreparedLaunch decode_swap_prepare(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
+                                   float* part, uint32_t* tickets, const CommCtxHost& comm, int num_sms,
+                                   const float* kscale = nullptr, const float* vscale = nullptr,
+                                   const uint32_t* k_sf = nullptr, const uint32_t* v_sf = nullptr,
+                                   const int* kv_len = nullptr);
 
 // ---- stand-alone combine of W per-rank partials (o fp32 normalised, lse natural log) ----
 // local: o_part (rows, D) fp32 + lse_part (rows); result written to out (dtype of `is_bf16`/fp16/fp32)
@@ -92,22 +123,9 @@ void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const voi
                      const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem = 0);
 void attn_fwd_phase_cycles(unsigned long long* out5);   // profiling aid, see attn_fwd_sm100.cu
 size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
-// M = 128 with two softmax warpgroups splitting the score columns (two resident softmax warps per SM sub-partition)
-void attn_fwd3_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                      const CommCtxHost& comm, cudaStream_t stream);
 // EXPERIMENTAL (compile-checked only): cluster of two CTAs, tcgen05.mma.cta_group::2 with M = 256, half of each B operand per CTA
 void attn_fwd7_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                       const CommCtxHost& comm, cudaStream_t stream);
-// M = 256 (two query tiles), BLOCK_N = 64, scores double-buffered per tile
-void attn_fwd5_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                      const CommCtxHost& comm, cudaStream_t stream);
-// two ping-ponged query tiles per CTA (M = 256), single-pass register softmax, setmaxnreg register split
-void attn_fwd4_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                      const CommCtxHost& comm, cudaStream_t stream);
-// two ping-ponged query tiles per CTA (M = 256); same contract and symmetric-buffer layout
-void attn_fwd2_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                      const CommCtxHost& comm, cudaStream_t stream);
-
 // ---- tcgen05 flash-attention backward over one KV shard with the GLOBAL o / lse ----
 // dq: fp32 (B, Hq, Sq, D) contiguous (this shard's partial); dk, dv: (B, Hkv, S, D) contiguous, I/O dtype;
 // delta, lse2: fp32 scratch (B, Hq, ceil64(Sq)).

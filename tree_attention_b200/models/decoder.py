@@ -2,19 +2,32 @@
 
 ``TreeDecodeSession`` is the user-facing wrapper for the reference's one use case -- a decode step over a
 sequence-sharded KV cache (``/root/reference/model.py:129-155`` runs exactly one such step) -- extended to
-what a server needs: several KV caches ("layers") resident in HBM, a step captured once per layer in a
-CUDA graph (the step is a single fused kernel; at 8 GPUs it is shorter than a Python launch), pinned-host
-I/O for the query / result, and a KV-append for the owning rank.
+what a server needs:
+
+* several KV caches ("layers") resident in HBM, each with a device-resident FILL LEVEL (``kv_len``): the kernels
+  read it at run time, so rows that have not been written yet never enter the softmax and a CUDA graph captured
+  once follows the growing cache (``append_kv`` bumps the level on the device);
+* a step prepared ONCE per layer in C++ (``_C.DecodeStep``: tensor maps encoded, parameter block filled) and
+  re-launched with a single runtime call, optionally chained by programmatic dependent launch, or replayed from a
+  CUDA graph; the session OWNS the split-merge workspace and its symmetric region, so nothing a graph or a prepared
+  launch points at can be re-allocated behind its back;
+* pinned-host I/O for the query / result (``step``).
 """
 from __future__ import annotations
 
+import itertools
 import time
 from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
 
+from ..ops import local as local_ops
+from ..ops import reference as ref
+from ..parallel import symm
 from ..parallel.tree import tree_attention
+
+_SESSION_IDS = itertools.count()
 
 
 class TreeDecodeSession:
@@ -30,10 +43,14 @@ class TreeDecodeSession:
         q_shape: Optional[Tuple[int, int, int, int]] = None,
         pdl: bool = False,
         dtype: Optional[torch.dtype] = None,
+        kv_lens: Optional[Sequence[int]] = None,
     ):
-        """``pdl=True``: eager launches with programmatic dependent launch + K/V prefetch (the KV caches of this
-        session are only written through ``append_kv``, never by the kernel that precedes a step) instead of CUDA
-        graph replay -- the next step's prologue and first tile loads overlap the previous step's peer wait."""
+        """``kv_layers``: per layer this rank's preallocated ``(k, v)`` shard, ``(B, Hkv, capacity, D)``.
+        ``kv_lens``: per layer the number of rows already filled (default: the shards are full).  Construction is
+        collective (every rank of ``group`` builds its session in the same order).
+        ``pdl=True``: ``step_device`` launches eagerly with programmatic dependent launch + K/V prefetch (the caches of
+        a session are only written through ``append_kv``) -- the next step's prologue and first tile loads overlap
+        the previous step's drain; the e2e path (``step``) replays a CUDA graph."""
         self.kv = list(kv_layers)
         k0 = self.kv[0][0]
         self.device = k0.device
@@ -46,8 +63,9 @@ class TreeDecodeSession:
         self.schedule = schedule
         self.group = group
         self.pdl = 2 if pdl else 0
-        self._kv_dirty = False  # set by append_kv: the next step must not prefetch K/V ahead of the append
+        self._kv_dirty = False  # set by append_kv: the next step must not prefetch K/V (or read kv_len) ahead of the append
         b, hkv, s, d = k0.shape
+        self.capacity = s
         self.q_shape = tuple(q_shape) if q_shape is not None else (b, hkv, 1, d)
         self.q_static = torch.zeros(self.q_shape, dtype=self.dtype, device=self.device)
         self.out_static: List[Optional[torch.Tensor]] = [None] * len(self.kv)
@@ -57,15 +75,44 @@ class TreeDecodeSession:
         self.e2e_graphs: List[torch.cuda.CUDAGraph] = []
         self.q_host: Optional[torch.Tensor] = None
         self.out_host: List[Optional[torch.Tensor]] = [None] * len(self.kv)
-        g = self.q_shape[1] // hkv
-        rows = g * self.q_shape[2]
         self.launches_per_step = 1
-        world = dist.get_world_size(group) if dist.is_initialized() else 1
-        graphable = self.device.type == "cuda" and (world == 1 or backend in ("fused", "symm", "auto"))
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        graphable = self.device.type == "cuda" and (self.world == 1 or backend in ("fused", "symm", "auto"))
         self._use_graph = bool(use_graph and graphable)
         self._prepared = False
+        # fill levels: host mirror + one int32 per layer on the device (the kernels' kv_len scalars are views of it)
+        self.kv_len_host: Optional[List[int]] = None
+        self.kv_len_dev: Optional[torch.Tensor] = None
+        if kv_lens is not None:
+            self.kv_len_host = [int(x) for x in kv_lens]
+            assert len(self.kv_len_host) == len(self.kv) and all(0 <= x <= s for x in self.kv_len_host)
+            self.kv_len_dev = torch.tensor(self.kv_len_host, dtype=torch.int32, device=self.device)
+        # native fast path: plain bf16 / fp16 caches on CUDA through the fused (or single-GPU) decode kernels
+        self._steps: List[object] = []
+        self._ws = None
+        self.region = None
+        self._family = None
+        self._fast = (self.device.type == "cuda" and not self.quantised and backend in ("fused", "auto") and
+                      schedule == "oneshot" and local_ops.decode_eligible(self.q_static, k0))
+
+    @classmethod
+    def allocate(cls, n_layers: int, b: int, hkv: int, capacity: int, d: int, device, dtype=torch.bfloat16, **kw):
+        """Session over freshly allocated, ZERO-initialised caches with fill level 0 (rows past the fill level inside a
+        128-row tile are multiplied by exact zeros on the tensor cores, so they must be finite -- zeros are)."""
+        kv = [(torch.zeros(b, hkv, capacity, d, dtype=dtype, device=device),
+               torch.zeros(b, hkv, capacity, d, dtype=dtype, device=device)) for _ in range(n_layers)]
+        return cls(kv, kv_lens=[0] * n_layers, **kw)
 
     # -- internals ---------------------------------------------------------------------------------
+    def _kv_len_of(self, layer: int):
+        return None if self.kv_len_dev is None else self.kv_len_dev[layer : layer + 1]
+
+    def _positions(self) -> Tuple[int, int]:
+        """(q_pos0, kv_pos0) as tree_attention derives them: contiguous capacity-sized shards in rank order, the
+        query at the end of the global sequence."""
+        return self.world * self.capacity - self.q_shape[2], self.rank * self.capacity
+
     def _eager(self, q: torch.Tensor, layer: int, use_pdl: bool = False) -> torch.Tensor:
         k, v = self.kv[layer]
         pdl = 0
@@ -73,13 +120,52 @@ class TreeDecodeSession:
             pdl = min(self.pdl, 1) if self._kv_dirty else self.pdl
         self._kv_dirty = False
         return tree_attention(q, k, v, group=self.group, causal=self.causal, softmax_scale=self.scale,
-                              backend=self.backend, schedule=self.schedule, decode_pdl=pdl)
+                              backend=self.backend, schedule=self.schedule, decode_pdl=pdl, kv_len=self._kv_len_of(layer))
+
+    def _prepare_fast(self) -> None:
+        from .. import _build
+
+        C = _build.load()
+        k0 = self.kv[0][0]
+        b, hq, sq, d = self.q_shape
+        impl = local_ops.decode_impl_for(self.q_shape, k0.shape)
+        nfloats, ntick = local_ops.decode_workspace_sizes(self.q_shape, k0.shape, impl)
+        self._ws = local_ops.new_workspace(self.device, nfloats, ntick)   # owned: never re-allocated under a graph
+        comm = None
+        if self.world > 1:
+            data, flags = local_ops.decode_comm_bytes(b, hq, k0.shape[1], sq, self.capacity, d, self.world)
+            self._family = f"decode.session{next(_SESSION_IDS)}"          # a region of its own, sized once
+            self.region = symm.get_region(self._family, data, flags, self.group, layout=(b, hq, k0.shape[1], sq, d))
+            comm = self.region.comm
+        scale = ref.default_scale(d) if self.scale is None else float(self.scale)
+        q_pos0, kv_pos0 = self._positions()
+        for i, (k, v) in enumerate(self.kv):
+            assert tuple(k.shape) == tuple(k0.shape), "all layers of a session share one shard shape"
+            self.out_static[i] = torch.empty(self.q_shape, dtype=self.dtype, device=self.device)
+            self._steps.append(C.decode_step(impl, self.q_static, k, v, self.out_static[i], None, self._ws["part"],
+                                             self._ws["tickets"], comm, scale, bool(self.causal), int(q_pos0),
+                                             int(kv_pos0), self._kv_len_of(i)))
+        self.launches_per_step = self._steps[0].kernels_per_step
+
+    def _launch(self, layer: int, use_pdl: bool = False) -> torch.Tensor:
+        if self._steps:
+            pdl = 0
+            if use_pdl:
+                pdl = min(self.pdl, 1) if self._kv_dirty else self.pdl
+            self._kv_dirty = False
+            self._steps[layer].launch(pdl)
+            return self.out_static[layer]
+        out = self._eager(self.q_static, layer, use_pdl)
+        self.out_static[layer] = out
+        return out
 
     def _prepare(self) -> None:
         if self._prepared:
             return
-        for i in range(len(self.kv)):  # allocates workspaces and (collectively) the symmetric region
-            self.out_static[i] = self._eager(self.q_static, i)
+        if self._fast:
+            self._prepare_fast()
+        for i in range(len(self.kv)):  # first launches: allocates workspaces and (collectively) symmetric regions
+            self._launch(i)
         if self.device.type == "cuda":
             torch.cuda.synchronize()
         if self._use_graph:
@@ -88,7 +174,7 @@ class TreeDecodeSession:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.stream(side):
                     with torch.cuda.graph(g):
-                        self.out_static[i] = self._eager(self.q_static, i)
+                        self._launch(i)
                 self.graphs.append(g)
             torch.cuda.synchronize()
             self.q_host = torch.empty(self.q_shape, dtype=self.dtype).pin_memory()
@@ -99,7 +185,7 @@ class TreeDecodeSession:
                 with torch.cuda.stream(side):
                     with torch.cuda.graph(g):
                         self.q_static.copy_(self.q_host, non_blocking=True)
-                        o = self._eager(self.q_static, i)
+                        o = self._launch(i)
                         self.out_host[i].copy_(o, non_blocking=True)
                 self.e2e_graphs.append(g)
             torch.cuda.synchronize()
@@ -113,13 +199,12 @@ class TreeDecodeSession:
         self._prepare()
         if q is not None and q.data_ptr() != self.q_static.data_ptr():
             self.q_static.copy_(q, non_blocking=True)
-        if self.pdl:  # throughput path: eager launches chained by programmatic dependent launch
-            return self._eager(self.q_static, layer, use_pdl=True)
+        if self.pdl:  # throughput path: launches chained by programmatic dependent launch
+            return self._launch(layer, use_pdl=True)
         if self.graphs:
             self.graphs[layer].replay()
             return self.out_static[layer]
-        self.out_static[layer] = self._eager(self.q_static, layer)
-        return self.out_static[layer]
+        return self._launch(layer)
 
     def step(self, q_host: torch.Tensor, out_host: torch.Tensor, layer: int) -> torch.Tensor:
         """End-to-end (latency) step: pinned host query -> device, attention, result -> pinned host, synchronised.
@@ -141,22 +226,43 @@ class TreeDecodeSession:
             self.graphs[layer].replay()
             out = self.out_static[layer]
         else:
-            out = self._eager(self.q_static, layer)
+            out = self._launch(layer)
         out_host.copy_(out, non_blocking=True)
         if self.device.type == "cuda":
             torch.cuda.current_stream().synchronize()
         return out_host
 
-    def append_kv(self, layer: int, k_new: torch.Tensor, v_new: torch.Tensor, position: int) -> None:
-        """Write one new token's K/V at local row ``position`` of this rank's shard (the owner of the
-        global position calls this; shards are preallocated)."""
+    def append_kv(self, layer: int, k_new: torch.Tensor, v_new: torch.Tensor, position: Optional[int] = None) -> None:
+        """Write new tokens' K/V at local row ``position`` of this rank's shard (default: at the current fill level) and
+        raise the fill level to cover them.  The rank that owns the global position calls this; other ranks do not."""
         k, v = self.kv[layer]
+        n = k_new.shape[2]
+        if position is None:
+            if self.kv_len_host is None:
+                raise ValueError("append_kv without a position needs a session created with kv_lens")
+            position = self.kv_len_host[layer]
+        if position + n > self.capacity:
+            raise ValueError(f"append_kv: rows {position}..{position + n} exceed the shard capacity {self.capacity}")
         self._kv_dirty = True
         for cache, new in ((k, k_new), (v, v_new)):
             if hasattr(cache, "write_rows"):      # quantised cache: quantise on the way in
                 cache.write_rows(position, new)
             else:
-                cache[:, :, position : position + new.shape[2]].copy_(new, non_blocking=True)
+                cache[:, :, position : position + n].copy_(new, non_blocking=True)
+        if self.kv_len_host is not None and position + n > self.kv_len_host[layer]:
+            self.kv_len_host[layer] = position + n
+            # stream-ordered device update (a fill kernel: graph replays and prepared launches queued behind it see it)
+            self.kv_len_dev[layer : layer + 1].fill_(position + n)
+
+    def close(self) -> None:
+        """Release the session's symmetric region (collective).  ``cleanup()`` does this for every live region."""
+        self.graphs.clear()
+        self.e2e_graphs.clear()
+        self._steps.clear()
+        if self._family is not None:
+            symm.release(self._family, self.group)
+            self._family = None
+            self.region = None
 
     def run_e2e(self, q: torch.Tensor, steps: int, barrier) -> dict:
         self._prepare()

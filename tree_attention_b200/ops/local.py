@@ -31,16 +31,36 @@ def _as_bhsd(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
+def new_workspace(device: torch.device, nfloats: int, nticket: int) -> Dict[str, torch.Tensor]:
+    """A private split-merge workspace (partials + tickets).  Objects that bake raw pointers into CUDA graphs or
+    prepared launches (``TreeDecodeSession``) own one of these instead of borrowing the shared cache below."""
+    return {
+        "part": torch.empty(max(nfloats, 1), dtype=torch.float32, device=device),
+        "tickets": torch.zeros(max(nticket, 64), dtype=torch.int32, device=device),
+    }
+
+
 def _workspace(device: torch.device, tag: str, nfloats: int, nticket: int) -> Dict[str, torch.Tensor]:
-    key = (device.index, tag)
+    """Shared workspace cache for eager calls, keyed by (device, STREAM, kernel family): two streams decoding
+    concurrently never share partials / tickets, and growth is stream-ordered (the old buffers go back to the caching
+    allocator, which only re-uses them behind the work already queued on that stream)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
     ws = _WS.get(key)
     if ws is None or ws["part"].numel() < nfloats or ws["tickets"].numel() < nticket:
-        ws = {
-            "part": torch.empty(max(nfloats, 1), dtype=torch.float32, device=device),
-            "tickets": torch.zeros(max(nticket, 64), dtype=torch.int32, device=device),
-        }
+        ws = new_workspace(device, nfloats, nticket)
         _WS[key] = ws
     return ws
+
+
+def _kv_len_arg(kv_len, like: torch.Tensor):
+    """``kv_len`` for the kernels: None, or a 1-element int32 tensor on the cache's device (python ints are wrapped)."""
+    if kv_len is None:
+        return None
+    if isinstance(kv_len, torch.Tensor):
+        if kv_len.dtype != torch.int32 or kv_len.device != like.device:
+            kv_len = kv_len.to(device=like.device, dtype=torch.int32)
+        return kv_len.reshape(1)
+    return torch.tensor([int(kv_len)], dtype=torch.int32, device=like.device)
 
 
 def decode_eligible(q: torch.Tensor, k: torch.Tensor) -> bool:
@@ -65,9 +85,15 @@ def decode_attention(
     return_lse: bool = True,
     impl: str = "auto",
     pdl: int = 0,
+    kv_len=None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Launch the fused streaming decode kernel.  With ``comm`` (a ``_C.Comm``) the kernel also performs
     the cross-GPU tree combine and ``out``/``lse`` are the GLOBAL results, identical on every rank.
+
+    ``kv_len``: number of VALID rows of this shard (python int or 1-element int32 device tensor; default: all
+    ``k.shape[2]`` rows).  The kernels read it on the device at run time, so a CUDA graph captured once follows a
+    growing KV cache; rows past ``kv_len`` never enter the softmax.  For the tensor-core kernels (``tc`` / ``swap``)
+    the rows between ``kv_len`` and the end of its 128-row tile must hold finite values (zero-initialised caches do).
 
     ``impl``: ``"simt"`` (CUDA-core math; HBM-bound for one query row per KV head), ``"tc"`` (tcgen05: the
     (Hq/Hkv) x Sq rows of a KV head packed into one MMA tile; stays HBM-bound for GQA / multi-token decode),
@@ -96,7 +122,7 @@ def decode_attention(
         if lse is None and return_lse:
             lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
         C.decode_tc_fwd(q, k, v, out, lse, ws["part"], ws["tickets"], comm, float(softmax_scale), bool(causal),
-                        int(q_pos0), int(kv_pos0), impl == "swap")
+                        int(q_pos0), int(kv_pos0), impl == "swap", _kv_len_arg(kv_len, k))
         return out, lse
     grid, max_parts, rows, part_floats, _, _ = C.decode_plan(b, hq, hkv, sq, s, d)
     ws = _workspace(q.device, "decode", part_floats, b * hkv + 2)
@@ -105,8 +131,32 @@ def decode_attention(
     if lse is None and return_lse:
         lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
     C.decode_fwd(q, k, v, out, lse, ws["part"], ws["tickets"], comm, float(softmax_scale), bool(causal),
-                 int(q_pos0), int(kv_pos0), int(os.environ.get("TREE_ATTN_PDL", pdl)))
+                 int(q_pos0), int(kv_pos0), int(os.environ.get("TREE_ATTN_PDL", pdl)), _kv_len_arg(kv_len, k))
     return out, lse
+
+
+def decode_impl_for(q_shape, k_shape, impl: str = "auto") -> str:
+    """Which decode kernel ``decode_attention`` picks for these shapes (bf16 / fp16 KV)."""
+    import os
+
+    b, hq, sq, d = q_shape
+    rows_total = (hq // k_shape[1]) * sq
+    impl = os.environ.get("TREE_ATTN_DECODE_IMPL", impl)
+    if impl == "auto":
+        impl = "simt" if rows_total == 1 else ("swap" if (rows_total <= 16 and d == 128) else "tc")
+    return impl
+
+
+def decode_workspace_sizes(q_shape, k_shape, impl: str) -> Tuple[int, int]:
+    """(part floats, ticket ints) of the split-merge workspace for this problem."""
+    C = _build.load()
+    b, hq, sq, d = q_shape
+    hkv, s = k_shape[1], k_shape[2]
+    if impl in ("tc", "swap"):
+        part_floats = C.decode_tc_plan(b, hq, hkv, sq, s, d)[3]
+    else:
+        part_floats = C.decode_plan(b, hq, hkv, sq, s, d)[3]
+    return int(part_floats), b * hkv + 2
 
 
 def decode_attention_mxfp8(
@@ -119,6 +169,7 @@ def decode_attention_mxfp8(
     kv_pos0: int = 0,
     comm=None,
     return_lse: bool = True,
+    kv_len=None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Streaming decode over a block-scaled fp8 KV shard (``k``, ``v``: ``ops.quant.MXFP8Tensor``)."""
     C = _build.load()
@@ -130,7 +181,7 @@ def decode_attention_mxfp8(
     out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
     lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device) if return_lse else None
     C.decode_fwd_mx(q, k.data, v.data, k.scales, v.scales, out, lse, ws["part"], ws["tickets"], comm,
-                    float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0))
+                    float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0), _kv_len_arg(kv_len, k.data))
     return out, lse
 
 
@@ -145,6 +196,7 @@ def decode_attention_fp8(
     comm=None,
     return_lse: bool = True,
     impl: str = "auto",
+    kv_len=None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """tcgen05 (kind::f8f6f4) decode over a per-channel-scaled e4m3 KV shard (``ops.quant.FP8ChannelTensor``).
     ``impl``: ``"swap"`` (keys on the TMEM lanes, <= 16 packed query rows) or ``"tc"`` (query rows on the lanes)."""
@@ -164,7 +216,7 @@ def decode_attention_fp8(
     if impl == "auto":
         impl = "swap" if rows <= 16 else "tc"
     C.decode_tc_fwd8(q, k.data, v.data, k.scales, v.scales, out, lse, ws["part"], ws["tickets"], comm,
-                     float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0), impl == "swap")
+                     float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0), impl == "swap", _kv_len_arg(kv_len, k.data))
     return out, lse
 
 
@@ -178,6 +230,7 @@ def decode_attention_mx_tc(
     kv_pos0: int = 0,
     comm=None,
     return_lse: bool = True,
+    kv_len=None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Block-scaled fp8 KV cache on the tensor cores: ``k`` is an ``MXFP8Tensor`` (scales per 32 channels), ``v`` an
     ``MXFP8SeqTensor`` (scales per 32 keys); both GEMMs of the swap-AB decode kernel are
@@ -194,7 +247,7 @@ def decode_attention_mx_tc(
     out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
     lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device) if return_lse else None
     C.decode_mx_tc_fwd(q, k.data, v.data, k.scales.contiguous(), v.scales.contiguous(), out, lse, ws["part"], ws["tickets"],
-                       comm, float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0))
+                       comm, float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0), _kv_len_arg(kv_len, k.data))
     return out, lse
 
 
@@ -215,12 +268,21 @@ def attention_partial(
     q_pos0: int = 0,
     kv_pos0: int = 0,
     impl: str = "auto",
+    kv_len=None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Shard-local attention: returns ``(o, lse)`` with ``o`` in q's dtype (fp32 on CPU) and ``lse`` fp32."""
+    """Shard-local attention: returns ``(o, lse)`` with ``o`` in q's dtype (fp32 on CPU) and ``lse`` fp32.
+    ``kv_len`` (valid rows of the shard) is honoured on the device by the decode kernels; every other path slices."""
     scale = ref.default_scale(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
     if q.is_cuda:
         if impl in ("auto", "decode") and decode_eligible(q, k):
-            return decode_attention(q, k, v, scale, causal, q_pos0, kv_pos0)
+            return decode_attention(q, k, v, scale, causal, q_pos0, kv_pos0, kv_len=kv_len)
+    if kv_len is not None:
+        n = max(0, min(int(kv_len), k.shape[2]))   # (a device scalar is read back here: non-decode paths are not graph paths)
+        if n == 0:
+            o = torch.zeros(q.shape, dtype=q.dtype if q.is_cuda else torch.float32, device=q.device)
+            return o, torch.full(q.shape[:-1], float("-inf"), dtype=torch.float32, device=q.device)
+        k, v = k[:, :, :n], v[:, :, :n]
+    if q.is_cuda:
         if impl in ("auto", "fwd"):
             from . import flash
 

@@ -207,6 +207,7 @@ def tree_attention(
     schedule: str = "oneshot",
     layout: str = "bhsd",
     decode_pdl: int = 0,
+    kv_len=None,
 ) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
     """Exact attention of replicated ``q`` over a KV sequence sharded across the ranks of ``group``.
 
@@ -221,21 +222,30 @@ def tree_attention(
     decode steps overlap one step's drain (peer wait) with the next step's prologue; ``2`` also prefetches K/V
     before the dependency wait and requires that the KV cache was not written by the preceding kernel.
 
+    ``kv_len``: number of VALID rows of this rank's shard (python int or 1-element int32 device tensor; default: the
+    whole shard).  A preallocated, partially filled KV cache passes its fill level here: rows past it never enter
+    the softmax.  The decode kernels read the value on the device, so a CUDA graph captured once follows a growing
+    cache; ranks may have different (including zero) fill levels.
+
     Returns the global attention output (replicated, bitwise identical across ranks for the fused and
     symm backends) and optionally the global ``lse``.
     """
+    from ..ops.quant import FP8ChannelTensor, MXFP8Tensor
+
+    quantised = isinstance(k, (MXFP8Tensor, FP8ChannelTensor))
     if layout == "bshd":
+        if quantised:
+            raise ValueError("quantised KV caches are stored (B, H, S, D): pass q as (B, H, Sq, D) with layout='bhsd'")
         q, k, v = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
     elif layout != "bhsd":
         raise ValueError("layout must be 'bhsd' or 'bshd'")
     rank, world = _world(group)
     scale = ref.default_scale(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
     s_local = k.shape[2]
-    from ..ops.quant import FP8ChannelTensor, MXFP8Tensor
 
-    if isinstance(k, (MXFP8Tensor, FP8ChannelTensor)):  # fp8 KV cache (block-scaled MX or per-channel scaled)
+    if quantised:  # fp8 KV cache (block-scaled MX or per-channel scaled)
         return _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset, q_offset, return_lse,
-                                     backend, schedule)
+                                     backend, schedule, kv_len)
     kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
     q_pos0 = (world * s_local - q.shape[2]) if q_offset is None else int(q_offset)
     be = _resolve_backend(backend, q, world)
@@ -243,9 +253,9 @@ def tree_attention(
     if be == "local":
         with _nvtx("tree_attention/local"):
             if decode_pdl and local_ops.decode_eligible(q, k):
-                o, lse = local_ops.decode_attention(q, k, v, scale, causal, q_pos0, kv_pos0, pdl=decode_pdl)
+                o, lse = local_ops.decode_attention(q, k, v, scale, causal, q_pos0, kv_pos0, pdl=decode_pdl, kv_len=kv_len)
             else:
-                o, lse = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0)
+                o, lse = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0, kv_len=kv_len)
     elif be == "fused":
         if not q.is_cuda:
             raise RuntimeError("backend='fused' needs CUDA tensors")
@@ -256,15 +266,18 @@ def tree_attention(
             reg = symm.get_region("decode" if rows == 1 else "decode_tc", data, flags, group,
                                   layout=(b, hq, k.shape[1], sq, d))
             o, lse = local_ops.decode_attention(q, k, v, scale, causal, q_pos0, kv_pos0, comm=reg.comm,
-                                                return_lse=return_lse, pdl=decode_pdl)
+                                                return_lse=return_lse, pdl=decode_pdl, kv_len=kv_len)
         else:
             from ..ops import flash
 
+            if kv_len is not None:
+                raise NotImplementedError("kv_len with the fused prefill kernel: slice the shard instead (every rank "
+                                          "must still launch; an empty shard is not supported on this path)")
             o, lse = flash.attention_fwd_fused(q, k, v, scale, causal, q_pos0, kv_pos0, group=group,
                                                return_lse=return_lse)
     else:  # symm | collective
         with _nvtx("tree_attention/local_partial"):
-            o_p, lse_p = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0)
+            o_p, lse_p = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0, kv_len=kv_len)
         sched = schedule
         if be == "collective" and schedule == "oneshot":
             sched = "allgather"
@@ -277,7 +290,7 @@ def tree_attention(
 
 
 def _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset, q_offset, return_lse, backend,
-                          schedule):
+                          schedule, kv_len=None):
     """mxfp8 KV: fused streaming decode when eligible (CUDA, head_dim 128, few query rows); otherwise dequantise."""
     s_local = k.shape[2]
     kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
@@ -297,11 +310,12 @@ def _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset,
             comm = symm.get_region(fam, data, flags, group, layout=("fp8", per_channel, mx_tc, b, hq, k.shape[1], sq, d)).comm
         fn = (local_ops.decode_attention_fp8 if per_channel else
               local_ops.decode_attention_mx_tc if mx_tc else local_ops.decode_attention_mxfp8)
-        o, lse = fn(q, k, v, scale, causal, q_pos0, kv_pos0, comm=comm, return_lse=return_lse)
+        o, lse = fn(q, k, v, scale, causal, q_pos0, kv_pos0, comm=comm, return_lse=return_lse, kv_len=kv_len)
         return (o, lse) if return_lse else o
     dt = q.dtype if q.is_cuda else torch.float32
     return tree_attention(q, k.dequantize(dt), v.dequantize(dt), group=group, causal=causal, softmax_scale=scale,
-                          kv_offset=kv_pos0, q_offset=q_pos0, return_lse=return_lse, backend=backend, schedule=schedule)
+                          kv_offset=kv_pos0, q_offset=q_pos0, return_lse=return_lse, backend=backend, schedule=schedule,
+                          kv_len=kv_len)
 
 
 def tree_decode(
