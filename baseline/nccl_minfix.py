@@ -20,6 +20,14 @@ import torch.distributed as dist
 
 
 def local_partial(q, k, v, softmax_scale: float = 1.0):
+    hq, hkv = q.shape[1], k.shape[1]
+    if hq != hkv:
+        # GQA / MQA (not in the reference, which has one KV head per query head): fold the group into the query-row
+        # axis so the same two stock matmuls serve it -- (B, Hkv, G * Sq, D) x (B, Hkv, T, D); no KV copy is made.
+        b, _, sq, d = q.shape
+        g = hq // hkv
+        res, lse = local_partial(q.reshape(b, hkv, g * sq, d), k, v, softmax_scale)
+        return res.reshape(b, hq, sq, d), lse.reshape(b, hq, sq)
     s = torch.matmul(q, k.transpose(-2, -1)) * softmax_scale
     lse = torch.logsumexp(s.float(), dim=-1)
     p = torch.softmax(s, dim=-1)

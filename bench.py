@@ -15,7 +15,16 @@ own public API on BHSD tensors.  For N > 1 it raises at model.py:111 (SURVEY.md 
 Timing rules implemented here: W >= 3 warm-ups; CUDA events on the launching stream bracketed by barrier +
 synchronize; max over ranks; the KV working set cycled per step is > 4x the 126 MB L2 (several KV buffers
 are rotated like layers of a model) so no step is served from L2; SM clocks / throttle reasons are sampled
-with nvidia-smi DURING the timed region.
+with nvidia-smi DURING the timed region.  Multi-GPU: after the host barrier every rank enqueues TWO untimed steps
+before the start event -- each step ends with an all-to-all, so the ranks leave it together and the host-side
+start skew of the barrier (hundreds of microseconds, i.e. several steps) is absorbed on the device instead of
+being charged to a K = 20 timed region.  Both arms, and the NCCL-structured comparator, use the same loop.
+
+Extra blocks of the JSON line (they explain the headline; the driver reads value / e2e):
+``vs_minfix`` (N > 1): the runnable "reference's own NCCL build" -- baseline/nccl_minfix.py, the reference's structure
+with its four documented defects fixed -- same steps / warm-up / KV rotation, with clocks, and own / minfix.
+``baseline_configs`` (N = 8, or --heavy on): the other BASELINE.json configs -- full-Sq 128K forward, 256K block-scaled
+fp8 decode on tcgen05, 1M GQA forward+backward -- each with latency, roofline fraction and clocks.
 """
 from __future__ import annotations
 
@@ -53,8 +62,12 @@ def parse_args():
     p.add_argument("--graph", action=argparse.BooleanOptionalAction, default=True,
                    help="replay the step from a CUDA graph (launch-bound at 8 GPUs)")
     p.add_argument("--pdl", action=argparse.BooleanOptionalAction, default=True,
-                   help="device-timed loop: eager launches chained by programmatic dependent launch (the e2e loop, which "
+                   help="device-timed loop: prepared launches chained by programmatic dependent launch (the e2e loop, which "
                         "synchronises every step, replays the CUDA graph)")
+    p.add_argument("--heavy", default="auto", choices=["auto", "on", "off"],
+                   help="also measure the other BASELINE.json configs (full-Sq 128K forward, 256K fp8, 1M GQA fwd+bwd); "
+                        "auto = only on 8 GPUs")
+    p.add_argument("--align", type=int, default=2, help="untimed steps enqueued between the host barrier and the start event")
     return p.parse_args()
 
 
@@ -126,6 +139,53 @@ def reexec_with_torchrun(args):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
     os.execv(sys.executable, cmd)
+
+
+def timed_loop(torch, dist, step_fn, steps, warmup, align, world, dev, barrier, sampler=None):
+    """warm-up -> host barrier -> `align` untimed steps (device-side alignment of the ranks) -> [event | K steps | event]
+    -> max over ranks.  Returns (ms total, (wall t0, wall t1))."""
+    for i in range(warmup):
+        step_fn(i)
+    barrier()
+    t0w = time.time()
+    for i in range(align):
+        step_fn(warmup + i)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step_fn(warmup + align + i)
+    e1.record()
+    torch.cuda.synchronize()
+    t1w = time.time()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), (t0w, t1w)
+
+
+def sampled_clocks(torch, dist, sampler, window, step_fn, ms_per_step, steps, world, dev, barrier):
+    """Clock record of a timed region; when it was too short for nvidia-smi (50 ms period), an identical loop is run for
+    ~1.5 s right after it and sampled instead (and the record says so)."""
+    source = "nvidia-smi during the timed region"
+    clocks = sampler.summary(*window) if sampler is not None else None
+    need = torch.tensor([1 if (clocks is not None and clocks["samples"] < 3) else 0], device=dev)
+    if world > 1:
+        dist.broadcast(need, 0)
+    if int(need.item()):
+        reps = max(steps, int(1.5e3 / max(ms_per_step, 1e-3)))
+        barrier()
+        p0 = time.time()
+        for i in range(reps):
+            step_fn(i)
+        torch.cuda.synchronize()
+        p1 = time.time()
+        if sampler is not None:
+            clocks = sampler.summary(p0, p1)
+            source = f"nvidia-smi during an identical {reps}-step loop run right after the timed region (too short to sample)"
+    if clocks is not None:
+        clocks["source"] = source
+    return clocks
 
 
 def main():
@@ -214,21 +274,8 @@ def main():
             ta.cleanup()
             return 0
         sampler = ClockSampler(local_rank) if rank == 0 else None
-        barrier()
-        t0w = time.time()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            ref_step(i)
-        e1.record()
-        torch.cuda.synchronize()
-        t1w = time.time()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+        ms, window = timed_loop(torch, dist, ref_step, steps, 0, args.align, world, dev, barrier)
+        clocks = sampled_clocks(torch, dist, sampler, window, ref_step, ms / steps, steps, world, dev, barrier)
         # e2e: pinned q -> device, step, result -> pinned host, every step
         qh = q.cpu().pin_memory()
         oh = torch.empty((B, Hq, 1, D), dtype=dtype).pin_memory()
@@ -243,10 +290,8 @@ def main():
             torch.cuda.synchronize()
         te1 = time.perf_counter()
         e2e_ms = (te1 - te0) * 1e3
-        clocks = None
         if sampler is not None:
             sampler.stop()
-            clocks = sampler.summary(t0w, t1w)
         if rank == 0:
             lat = ms / steps
             emit({"impl": "reference", "metric": metric, "value": B * S / (lat * 1e-3), "unit": "tokens/s",
@@ -269,10 +314,10 @@ def main():
     from tree_attention_b200.models.decoder import TreeDecodeSession
 
     sess = TreeDecodeSession(kvs, softmax_scale=scale, backend=args.backend, use_graph=args.graph, pdl=args.pdl)
-    launches_per_step = sess.launches_per_step
 
     # correctness gate before timing (never time a wrong kernel)
     out = sess.step_device(q, 0)
+    launches_per_step = sess.launches_per_step
     o_p, l_p = ref.attention_partial_ref(q, kvs[0][0], kvs[0][1], scale, False, 0, 0, torch.float32, block=16384)
     if world > 1:
         packed = torch.cat([o_p, l_p[..., None]], -1).contiguous()
@@ -289,46 +334,10 @@ def main():
         return 1
 
     sess.q_static.copy_(q)
-    for i in range(warmup):
-        sess.step_device(None, i)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    t0w = time.time()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        sess.step_device(None, i)
-    e1.record()
-    torch.cuda.synchronize()
-    t1w = time.time()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    clock_source = "nvidia-smi during the timed region"
-    clocks = None
-    if sampler is not None:
-        clocks = sampler.summary(t0w, t1w)
-    need_probe = torch.tensor([1 if (clocks is not None and clocks["samples"] < 3) else 0], device=dev)
-    if world > 1:
-        dist.broadcast(need_probe, 0)
-    if int(need_probe.item()):
-        # timed region too short for a 50 ms sampler: repeat the identical loop for ~1.5 s and sample that
-        reps = max(steps, int(1.5e3 / max(ms / steps, 1e-3)))
-        barrier()
-        p0 = time.time()
-        for i in range(reps):
-            sess.step_device(None, i)
-        torch.cuda.synchronize()
-        p1 = time.time()
-        if sampler is not None:
-            clocks = sampler.summary(p0, p1)
-            clock_source = f"nvidia-smi during an identical {reps}-step loop run right after the timed region (too short to sample)"
-    if sampler is not None:
-        sampler.stop()
-        clocks["source"] = clock_source
+    own_step = lambda i: sess.step_device(None, i)
+    ms, window = timed_loop(torch, dist, own_step, steps, warmup, args.align, world, dev, barrier)
+    clocks = sampled_clocks(torch, dist, sampler, window, own_step, ms / steps, steps, world, dev, barrier)
 
     # end-to-end through the public API: pinned host q -> device, step, result -> pinned host, every step
     e2e = sess.run_e2e(q, steps, barrier)
@@ -338,8 +347,36 @@ def main():
     e2e_lat = float(e2e_ms.item()) / steps
 
     extras = {}
+    if world > 1 and not args.no_extras:
+        # the runnable "reference's own NCCL build" on the same box, same loop, with its own clock record
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import nccl_minfix
+
+            mf_step = lambda i: nccl_minfix.tree_decode_minfix(q, kvs[i % nbuf][0], kvs[i % nbuf][1], scale)
+            mf_ms, mf_window = timed_loop(torch, dist, mf_step, steps, warmup, args.align, world, dev, barrier)
+            mf_clocks = sampled_clocks(torch, dist, sampler, mf_window, mf_step, mf_ms / steps, steps, world, dev, barrier)
+            mf_lat = mf_ms / steps
+            extras["vs_minfix"] = {
+                "impl": "baseline/nccl_minfix.py: the reference's structure (stock torch matmul/softmax + all_reduce MAX, SUM, SUM "
+                        "on NCCL) with its four documented defects fixed; the verbatim reference raises at model.py:111 for N > 1",
+                "ms_per_step": mf_lat, "value": B * S / (mf_lat * 1e-3), "unit": "tokens/s", "steps": steps, "warmup": warmup,
+                "own_ms_per_step": ms / steps, "ratio_own_over_minfix": mf_lat / (ms / steps), "clocks": mf_clocks,
+            }
+        except Exception as e:
+            extras["vs_minfix"] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    if sampler is not None:
+        sampler.stop()
     if not args.no_extras:
-        extras = run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier)
+        extras.update(run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier))
+        heavy = args.heavy == "on" or (args.heavy == "auto" and world == 8)
+        if heavy:
+            try:
+                from bench_tools import configs as heavy_configs
+
+                extras["baseline_configs"] = heavy_configs.run_all(ta, world, rank, dev, barrier, ROOT)
+            except Exception as e:
+                extras["baseline_configs"] = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     if rank == 0:
         lat = ms / steps
@@ -354,12 +391,15 @@ def main():
             "metric": metric, "value": B * S / (lat * 1e-3), "unit": "tokens/s", "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": lat, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": config, "clocks": clocks,
+            "timing": f"CUDA events around {steps} steps after {warmup} warm-ups; {args.align} untimed step(s) between the host barrier "
+                      "and the start event align the ranks on the device (every step ends with an all-to-all); max over ranks",
             "e2e": {"value": B * S / (e2e_lat * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_lat,
                     "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]},
             "gpu_launches": launches_per_step * steps,
             "decode_tokens_per_s": B / (lat * 1e-3),
             "hbm_gbs_per_gpu": gbs, "hbm_frac_of_measured": gbs / hbm,
             "max_abs_err_vs_oracle": err, "backend": args.backend, "cuda_graph": bool(sess.graphs), "pdl": bool(args.pdl),
+            "launch_path": "prepared C++ launch (_C.DecodeStep), one cudaLaunchKernelEx per step" if getattr(sess, "_steps", None) else "python",
             **extras,
         })
     ta.cleanup()
@@ -393,14 +433,9 @@ def run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier):
     try:
         if sess.graphs:
             out["graph_replay_ms_per_step"] = timeit(lambda i: sess.graphs[i % nb].replay(), steps=200)
-        out["eager_launch_ms_per_step"] = timeit(
+        out["python_api_launch_ms_per_step"] = timeit(
             lambda i: ta.tree_attention(q, kvs[i % nb][0], kvs[i % nb][1], softmax_scale=scale, backend=args.backend))
         if world > 1:
-            sys.path.insert(0, os.path.join(ROOT, "baseline"))
-            import nccl_minfix
-
-            out["nccl_minfix_ms_per_step"] = timeit(
-                lambda i: nccl_minfix.tree_decode_minfix(q, kvs[i % nb][0], kvs[i % nb][1], scale))
             out["own_kernel_plus_nccl_allreduce3_ms_per_step"] = timeit(
                 lambda i: ta.tree_attention(q, kvs[i % nb][0], kvs[i % nb][1], softmax_scale=scale, backend="nccl",
                                             schedule="allreduce3"))
@@ -413,8 +448,7 @@ def run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier):
         out["mxfp8_kv_max_abs_diff_vs_bf16"] = float((o8.float() - o16.float()).abs().max())
         out["mxfp8_kv_eager_ms_per_step"] = timeit(
             lambda i: ta.tree_attention(q, kq, vq, softmax_scale=scale, backend=args.backend), steps=200)
-        if world == 1 and q.shape[-1] == 128 and (q.shape[1] // kvs[0][0].shape[1]) * q.shape[2] <= 16:
-            # (single-GPU extra; the multi-GPU fused fp8 paths are covered by tests/test_gpu_multi.py)
+        if q.shape[-1] == 128 and (q.shape[1] // kvs[0][0].shape[1]) * q.shape[2] <= 16:
             # the same MX cache with V blocked along the keys: both GEMMs on tcgen05.mma.kind::mxf8f6f4.block_scale
             from tree_attention_b200.ops.quant import FP8ChannelTensor, MXFP8SeqTensor
 
@@ -428,23 +462,21 @@ def run_extras(args, ta, sess, q, kvs, scale, world, rank, dev, barrier):
                 lambda i: ta.tree_attention(q, kc, vc, softmax_scale=scale, backend=args.backend), steps=200)
             del vs, kc, vc
         del kq, vq
-        if world > 1:
-            from tree_attention_b200.parallel import symm
-
-            reg = symm.regions().get(("decode", 0))
-            if reg is not None:
-                reg.combine_stamps(reset=True)
-                for i in range(200):
-                    sess.step_device(None, i)
-                torch.cuda.synchronize()
-                st = reg.combine_stamps(reset=True)
-                B_, Hq_, D_ = q.shape[0], q.shape[1], q.shape[3]
-                recv = (world - 1) * B_ * Hq_ * (D_ + 4) * 4
-                out["combine_step"] = {
-                    **st, "bytes_received_per_rank": recv,
-                    "nvlink_gbs_per_combine_step": recv / max(st["combine_step_ns"], 1),
-                    "note": "in-kernel globaltimer stamps, max over CTAs and 200 steps: publish -> merged output written",
-                }
+        reg = getattr(sess, "region", None)
+        if world > 1 and reg is not None:
+            reg.combine_stamps(reset=True)
+            for i in range(200):
+                sess.step_device(None, i)
+            torch.cuda.synchronize()
+            st = reg.combine_stamps(reset=True)
+            B_, Hq_, D_ = q.shape[0], q.shape[1], q.shape[3]
+            recv = (world - 1) * B_ * Hq_ * (D_ + 1) * 8
+            out["combine_step"] = {
+                **st, "bytes_received_per_rank": recv,
+                "nvlink_gbs_per_combine_step": recv / max(st["combine_step_ns"], 1),
+                "note": "in-kernel globaltimer stamps, max over CTAs and 200 steps: publish -> merged output written; "
+                        "payload = (W-1) x heads x (D+1) tagged 8-byte words per rank",
+            }
     except Exception as e:  # extras must never take the headline down
         out["extras_error"] = f"{type(e).__name__}: {e}"[:200]
     return out

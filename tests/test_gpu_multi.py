@@ -269,3 +269,63 @@ def _worker_reduce_and_bwd(rank, world):
 @need2
 def test_symm_allreduce_and_distributed_backward(port):
     run_distributed(_worker_reduce_and_bwd, min(NGPU, 4) if NGPU >= 4 else 2, port)
+
+
+def _worker_fill_levels(rank, world):
+    """Ragged, device-resident fill levels across ranks (one rank EMPTY), fused decode kernels + TreeDecodeSession on the
+    native fast path: every rank must still publish (the identity for an empty shard) and the result must equal
+    attention over the filled rows only; an append on one rank is picked up by the captured graphs."""
+    import torch.distributed as dist
+    import tree_attention_b200 as ta
+    from tree_attention_b200.models.decoder import TreeDecodeSession
+    from tree_attention_b200.ops import reference as ref
+
+    dev = torch.device("cuda", rank)
+    cap = 4096
+    lens = [cap, 1000, 0, 77, 129, 4095, 1, 2048][:world]
+    if world == 2:
+        lens = [1000, 0]
+    for hq, hkv in [(16, 16), (16, 4)]:        # CUDA-core streaming kernel / tcgen05 swap-AB kernel
+        q, k, v = ta.make_data((1, hq, cap, 128), rank, dev, dtype=torch.bfloat16, num_kv_heads=hkv, log=False)
+        n = lens[rank]
+        k[:, :, n:] = 0
+        v[:, :, n:] = 0
+        sess = TreeDecodeSession([(k, v)], softmax_scale=0.088, q_shape=(1, hq, 1, 128), kv_lens=[n], backend="fused")
+
+        def oracle():
+            cur = torch.tensor([sess.kv_len_host[0]], device=dev)
+            all_lens = [torch.empty_like(cur) for _ in range(world)]
+            dist.all_gather(all_lens, cur)
+            ks = [torch.empty_like(k) for _ in range(world)]
+            vs = [torch.empty_like(v) for _ in range(world)]
+            dist.all_gather(ks, k)
+            dist.all_gather(vs, v)
+            kf = torch.cat([ks[r][:, :, : int(all_lens[r])] for r in range(world)], 2)
+            vf = torch.cat([vs[r][:, :, : int(all_lens[r])] for r in range(world)], 2)
+            return ref.attention_partial_ref(q, kf, vf, 0.088, False, 0, 0, torch.float32)[0]
+
+        out = sess.step_device(q, 0).clone()
+        torch.cuda.synchronize()
+        assert (out.float() - oracle()).abs().max().item() < 2e-2, (hq, hkv, "initial")
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        for it in range(3):
+            owner = (it + 1) % world
+            if rank == owner and sess.kv_len_host[0] + 5 <= cap:
+                k_new = torch.randn(1, hkv, 5, 128, device=dev, generator=g).bfloat16()
+                v_new = torch.randn(1, hkv, 5, 128, device=dev, generator=g).bfloat16()
+                sess.append_kv(0, k_new, v_new)
+            out = sess.step_device(q, 0).clone()
+            torch.cuda.synchronize()
+            assert (out.float() - oracle()).abs().max().item() < 2e-2, (hq, hkv, it)
+            outs = [torch.empty_like(out) for _ in range(world)]
+            dist.all_gather(outs, out.contiguous())
+            for o in outs:
+                assert torch.equal(o, outs[0]), "fill levels: ranks disagree bitwise"
+        sess.region.check()
+        sess.close()
+
+
+@need2
+@pytest.mark.parametrize("world", WORLDS)
+def test_fused_decode_ragged_fill_levels(world, port):
+    run_distributed(_worker_fill_levels, world, port)

@@ -185,7 +185,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
               umma_ss_f16(d_tmem, q_desc0 + off, k_desc0 + off, idesc_qk, kk > 0 ? 1u : 0u);
             }
           }
-          umma_commit(&k_empty[st]);
+          if (j + NS < n_tiles) umma_commit(&k_empty[st]);   // only when the producer will refill this stage: no arrival is left un-waited
           umma_commit(&s_full[j & 1]);
         }
         __syncwarp();
@@ -205,7 +205,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 #pragma unroll
           for (int kk = 0; kk < kBlockN / 16; ++kk)
             umma_ts_f16(tmem_o, p_tmem + kk * 8, v_desc0 + ((kk * 2048) >> 4), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(&v_empty[st]);
+          if (j + NS < n_tiles) umma_commit(&v_empty[st]);
           umma_commit(&pv_done[j & 1]);
         }
         __syncwarp();
@@ -372,6 +372,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     }
     // ------------------------------- epilogue --------------------------------------------------
     const int jl = n_tiles - 1;
+    // both PV barriers are waited to their final phase: the MMAs retire in order, so the second wait is free, and no
+    // barrier phase is left completed-but-never-waited at CTA exit (compute-sanitizer synccheck "Missing wait", round 1)
+    if (jl >= 1) mbar_wait(&pv_done[(jl - 1) & 1], ((jl - 1) >> 1) & 1);
     mbar_wait(&pv_done[jl & 1], (jl >> 1) & 1);
     tc_fence_after();
     const float inv_l = l_sum > 0.f ? 1.f / l_sum : 0.f;
