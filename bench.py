@@ -394,7 +394,8 @@ def main():
             "timing": f"CUDA events around {steps} steps after {warmup} warm-ups; {args.align} untimed step(s) between the host barrier "
                       "and the start event align the ranks on the device (every step ends with an all-to-all); max over ranks",
             "e2e": {"value": B * S / (e2e_lat * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_lat,
-                    "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"]},
+                    "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                    "per_step_ms_rank0": {"median": e2e["median_ms"], "min": e2e["min_ms"], "max": e2e["max_ms"]}},
             "gpu_launches": launches_per_step * steps,
             "decode_tokens_per_s": B / (lat * 1e-3),
             "hbm_gbs_per_gpu": gbs, "hbm_frac_of_measured": gbs / hbm,

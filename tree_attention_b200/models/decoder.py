@@ -155,9 +155,7 @@ class TreeDecodeSession:
             self._kv_dirty = False
             self._steps[layer].launch(pdl)
             return self.out_static[layer]
-        out = self._eager(self.q_static, layer, use_pdl)
-        self.out_static[layer] = out
-        return out
+        return self._eager(self.q_static, layer, use_pdl)   # a fresh output tensor per call (graph capture pins it)
 
     def _prepare(self) -> None:
         if self._prepared:
@@ -165,7 +163,7 @@ class TreeDecodeSession:
         if self._fast:
             self._prepare_fast()
         for i in range(len(self.kv)):  # first launches: allocates workspaces and (collectively) symmetric regions
-            self._launch(i)
+            self.out_static[i] = self._launch(i)
         if self.device.type == "cuda":
             torch.cuda.synchronize()
         if self._use_graph:
@@ -174,7 +172,7 @@ class TreeDecodeSession:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.stream(side):
                     with torch.cuda.graph(g):
-                        self._launch(i)
+                        self.out_static[i] = self._launch(i)
                 self.graphs.append(g)
             torch.cuda.synchronize()
             self.q_host = torch.empty(self.q_shape, dtype=self.dtype).pin_memory()
@@ -200,11 +198,13 @@ class TreeDecodeSession:
         if q is not None and q.data_ptr() != self.q_static.data_ptr():
             self.q_static.copy_(q, non_blocking=True)
         if self.pdl:  # throughput path: launches chained by programmatic dependent launch
-            return self._launch(layer, use_pdl=True)
+            self.out_static[layer] = self._launch(layer, use_pdl=True)
+            return self.out_static[layer]
         if self.graphs:
             self.graphs[layer].replay()
             return self.out_static[layer]
-        return self._launch(layer)
+        self.out_static[layer] = self._launch(layer)
+        return self.out_static[layer]
 
     def step(self, q_host: torch.Tensor, out_host: torch.Tensor, layer: int) -> torch.Tensor:
         """End-to-end (latency) step: pinned host query -> device, attention, result -> pinned host, synchronised.
@@ -265,15 +265,23 @@ class TreeDecodeSession:
             self.region = None
 
     def run_e2e(self, q: torch.Tensor, steps: int, barrier) -> dict:
+        """Time ``steps`` end-to-end steps (host clock around the whole loop; per-step times are kept for diagnosis)."""
         self._prepare()
         qh = q.detach().cpu().pin_memory()
         oh = torch.empty(self.q_shape, dtype=self.dtype).pin_memory()
         for i in range(3):
             self.step(qh, oh, i)
         barrier()
+        per = []
         t0 = time.perf_counter()
+        tp = t0
         for i in range(steps):
             self.step(qh, oh, i)
+            tn = time.perf_counter()
+            per.append((tn - tp) * 1e3)
+            tp = tn
         t1 = time.perf_counter()
         barrier()
-        return {"ms": (t1 - t0) * 1e3, "h2d": qh.numel() * qh.element_size(), "d2h": oh.numel() * oh.element_size()}
+        per.sort()
+        return {"ms": (t1 - t0) * 1e3, "h2d": qh.numel() * qh.element_size(), "d2h": oh.numel() * oh.element_size(),
+                "median_ms": per[len(per) // 2], "max_ms": per[-1], "min_ms": per[0]}
