@@ -54,7 +54,7 @@ def _timed(torch, dist, fn, steps, warmup, world, dev, barrier):
     return float(t.item()), (t0w, t1w)
 
 
-def run_all(ta, world, rank, dev, barrier, root, only=None, sampler=None):
+def run_all(ta, world, rank, dev, barrier, root, only=None, sampler=None, scale_down=1):
     import torch
     import torch.distributed as dist
 
@@ -81,7 +81,7 @@ def run_all(ta, world, rank, dev, barrier, root, only=None, sampler=None):
     # ------------------------------------------------------------------------------------------ (a) full-Sq forward
     if want("fwd_128k_bf16"):
         try:
-            S, H, D = 131072, 32, 128
+            S, H, D = 131072 // scale_down, 32, 128
             s_local = S // world
             g = torch.Generator(device=dev).manual_seed(77)
             q = torch.randn(1, H, S, D, device=dev, generator=g).to(torch.bfloat16)   # same seed on every rank: replicated Q
@@ -127,7 +127,7 @@ def run_all(ta, world, rank, dev, barrier, root, only=None, sampler=None):
         try:
             from tree_attention_b200.ops.quant import MXFP8SeqTensor, MXFP8Tensor
 
-            S, H, D = 262144, 32, 128
+            S, H, D = 262144 // scale_down, 32, 128
             s_local = S // world
             g = torch.Generator(device=dev).manual_seed(78)
             q = torch.randn(1, H, 1, D, device=dev, generator=g).to(torch.bfloat16)
@@ -169,7 +169,7 @@ def run_all(ta, world, rank, dev, barrier, root, only=None, sampler=None):
             from tree_attention_b200.ops.autograd import tree_attention_func
             from tree_attention_b200.parallel.tree import allreduce_sum
 
-            S, H, HKV, D = 1 << 20, 32, 8, 128
+            S, H, HKV, D = (1 << 20) // scale_down, 32, 8, 128
             s_local = S // world
             g = torch.Generator(device=dev).manual_seed(79)
             q = torch.randn(1, H, S, D, device=dev, generator=g).to(torch.bfloat16).requires_grad_(True)
@@ -210,7 +210,7 @@ def run_all(ta, world, rank, dev, barrier, root, only=None, sampler=None):
             del do
             torch.cuda.empty_cache()
             if world > 1:   # the backward's reduce on its own: 1 GiB of fp32 per rank
-                x = torch.randn(1 << 28, device=dev, dtype=torch.float32)
+                x = torch.randn((1 << 28) // scale_down, device=dev, dtype=torch.float32)
                 t_own, _ = _timed(torch, dist, lambda: allreduce_sum(x), 5, 2, world, dev, barrier)
                 y = x.clone()
                 t_nccl, _ = _timed(torch, dist, lambda: dist.all_reduce(y), 5, 2, world, dev, barrier)
@@ -239,6 +239,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/configs.json")
     ap.add_argument("--only", nargs="*", default=None)
+    ap.add_argument("--scale-down", type=int, default=1, help="divide every sequence length (smoke-testing the runner on fewer GPUs)")
     a = ap.parse_args()
     import tree_attention_b200 as ta
 
@@ -252,12 +253,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    res = run_all(ta, world, rank, dev, barrier, ROOT, only=a.only)
+    res = run_all(ta, world, rank, dev, barrier, ROOT, only=a.only, scale_down=a.scale_down)
     if rank == 0:
         os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
         with open(a.out, "w") as f:
-            json.dump({"world": world, **res}, f, indent=1)
-        print(json.dumps({"world": world, **res}))
+            json.dump({"world": world, "scale_down": a.scale_down, **res}, f, indent=1)
+        print(json.dumps({"world": world, "scale_down": a.scale_down, **res}))
     ta.cleanup()
 
 

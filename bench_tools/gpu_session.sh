@@ -65,6 +65,8 @@ for st in $STEPS; do
       timeout 600 python bench_tools/bench_bwd.py --seq 16384 > "$OUT/bench_bwd.log" 2>&1; echo "rc=$?"; tail -n 4 "$OUT/bench_bwd.log";;
     fwd_phases)
       timeout 300 python bench_tools/prof_fwd_phases.py > "$OUT/fwd_phases.log" 2>&1; echo "rc=$?"; tail -n 4 "$OUT/fwd_phases.log";;
+    bench1)    # same-box 1-GPU reference point for the scaling efficiency (boxes differ by several percent)
+      CUDA_VISIBLE_DEVICES=0 timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-extras > "$OUT/bench20_own_1_samebox.json" 2> "$OUT/bench20_own_1_samebox.err"; echo "own20 n=1 rc=$?"; tail -n 1 "$OUT/bench20_own_1_samebox.json" | cut -c1-500;;
     bench20)   # the driver's own invocation: 20 timed steps, 5 warm-ups, both arms
       if [ "$NG" -ge 2 ]; then
         timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29841 bench.py --gpus $NG --steps 20 --warmup 5 > "$OUT/bench20_own_$NG.json" 2> "$OUT/bench20_own_$NG.err"; echo "own20 n=$NG rc=$?"; tail -n 1 "$OUT/bench20_own_$NG.json" | cut -c1-1500; tail -n 3 "$OUT/bench20_own_$NG.err" | cut -c1-300
@@ -78,7 +80,7 @@ for st in $STEPS; do
     sanitize)
       bash bench_tools/sanitize.sh ${SAN_TOOLS:-memcheck synccheck} > "$OUT/sanitize.log" 2>&1; mkdir -p "$OUT/sanitize"; cp gpurun_out/sanitize/* "$OUT/sanitize/" 2>/dev/null; cat gpurun_out/sanitize/summary.txt;;
     configs)
-      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29844 bench_tools/configs.py --out "$OUT/configs_$NG.json" > "$OUT/configs_$NG.log" 2>&1; echo "rc=$?"; tail -n 3 "$OUT/configs_$NG.log" | cut -c1-2500;;
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29844 bench_tools/configs.py --scale-down ${CONFIGS_SCALE:-1} --out "$OUT/configs_$NG.json" > "$OUT/configs_$NG.log" 2>&1; echo "rc=$?"; tail -n 3 "$OUT/configs_$NG.log" | cut -c1-2500;;
     cli)   # the reference UX on hardware: zero-arg spawn over every visible GPU, then torchrun --json
       timeout 300 python3 model.py > "$OUT/cli_zero_arg_$NG.log" 2>&1; echo "model.py rc=$?" | tee -a "$OUT/cli_zero_arg_$NG.log"; tail -n 6 "$OUT/cli_zero_arg_$NG.log" | cut -c1-300
       timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29845 model.py --json > "$OUT/cli_torchrun_$NG.log" 2>&1; echo "torchrun model.py rc=$?" | tee -a "$OUT/cli_torchrun_$NG.log"; tail -n 3 "$OUT/cli_torchrun_$NG.log" | cut -c1-600;;

@@ -37,8 +37,8 @@ struct DecodeParams {
   float* lse;
   const uint32_t* kscale;  // KV8 only: (B, Hkv, S) words of 4 UE8M0 scales (one per 32 elements of D = 128)
   const uint32_t* vscale;
-  float* part;
-  uint32_t* tickets;  // [BH] tickets, [BH] = done-CTA counter
+  uint64_t* part;             // workspace: tagged partial words (decode_comm.cuh)
+  unsigned long long* wctr;   // workspace arrival counter (launch tag of the partial words), zero-initialised once
   const int* kv_len;  // optional device scalar: valid rows of this shard (<= S); read by the kernel => graph-replayable
   int B, Hq, Hkv, G, Sq, S;   // S = capacity of the shard (rows covered by the tensor maps)
   int rows_valid;     // G * Sq - r_base, clipped to R
@@ -108,7 +108,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   float* p_s = q_s + R * D;                                                    // [warps][(blk)][R][16]
   float* merge_s = p_s + kConsumerWarps * L::kPsPerWarp * R * kRowsPerWarp;    // [warps][R][D+4]
   int* pending = reinterpret_cast<int*>(merge_s + kConsumerWarps * R * (D + 4));
-  int* s_misc = pending + kMaxPending;  // [0]=ticket, [1]=n_pending, [2]=head+1 to combine inline
+  int* s_misc = pending + kMaxPending;  // [0]=n_pending, [1]=scratch, [4]=intra-GPU tag, [5]=cross-GPU tag, [6]=tags ready
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_misc + 8);
   uint64_t* empty_bar = full_bar + NS;
   uint64_t* stamps = empty_bar + NS;   // [0] CTA start, [1] last publish (globaltimer, thread 0)
@@ -125,7 +125,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       mbar_init(&empty_bar[i], kConsumerWarps);
     }
     fence_mbar_init();
-    s_misc[1] = 0; s_misc[2] = 0;
+    s_misc[0] = 0; s_misc[1] = 0; s_misc[6] = 0;
   }
   if (warp == kConsumerWarps && lane == 0) {
     tma_prefetch_desc(&kmap);
@@ -153,12 +153,27 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       if (p.pdl == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
       const dcomm::Geom geo = dcomm::make_geom(p.S, p.kv_len, BH, gridDim.x);
       const int t_lo = dcomm::cta_lo(geo, cta), t_hi = dcomm::cta_lo(geo, cta + 1);
-      int stage = 0;
+      int stage = 0, issued = 0;
       uint32_t phase = 0;
+      bool tags_done = false;
+      // launch tags (decode_comm.cuh): the arrival atomics are issued once the ring is full -- the producer would block
+      // on the first `empty` barrier anyway, and no consumer can free a stage before the dependency of a programmatic
+      // launch has resolved -- so their round trip is never exposed; consumers pick the tags up at their first segment end
+      auto fetch_tags = [&]() {
+        if (p.pdl == 2) asm volatile("griddepcontrol.wait;" ::: "memory");
+        const uint32_t wtag = dcomm::launch_tag(p.wctr);
+        const uint32_t ctag = world > 1 ? dcomm::launch_tag(reinterpret_cast<unsigned long long*>(p.comm.epoch)) : 0u;
+        volatile int* sm = s_misc;
+        sm[4] = (int)wtag; sm[5] = (int)ctag;
+        __threadfence_block();
+        sm[6] = 1;
+        tags_done = true;
+      };
       for (int t = t_lo; t < t_hi; ++t) {
         const int x = t / geo.tph, j = t - x * geo.tph;
         if (!tile_visible(j)) continue;
         const int b = x / p.Hkv, h = x - b * p.Hkv;
+        if (issued == NS && !tags_done) fetch_tags();
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
         uint8_t* ks = stage_base + size_t(stage) * L::kStageBytes;
@@ -168,19 +183,16 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
           tma_load_4d(ks + a * (kTileRows * 128), &kmap, &full_bar[stage], a * (128 / L::kElem), j * kTileRows, h, b);
           tma_load_4d(vs + a * (kTileRows * 128), &vmap, &full_bar[stage], a * (128 / L::kElem), j * kTileRows, h, b);
         }
+        ++issued;
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
+      if (!tags_done) fetch_tags();
     }
     return;
   }
 
   // --------------------------------- consumers ----------------------------------------------
   if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-  // The epoch of this launch.  Every CTA reads the counter before any CTA of THIS launch can have bumped it (the
-  // bump happens after all CTAs passed their end-of-kernel arrival) and, under PDL, after the previous launch
-  // has completed (griddepcontrol.wait above).
-  uint32_t epoch = 0;
-  if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
   const dcomm::Geom geo = dcomm::make_geom(p.S, p.kv_len, BH, gridDim.x);
   const int t_lo = dcomm::cta_lo(geo, cta), t_hi = dcomm::cta_lo(geo, cta + 1);
   constexpr int RB = R;  // rows of one output channel gathered per batch of the cross-GPU merge (R <= 4)
@@ -188,8 +200,10 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   // built on demand (kept out of the streaming loop's live registers)
   auto make_tail = [&]() {
     dcomm::Tail tl;
-    tl.comm = &p.comm; tl.part = p.part; tl.tickets = p.tickets; tl.max_parts = p.max_parts; tl.BH = BH;
-    tl.R = R; tl.rows_valid = p.rows_valid; tl.epoch = epoch; tl.parity = epoch & 1;
+    volatile int* sm = s_misc;
+    while (sm[6] == 0) { }   // launch tags fetched by the producer warp (long done by the first segment end)
+    tl.comm = &p.comm; tl.part = p.part; tl.max_parts = p.max_parts; tl.BH = BH;
+    tl.R = R; tl.rows_valid = p.rows_valid; tl.wtag = (uint32_t)sm[4]; tl.ctag = (uint32_t)sm[5]; tl.geo = geo;
     tl.s_misc = s_misc; tl.pending = pending; tl.max_pending = kMaxPending; tl.stamps = stamps;
     return tl;
   };
@@ -257,11 +271,11 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       if (lane == 0) { ms[D] = m_run[r]; ms[D + 1] = lt; }
     }
     named_bar_sync(1, kConsumerThreads);
-    // (b) CTA partial -> global
-    const int first_cta = dcomm::cta_of_tile(geo, x * geo.tph);
-    const int nparts = dcomm::cta_of_tile(geo, (x + 1) * geo.tph - 1) - first_cta + 1;
-    const int pidx = cta - first_cta;
-    float* my_part = p.part + ((size_t)x * p.max_parts + pidx) * (size_t)(R * (D + 4));
+    // (b) CTA partial -> workspace as tagged words (no fence, no ticket: every word validates itself)
+    const dcomm::Tail tail = make_tail();
+    int nparts, pidx;
+    dcomm::head_parts(geo, x, cta, nparts, pidx);
+    uint64_t* my_part = dcomm::part_ptr<D>(tail, x, pidx);
     for (int idx = tid; idx < R * D; idx += kConsumerThreads) {
       const int r = idx / D, d = idx - r * D;
       float M = neg_inf();
@@ -276,11 +290,14 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         acc = fmaf(ms[d], sc, acc);
         Lsum = fmaf(ms[D + 1], sc, Lsum);
       }
-      __stcg(my_part + r * (D + 4) + d, acc);
-      if (d == 0) { __stcg(my_part + r * (D + 4) + D, M); __stcg(my_part + r * (D + 4) + D + 1, Lsum); }
+      dcomm::ll_store_gpu(my_part + r * (D + 2) + d, acc, tail.wtag);
+      if (d == 0) {
+        dcomm::ll_store_gpu(my_part + r * (D + 2) + D, M, tail.wtag);
+        dcomm::ll_store_gpu(my_part + r * (D + 2) + D + 1, Lsum, tail.wtag);
+      }
     }
-    const dcomm::Tail tail = make_tail();
-    dcomm::finish_head<D, kConsumerThreads, RB>(tail, x, nparts, tid, 1, store_out);
+    // (c) the owner of the head's last tile merges it -- after this CTA's own last tile (drain below)
+    dcomm::segment_done<D, kConsumerThreads, RB>(tail, x, min(t_hi, (x + 1) * geo.tph), tid, 1, store_out);
   };
 
   // KV8: the block scales of the NEXT tile are prefetched into registers one iteration ahead, so that their
@@ -491,7 +508,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
 
   // ------------- deferred cross-GPU merges for the heads this CTA finished, end-of-kernel arrival -----
   const dcomm::Tail tail = make_tail();
-  dcomm::drain_and_exit<D, kConsumerThreads, RB>(tail, tid, 1, store_out);
+  dcomm::drain<D, kConsumerThreads, RB>(tail, tid, 1, store_out);
 }
 
 template <int D, int R, bool BF16, bool KV8>
@@ -541,7 +558,7 @@ void decode_simt_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, in
   decode_split(BH, s.S, nsm, grid, max_parts);
   const int R = pick_rows((s.Hq / s.Hkv) * s.Sq);
   *rows_per_pass = R;
-  *part_floats = (size_t)BH * *max_parts * R * (s.D + 4);
+  *part_floats = (size_t)BH * *max_parts * R * (s.D + 2) * 2;   // tagged 8-byte words, counted in floats
   *comm_floats = (size_t)2 * kMaxWorldHost * BH * R * (s.D + 2) * 2;
   *comm_flags = (size_t)2 * kMaxWorldHost * BH;
 }
@@ -549,6 +566,8 @@ void decode_simt_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, in
 PreparedLaunch decode_simt_prepare(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                                    float* part, uint32_t* tickets, const CommCtxHost& comm, int nsm,
                                    const uint32_t* kscale, const uint32_t* vscale, int pdl, const int* kv_len) {
+  if ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(tickets)) & 7)
+    throw std::runtime_error("decode_simt: workspace must be 8-byte aligned");
   const bool kv8 = kscale != nullptr;
   if (s.D != 64 && s.D != 128) throw std::runtime_error("decode_simt: head_dim must be 64 or 128");
   if (kv8 && s.D != 128) throw std::runtime_error("decode_simt(mxfp8): head_dim must be 128");
@@ -571,7 +590,8 @@ PreparedLaunch decode_simt_prepare(const AttnShape& s, const void* q, const void
                                     CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeParams p;
   p.kscale = kscale; p.vscale = vscale; p.pdl = pdl; p.kv_len = kv_len;
-  p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
+  p.q = q; p.out = out; p.lse = lse;
+  p.part = reinterpret_cast<uint64_t*>(part); p.wctr = reinterpret_cast<unsigned long long*>(tickets);
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S;
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
   p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;

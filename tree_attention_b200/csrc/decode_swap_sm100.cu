@@ -39,8 +39,8 @@ struct DecodeSwParams {
   const void* q;
   void* out;
   float* lse;
-  float* part;
-  uint32_t* tickets;
+  uint64_t* part;             // workspace: tagged partial words (decode_comm.cuh)
+  unsigned long long* wctr;   // workspace arrival counter (launch tag of the partial words), zero-initialised once
   const float* kscale;  // KV8: per-channel fp32 scales (B, Hkv, D) of the e4m3 K / V shards
   const float* vscale;
   const uint32_t* k_sf;   // MX: one word per key = the 4 UE8M0 scales of its 4 blocks of 32 channels, (B, Hkv, S)
@@ -110,7 +110,8 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   uint64_t* stamps = pv_done + 2;      // 2: globaltimer at CTA start / last publish (thread 0)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stamps + 2);
   int* s_misc = reinterpret_cast<int*>(tmem_slot + 2);
-  int* pending = s_misc + 4;
+  int* s_tags = s_misc + 4;      // [0] intra-GPU tag, [1] cross-GPU tag, [2] ready (written by the TMA thread)
+  int* pending = s_tags + 4;
   [[maybe_unused]] float* ch_scale = reinterpret_cast<float*>(pending + kSwMaxPending);  // KV8: [2][D]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -131,7 +132,7 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
-    s_misc[1] = 0; s_misc[2] = 0;
+    s_misc[0] = 0; s_misc[1] = 0; s_tags[2] = 0;
   }
   if (warp == 4 && lane == 0) { tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); }
   if (warp == 5) tmem_alloc<128>(tmem_slot);
@@ -144,8 +145,6 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   const uint32_t tmem = *tmem_slot;       // S^T0 [0,16) | S^T1 [32,48) | O^T [64,80)
   const uint32_t tmem_o = tmem + 64;
 
-  uint32_t epoch = 0;
-  if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
   if (tid == 0) { stamps[0] = globaltimer_ns(); stamps[1] = 0; }
 
   auto next_segment = [&](int t, int& x, int& j0, int& n, int& t_next) {
@@ -161,6 +160,18 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     // =============================== TMA producer ===============================================
     if (lane == 0) {
       int it = 0;
+      bool tags_done = false;
+      // launch tags (decode_comm.cuh): arrival atomics issued once the ring is full (the producer would block on the
+      // first `empty` barrier anyway), so their round trip is never exposed
+      auto fetch_tags = [&]() {
+        const uint32_t wtag = dcomm::launch_tag(p.wctr);
+        const uint32_t ctag = world > 1 ? dcomm::launch_tag(reinterpret_cast<unsigned long long*>(p.comm.epoch)) : 0u;
+        volatile int* sm = s_tags;
+        sm[0] = (int)wtag; sm[1] = (int)ctag;
+        __threadfence_block();
+        sm[2] = 1;
+        tags_done = true;
+      };
       for (int t = t_lo; t < t_hi;) {
         int x, j0, n, tn;
         next_segment(t, x, j0, n, tn);
@@ -168,6 +179,7 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         for (int jj = 0; jj < n; ++jj, ++it) {
           const int st = it % NS;
           const uint32_t ph = (it / NS) & 1;
+          if (it == NS && !tags_done) fetch_tags();
           mbar_wait(&k_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&k_full[st], SM::kTileBytes);
 #pragma unroll
@@ -181,6 +193,7 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         }
         t = tn;
       }
+      if (!tags_done) fetch_tags();
     }
   } else if (warp == 5) {
     // =============================== MMA issuer =================================================
@@ -273,8 +286,10 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     // split merge + LL-word cross-GPU combine: decode_comm.cuh (shared with decode_simt.cu / decode_tc_sm100.cu)
     auto make_tail = [&]() {   // built on demand: keeps the tail's bookkeeping out of the tile loop's live registers
       dcomm::Tail tl;
-      tl.comm = &p.comm; tl.part = p.part; tl.tickets = p.tickets; tl.max_parts = p.max_parts; tl.BH = BH;
-      tl.R = R; tl.rows_valid = R; tl.epoch = epoch; tl.parity = epoch & 1;
+      volatile int* sm = s_tags;
+      while (sm[2] == 0) { }    // launch tags fetched by the TMA thread (long done by the first segment end)
+      tl.comm = &p.comm; tl.part = p.part; tl.max_parts = p.max_parts; tl.BH = BH;
+      tl.R = R; tl.rows_valid = R; tl.wtag = (uint32_t)sm[0]; tl.ctag = (uint32_t)sm[1]; tl.geo = geo;
       tl.s_misc = s_misc; tl.pending = pending; tl.max_pending = kSwMaxPending; tl.stamps = stamps;
       return tl;
     };
@@ -520,9 +535,10 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         if (lane == 0) mbar_arrive(&p_full[i & 1]);
       }
       // ---- segment epilogue: O^T (thread = channel d, 16 query columns), row sums reduced over the 128 keys
-      const int first_cta = dcomm::cta_of_tile(geo, x * geo.tph);
-      const int nparts = dcomm::cta_of_tile(geo, (x + 1) * geo.tph - 1) - first_cta + 1;
-      float* my_part = p.part + ((size_t)x * p.max_parts + (cta - first_cta)) * (size_t)(R * (D + 4));
+      const dcomm::Tail tail = make_tail();
+      int nparts, pidx;
+      dcomm::head_parts(geo, x, cta, nparts, pidx);
+      uint64_t* my_part = dcomm::part_ptr<D>(tail, x, pidx);   // tagged words: no fence, no ticket (decode_comm.cuh)
       {
         float lw[kSwN];
 #pragma unroll
@@ -552,27 +568,24 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         if constexpr (KV8 && !MX) vs_d = ch_scale[D + row];
 #pragma unroll
         for (int qn = 0; qn < kSwN; ++qn)
-          if (qn < R) __stcg(my_part + qn * (D + 4) + row, __uint_as_float(orow[qn]) * vs_d);   // thread = channel d
+          if (qn < R) dcomm::ll_store_gpu(my_part + qn * (D + 2) + row, __uint_as_float(orow[qn]) * vs_d, tail.wtag);   // thread = channel d
         if (tid < R) {
           const float lsum = red_s[tid] + red_s[kSwN + tid] + red_s[2 * kSwN + tid] + red_s[3 * kSwN + tid];
           float mq = sw_ninf();
 #pragma unroll
           for (int qn = 0; qn < kSwN; ++qn) mq = (qn == tid) ? m_used[qn] : mq;
-          __stcg(my_part + tid * (D + 4) + D, mq);
-          __stcg(my_part + tid * (D + 4) + D + 1, lsum);
+          dcomm::ll_store_gpu(my_part + tid * (D + 2) + D, mq, tail.wtag);
+          dcomm::ll_store_gpu(my_part + tid * (D + 2) + D + 1, lsum, tail.wtag);
         }
         tc_fence_before();
       }
       it += n;
-      {
-        const dcomm::Tail tail = make_tail();
-        dcomm::finish_head<D, kSmx, 4>(tail, x, nparts, tid, 1, store_out);
-      }
+      dcomm::segment_done<D, kSmx, 4>(tail, x, tn, tid, 1, store_out);   // the owner of the head's last tile queues the merge
       named_bar_sync(1, kSmx);  // Q / P^T smem and s_misc reuse by the next segment
       t = tn;
     }
     const dcomm::Tail tail = make_tail();
-    dcomm::drain_and_exit<D, kSmx, 4>(tail, tid, 1, store_out);
+    dcomm::drain<D, kSmx, 4>(tail, tid, 1, store_out);
   }
   tc_fence_before();
   __syncthreads();
@@ -618,7 +631,8 @@ PreparedLaunch decode_swap_prepare(const AttnShape& s, const void* q, const void
   CUtensorMap vmap = make_tmap_bhsd(v, eb, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 128 / eb, kSwKV, CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeSwParams p;
   p.kscale = kscale; p.vscale = vscale; p.k_sf = k_sf; p.v_sf = v_sf; p.kv_len = kv_len;
-  p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
+  p.q = q; p.out = out; p.lse = lse;
+  p.part = reinterpret_cast<uint64_t*>(part); p.wctr = reinterpret_cast<unsigned long long*>(tickets);
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S; p.R = R;
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
   p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;

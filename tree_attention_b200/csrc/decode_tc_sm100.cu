@@ -34,8 +34,8 @@ struct DecodeTcParams {
   const void* q;
   void* out;
   float* lse;
-  float* part;
-  uint32_t* tickets;
+  uint64_t* part;             // workspace: tagged partial words (decode_comm.cuh)
+  unsigned long long* wctr;   // workspace arrival counter (launch tag of the partial words), zero-initialised once
   const float* kscale;  // KV8: per-channel scales (B, Hkv, D) of the e4m3 K / V shards
   const float* vscale;
   const int* kv_len;      // optional device scalar: valid rows of this shard (<= S); rows past it inside the last tile
@@ -96,7 +96,8 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
   uint64_t* stamps = pv_done + 2;      // 2: globaltimer at CTA start / last publish (thread 0)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stamps + 2);
   int* s_misc = reinterpret_cast<int*>(tmem_slot + 2);  // [0] ticket, [1] n_pending, [2] inline-combine head+1
-  int* pending = s_misc + 4;                            // [kTcMaxPending]
+  int* s_tags = s_misc + 4;      // [0] intra-GPU tag, [1] cross-GPU tag, [2] ready (written by the TMA thread)
+  int* pending = s_tags + 4;                            // [kTcMaxPending]
   [[maybe_unused]] float* ch_scale = reinterpret_cast<float*>(pending + kTcMaxPending);  // KV8: [2][D] K / V channel scales
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -118,7 +119,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
     for (int i = 0; i < NS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], n_active_warps); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
-    s_misc[1] = 0; s_misc[2] = 0;
+    s_misc[0] = 0; s_misc[1] = 0; s_tags[2] = 0;
   }
   if (warp == 4 && lane == 0) { tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); }
   if (warp == 5) tmem_alloc<512>(tmem_slot);
@@ -132,8 +133,6 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_o = tmem + 256;
 
-  uint32_t epoch = 0;
-  if (world > 1) epoch = ld_relaxed_sys_u32(p.comm.epoch) + 1;
   if (tid == 0) { stamps[0] = globaltimer_ns(); stamps[1] = 0; }
 
   // segment iteration shared by all roles: consecutive tiles of one head, clipped to the visible (causal) prefix
@@ -150,6 +149,18 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
     // =============================== TMA producer ===============================================
     if (lane == 0) {
       int it = 0;
+      bool tags_done = false;
+      // launch tags (decode_comm.cuh): arrival atomics issued once the ring is full (the producer would block on the
+      // first `empty` barrier anyway), so their round trip is never exposed
+      auto fetch_tags = [&]() {
+        const uint32_t wtag = dcomm::launch_tag(p.wctr);
+        const uint32_t ctag = world > 1 ? dcomm::launch_tag(reinterpret_cast<unsigned long long*>(p.comm.epoch)) : 0u;
+        volatile int* sm = s_tags;
+        sm[0] = (int)wtag; sm[1] = (int)ctag;
+        __threadfence_block();
+        sm[2] = 1;
+        tags_done = true;
+      };
       for (int t = t_lo; t < t_hi;) {
         int x, j0, n, tn;
         next_segment(t, x, j0, n, tn);
@@ -157,6 +168,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
         for (int jj = 0; jj < n; ++jj, ++it) {
           const int st = it % NS;
           const uint32_t ph = (it / NS) & 1;
+          if (it == NS && !tags_done) fetch_tags();
           mbar_wait(&k_empty[st], ph ^ 1);
           mbar_arrive_expect_tx(&k_full[st], SM::kTileBytes);
 #pragma unroll
@@ -170,6 +182,7 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
         }
         t = tn;
       }
+      if (!tags_done) fetch_tags();
     }
   } else if (warp == 5) {
     // =============================== MMA issuer =================================================
@@ -255,8 +268,10 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
     // split merge + LL-word cross-GPU combine: decode_comm.cuh (shared with decode_simt.cu / decode_swap_sm100.cu)
     auto make_tail = [&]() {   // built on demand: keeps the tail's bookkeeping out of the tile loop's live registers
       dcomm::Tail tl;
-      tl.comm = &p.comm; tl.part = p.part; tl.tickets = p.tickets; tl.max_parts = p.max_parts; tl.BH = BH;
-      tl.R = R; tl.rows_valid = R; tl.epoch = epoch; tl.parity = epoch & 1;
+      volatile int* sm = s_tags;
+      while (sm[2] == 0) { }    // launch tags fetched by the TMA thread (long done by the first segment end)
+      tl.comm = &p.comm; tl.part = p.part; tl.max_parts = p.max_parts; tl.BH = BH;
+      tl.R = R; tl.rows_valid = R; tl.wtag = (uint32_t)sm[0]; tl.ctag = (uint32_t)sm[1]; tl.geo = geo;
       tl.s_misc = s_misc; tl.pending = pending; tl.max_pending = kTcMaxPending; tl.stamps = stamps;
       return tl;
     };
@@ -404,9 +419,10 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
         }
       }
       // ---- segment epilogue: (O, m, l) of the valid rows -> CTA partial in the workspace
-      const int first_cta = dcomm::cta_of_tile(geo, x * geo.tph);
-      const int nparts = dcomm::cta_of_tile(geo, (x + 1) * geo.tph - 1) - first_cta + 1;
-      float* my_part = p.part + ((size_t)x * p.max_parts + (cta - first_cta)) * (size_t)(R * (D + 4));
+      const dcomm::Tail tail = make_tail();
+      int nparts, pidx;
+      dcomm::head_parts(geo, x, cta, nparts, pidx);
+      uint64_t* my_part = dcomm::part_ptr<D>(tail, x, pidx);   // tagged words: no fence, no ticket (decode_comm.cuh)
       if (warp_active) {
         if (n > 0) {
           const int il = it + n - 1;
@@ -424,32 +440,28 @@ decode_tc_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_constant
             for (int u = 0; u < 32; ++u) orow[u] = 0u;
           }
           if (row_valid) {
-            float4* dst = reinterpret_cast<float4*>(my_part + row * (D + 4) + c0);
+            uint64_t* dst = my_part + row * (D + 2) + c0;
 #pragma unroll
-            for (int u = 0; u < 32; u += 4) {
-              float4 o4 = make_float4(__uint_as_float(orow[u]), __uint_as_float(orow[u + 1]), __uint_as_float(orow[u + 2]),
-                                      __uint_as_float(orow[u + 3]));
-              if constexpr (KV8) {  // de-quantise the V channels
-                o4.x *= ch_scale[D + c0 + u]; o4.y *= ch_scale[D + c0 + u + 1];
-                o4.z *= ch_scale[D + c0 + u + 2]; o4.w *= ch_scale[D + c0 + u + 3];
-              }
-              __stcg(dst + (u >> 2), o4);
+            for (int u = 0; u < 32; ++u) {
+              float o1 = __uint_as_float(orow[u]);
+              if constexpr (KV8) o1 *= ch_scale[D + c0 + u];   // de-quantise the V channels
+              dcomm::ll_store_gpu(dst + u, o1, tail.wtag);
             }
           }
         }
-        if (row_valid) { __stcg(my_part + row * (D + 4) + D, m_used); __stcg(my_part + row * (D + 4) + D + 1, l_sum); }
+        if (row_valid) {
+          dcomm::ll_store_gpu(my_part + row * (D + 2) + D, m_used, tail.wtag);
+          dcomm::ll_store_gpu(my_part + row * (D + 2) + D + 1, l_sum, tail.wtag);
+        }
         tc_fence_before();
       }
       it += n;
-      {
-        const dcomm::Tail tail = make_tail();
-        dcomm::finish_head<D, kSmx, 4>(tail, x, nparts, tid, 1, store_out);
-      }
+      dcomm::segment_done<D, kSmx, 4>(tail, x, tn, tid, 1, store_out);   // the owner of the head's last tile queues the merge
       named_bar_sync(1, kSmx);  // Q smem / s_misc reuse by the next segment
       t = tn;
     }
     const dcomm::Tail tail = make_tail();
-    dcomm::drain_and_exit<D, kSmx, 4>(tail, tid, 1, store_out);
+    dcomm::drain<D, kSmx, 4>(tail, tid, 1, store_out);
   }
   tc_fence_before();
   __syncthreads();
@@ -483,7 +495,7 @@ void decode_tc_plan(const AttnShape& s, int nsm, int* grid, int* max_parts, int*
   decode_split(BH, s.S, nsm, grid, max_parts);
   const int R = (s.Hq / s.Hkv) * s.Sq;
   *rows = R;
-  *part_floats = (size_t)BH * *max_parts * R * (s.D + 4);
+  *part_floats = (size_t)BH * *max_parts * R * (s.D + 2) * 2;   // tagged 8-byte words, counted in floats
   *comm_bytes = (size_t)2 * kMaxWorldHost * BH * R * (s.D + 2) * 8;
 }
 
@@ -510,7 +522,8 @@ PreparedLaunch decode_tc_prepare(const AttnShape& s, const void* q, const void* 
   CUtensorMap vmap = make_tmap_bhsd(v, eb, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 128 / eb, kTN, CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeTcParams p;
   p.kscale = kscale; p.vscale = vscale; p.kv_len = kv_len;
-  p.q = q; p.out = out; p.lse = lse; p.part = part; p.tickets = tickets;
+  p.q = q; p.out = out; p.lse = lse;
+  p.part = reinterpret_cast<uint64_t*>(part); p.wctr = reinterpret_cast<unsigned long long*>(tickets);
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S; p.R = R;
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
   p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;

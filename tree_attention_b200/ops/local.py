@@ -34,8 +34,10 @@ def _as_bhsd(x: torch.Tensor) -> torch.Tensor:
 def new_workspace(device: torch.device, nfloats: int, nticket: int) -> Dict[str, torch.Tensor]:
     """A private split-merge workspace (partials + tickets).  Objects that bake raw pointers into CUDA graphs or
     prepared launches (``TreeDecodeSession``) own one of these instead of borrowing the shared cache below."""
+    # `part` holds tagged 8-byte words {fp32, launch tag} and `tickets` the 64-bit arrival counter the tags are derived
+    # from (csrc/decode_comm.cuh): both start at zero, a tag is never zero, so stale memory can never pass for a word
     return {
-        "part": torch.empty(max(nfloats, 1), dtype=torch.float32, device=device),
+        "part": torch.zeros(max(nfloats, 2), dtype=torch.float32, device=device),
         "tickets": torch.zeros(max(nticket, 64), dtype=torch.int32, device=device),
     }
 

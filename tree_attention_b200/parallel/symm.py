@@ -9,7 +9,8 @@ acquire the peers' flags with ``ld.acquire.sys`` (``csrc/decode_simt.cu``, ``csr
 
 Buffer layout (per family, per rank)::
 
-    [0      ) epoch   u32   device-resident call counter (bumped by the kernel => CUDA-graph safe)
+    [0      ) epoch   u32   device-resident call counter (bumped by the kernel => CUDA-graph safe); the fused decode
+                            kernels use [0, 8) as a 64-bit arrival counter instead (4096 per launch)
     [64     ) status  16xu32  [0]=error code [1]=item [2]=source rank [3]=epoch, [8]=done counter
     [4096   ) flags   u32[flag_bytes/4]
     [4096+flag_bytes, ...) data  (float)
@@ -67,8 +68,13 @@ class SymmRegion:
         return tuple(int(x) for x in v)
 
     def epoch(self) -> int:
+        """Launches of this family so far.  The fused decode kernels keep a 64-bit ARRIVAL counter at offset 0 (every
+        launch advances it by 4096, csrc/decode_comm.cuh); the other families keep a 32-bit epoch there."""
         C = _build.load()
-        return int(C.symm_read_u32(self.local_ptr, 1)[0])
+        lo, hi = (int(x) for x in C.symm_read_u32(self.local_ptr, 2))
+        if self.family.startswith("decode"):
+            return ((hi << 32) | lo) >> 12
+        return lo
 
     def check(self) -> None:
         """Raise if a kernel of this family reported a bounded-spin timeout (failure detection)."""
