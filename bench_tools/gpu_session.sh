@@ -65,6 +65,16 @@ for st in $STEPS; do
       timeout 600 python bench_tools/bench_bwd.py --seq 16384 > "$OUT/bench_bwd.log" 2>&1; echo "rc=$?"; tail -n 4 "$OUT/bench_bwd.log";;
     fwd_phases)
       timeout 300 python bench_tools/prof_fwd_phases.py > "$OUT/fwd_phases.log" 2>&1; echo "rc=$?"; tail -n 4 "$OUT/fwd_phases.log";;
+    scale)     # what the driver does at round end: N = 1, 2, 4, 8 back to back on ONE box, 20 timed steps, 5 warm-ups
+      for n in 1 2 4 8; do
+        [ "$n" -le "$NG" ] || continue
+        if [ "$n" -eq 1 ]; then
+          timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-extras > "$OUT/scale_own_1.json" 2> "$OUT/scale_own_1.err"
+        else
+          timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29850+n)) bench.py --gpus $n --steps 20 --warmup 5 --no-extras > "$OUT/scale_own_$n.json" 2> "$OUT/scale_own_$n.err"
+        fi
+        echo "scale n=$n rc=$?"; tail -n 1 "$OUT/scale_own_$n.json" | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['n_gpus'], d['ms_per_step'], d['e2e']['ms_per_step'], d['clocks'])"
+      done;;
     bench1)    # same-box 1-GPU reference point for the scaling efficiency (boxes differ by several percent)
       CUDA_VISIBLE_DEVICES=0 timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-extras > "$OUT/bench20_own_1_samebox.json" 2> "$OUT/bench20_own_1_samebox.err"; echo "own20 n=1 rc=$?"; tail -n 1 "$OUT/bench20_own_1_samebox.json" | cut -c1-500;;
     bench20)   # the driver's own invocation: 20 timed steps, 5 warm-ups, both arms
