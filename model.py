@@ -60,7 +60,14 @@ def main(rank: int, world_size: int) -> None:
     """Per-rank driver (model.py:129): init, data, one timed tree-decode step, validate, clean up."""
     cfg = _CFG
     device = torch.device(f"cuda:{rank}" if torch.cuda.is_available() else "cpu")
-    setup(rank, world_size, master_addr=cfg.master_addr, master_port=cfg.master_port)
+    # Under torchrun the rendezvous belongs to the launcher: the workers must connect to ITS store (MASTER_ADDR/PORT of the
+    # environment; TORCHELASTIC_USE_AGENT_STORE means rank 0 does not open one of its own), so the config's default port
+    # (the reference's 12355, model.py:21) only applies to the self-spawned path.  Overriding it hung all 8 ranks (round 2).
+    under_launcher = "TORCHELASTIC_RUN_ID" in os.environ or ("RANK" in os.environ and "MASTER_PORT" in os.environ)
+    setup(rank, world_size,
+          master_addr=None if under_launcher else cfg.master_addr,
+          master_port=None if under_launcher else cfg.master_port,
+          local_rank=int(os.environ["LOCAL_RANK"]) if "LOCAL_RANK" in os.environ else None)
     dtype = cfg.torch_dtype if device.type == "cuda" else torch.float32
     shape = (cfg.batch, cfg.num_heads, cfg.seq_len, cfg.head_dim)
     qfl, kfl, vfl = make_data(shape, rank, device, dtype=dtype, layout=cfg.layout, sq=cfg.q_len,
