@@ -536,6 +536,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("decode_fwd_mx", &decode_fwd_mx, py::arg("q"), py::arg("k8"), py::arg("v8"), py::arg("ks"), py::arg("vs"), py::arg("out"),
         py::arg("lse"), py::arg("part"), py::arg("tickets"), py::arg("comm"), py::arg("scale"), py::arg("causal"),
         py::arg("q_pos0"), py::arg("kv_pos0"), py::arg("kv_len") = py::none());
+  m.def("decode_set_trace", [](c10::optional<at::Tensor> t) {   // profiling aid (bench_tools/trace_decode.py)
+    if (!t.has_value()) { ta::decode_simt_set_trace(nullptr); return; }
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kLong && t->is_contiguous() && t->numel() >= 16 * ta::num_sms());
+    ta::decode_simt_set_trace(reinterpret_cast<unsigned long long*>(t->data_ptr<int64_t>()));
+  });
   m.def("decode_tc_plan", &decode_tc_plan);
   m.def("decode_tc_fwd", &decode_tc_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("lse"), py::arg("part"),
         py::arg("tickets"), py::arg("comm"), py::arg("scale"), py::arg("causal"), py::arg("q_pos0"), py::arg("kv_pos0"),

@@ -139,7 +139,6 @@ struct Tail {
   uint32_t wtag;         // tag of this launch's intra-GPU partial words (workspace counter)
   uint32_t ctag;         // tag of this launch's cross-GPU words (region counter); its parity selects the slot set
   Geom geo;
-  int* s_misc;           // smem: [0] n_pending, [1] scratch
   int* pending;          // smem: heads this CTA merges (it owns their last tile), merged after the CTA's last tile
   int max_pending;
   uint64_t* stamps;      // smem (thread 0 only): [0] globaltimer at CTA start, [1] at the last publish (0 = none yet)
@@ -341,39 +340,38 @@ __device__ __noinline__ void merge_head(const Tail& t, int x, int tid, StoreOut&
 // The CTA partial of head x has been written to the workspace as tagged words by the calling threads (part_ptr /
 // ll_store_gpu; nothing to fence).  If this CTA owns the head's last tile it is the head's merger: queue the head; the
 // merge itself happens after the CTA's last tile (drain), when the other CTAs' words are on their way.
-// Must be called by all NT threads.  Returns true when the list was full and the head was completed inline.
+// No barrier on the common path (a head switch must not stall the stream): `n_pend` is the number of queued heads, kept
+// in a register by EVERY calling thread (all threads see the same segments), thread 0 mirrors the heads into smem.
 template <int D, int NT, int RB, typename StoreOut>
-__device__ __forceinline__ void segment_done(const Tail& t, int x, int seg_end_tile, int tid, int bar_id, StoreOut& store_out) {
+__device__ __forceinline__ void segment_done(const Tail& t, int x, int seg_end_tile, int& n_pend, int tid, int bar_id,
+                                             StoreOut& store_out) {
   if (seg_end_tile != (x + 1) * t.geo.tph) return;   // not the owner of the head's last tile: nothing else to do
-  named_bar_sync(bar_id, NT);                        // (uniform branch: every thread sees the same segment)
-  if (tid == 0) {
-    const int n = t.s_misc[0];
-    if (n < t.max_pending) { t.pending[n] = x; t.s_misc[0] = n + 1; t.s_misc[1] = 0; }
-    else t.s_misc[1] = 1;                            // list full (more than max_pending whole heads per CTA): finish it now
+  if (n_pend < t.max_pending) {
+    if (tid == 0) t.pending[n_pend] = x;
+    ++n_pend;
+    return;
+  }
+  // list full (more than max_pending whole heads in one CTA's range): finish this head now
+  named_bar_sync(bar_id, NT);
+  merge_head<D, NT>(t, x, tid, store_out);
+  if (t.comm->world > 1) {
+    if (tid == 0) t.stamps[1] = globaltimer_ns();
+    named_bar_sync(bar_id, NT);
+    combine_ranks<D, NT, RB>(t, x, tid, bar_id, store_out);
   }
   named_bar_sync(bar_id, NT);
-  if (t.s_misc[1] != 0) {
-    merge_head<D, NT>(t, x, tid, store_out);
-    if (t.comm->world > 1) {
-      if (tid == 0) t.stamps[1] = globaltimer_ns();
-      named_bar_sync(bar_id, NT);
-      combine_ranks<D, NT, RB>(t, x, tid, bar_id, store_out);
-    }
-    named_bar_sync(bar_id, NT);
-  }
 }
 
 // after the CTA's last tile: merge (and publish) every queued head, THEN wait for the peers' words of those heads --
 // all publishes are in flight over NVLink before the first wait
 template <int D, int NT, int RB, typename StoreOut>
-__device__ __forceinline__ void drain(const Tail& t, int tid, int bar_id, StoreOut& store_out) {
-  named_bar_sync(bar_id, NT);
-  const int n = t.s_misc[0];
-  for (int i = 0; i < n; ++i) merge_head<D, NT>(t, t.pending[i], tid, store_out);
-  if (t.comm->world <= 1 || n == 0) return;
+__device__ __forceinline__ void drain(const Tail& t, int n_pend, int tid, int bar_id, StoreOut& store_out) {
+  named_bar_sync(bar_id, NT);   // thread 0's pending[] writes
+  for (int i = 0; i < n_pend; ++i) merge_head<D, NT>(t, t.pending[i], tid, store_out);
+  if (t.comm->world <= 1 || n_pend == 0) return;
   if (tid == 0) t.stamps[1] = globaltimer_ns();
   named_bar_sync(bar_id, NT);
-  for (int i = 0; i < n; ++i) combine_ranks<D, NT, RB>(t, t.pending[i], tid, bar_id, store_out);
+  for (int i = 0; i < n_pend; ++i) combine_ranks<D, NT, RB>(t, t.pending[i], tid, bar_id, store_out);
 }
 
 inline CommCtx to_device_ctx(const CommCtxHost& h) {

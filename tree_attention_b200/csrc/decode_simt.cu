@@ -48,6 +48,7 @@ struct DecodeParams {
   long long q_pos0, kv_pos0;
   long long q_sb, q_sh, q_ss, o_sb, o_sh, o_ss;
   int max_parts;      // bound on the CTAs sharing one head, for ANY number of valid rows (decode_simt_plan)
+  unsigned long long* trace;  // optional [grid][16] timeline stamps (bench_tools/trace_decode.py); null in production
   int pdl;  // 0: plain launch; 1: programmatic dependent launch; 2: + K/V prefetch before the dependency wait (static KV)
   CommCtx comm;
 };
@@ -67,7 +68,8 @@ template <int D, int R, bool KV8>
 constexpr size_t smem_bytes() {
   using L = SmemLayout<D, KV8>;
   return 1024 /*align slack*/ + size_t(L::kStages) * L::kStageBytes +
-         sizeof(float) * (R * D + kConsumerWarps * L::kPsPerWarp * R * kRowsPerWarp + kConsumerWarps * R * (D + 4)) +
+         sizeof(float) * (2 * R * D + kConsumerWarps * L::kPsPerWarp * R * kRowsPerWarp +
+                          (R <= 2 ? 2 : 1) * kConsumerWarps * R * (D + 4)) +
          sizeof(int) * (kMaxPending + 8) + sizeof(uint64_t) * (2 * L::kStages + 2);
 }
 
@@ -104,10 +106,11 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  float* q_s = reinterpret_cast<float*>(smem + size_t(NS) * L::kStageBytes);  // [R][D], pre-scaled
-  float* p_s = q_s + R * D;                                                    // [warps][(blk)][R][16]
-  float* merge_s = p_s + kConsumerWarps * L::kPsPerWarp * R * kRowsPerWarp;    // [warps][R][D+4]
-  int* pending = reinterpret_cast<int*>(merge_s + kConsumerWarps * R * (D + 4));
+  float* q_s = reinterpret_cast<float*>(smem + size_t(NS) * L::kStageBytes);  // [2][R][D], pre-scaled: this CTA's first two heads
+  float* p_s = q_s + 2 * R * D;                                                // [warps][(blk)][R][16]
+  float* merge_s = p_s + kConsumerWarps * L::kPsPerWarp * R * kRowsPerWarp;    // [2][warps][R][D+4] (double-buffered by segment)
+  constexpr int kMergeBufs = R <= 2 ? 2 : 1;   // R = 4: no room for a second buffer, a trailing barrier instead
+  int* pending = reinterpret_cast<int*>(merge_s + kMergeBufs * kConsumerWarps * R * (D + 4));
   int* s_misc = pending + kMaxPending;  // [0]=n_pending, [1]=scratch, [4]=intra-GPU tag, [5]=cross-GPU tag, [6]=tags ready
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_misc + 8);
   uint64_t* empty_bar = full_bar + NS;
@@ -118,6 +121,16 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   const int lane = tid & 31;
   const int cta = blockIdx.x;
   const int world = p.comm.world;
+  // timeline stamps: [0] entry (globaltimer) [1] entry (clock64) [2] prologue done [3] dependency resolved [4] first tile
+  // landed [5] last tile consumed [6] last partial stored [7] merges published [8] end (clock64) [9] end (globaltimer)
+  // [10] producer: first TMA issued [11] producer: last TMA issued [12] tiles of this CTA
+  unsigned long long* trc = p.trace ? p.trace + (size_t)cta * 16 : nullptr;
+  if (trc && tid == 0) {
+    trc[0] = globaltimer_ns(); trc[1] = clock64();
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trc[13] = smid; trc[14] = 0; trc[15] = 0;   // [13] SM id [14] cycles inside mid-stream finalize_segment calls [15] their count
+  }
 
   if (tid == 0) {
     for (int i = 0; i < NS; ++i) {
@@ -132,6 +145,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     tma_prefetch_desc(&vmap);
   }
   __syncthreads();
+  if (trc && tid == 0) trc[2] = clock64();
 
   // Programmatic dependent launch: let the NEXT launch of the stream start its prologue (and, for a static KV
   // cache, its first K/V tile loads) on SMs this grid has already vacated, while our last CTAs still wait for
@@ -175,6 +189,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         const int b = x / p.Hkv, h = x - b * p.Hkv;
         if (issued == NS && !tags_done) fetch_tags();
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (trc && issued == 0) trc[10] = clock64();
         mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
         uint8_t* ks = stage_base + size_t(stage) * L::kStageBytes;
         uint8_t* vs = ks + L::kTensorBytes;
@@ -187,12 +202,14 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         if (++stage == NS) { stage = 0; phase ^= 1; }
       }
       if (!tags_done) fetch_tags();
+      if (trc) { trc[11] = clock64(); trc[12] = (unsigned long long)issued; }
     }
     return;
   }
 
   // --------------------------------- consumers ----------------------------------------------
   if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (trc && tid == 0) trc[3] = clock64();
   const dcomm::Geom geo = dcomm::make_geom(p.S, p.kv_len, BH, gridDim.x);
   const int t_lo = dcomm::cta_lo(geo, cta), t_hi = dcomm::cta_lo(geo, cta + 1);
   constexpr int RB = R;  // rows of one output channel gathered per batch of the cross-GPU merge (R <= 4)
@@ -204,7 +221,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     while (sm[6] == 0) { }   // launch tags fetched by the producer warp (long done by the first segment end)
     tl.comm = &p.comm; tl.part = p.part; tl.max_parts = p.max_parts; tl.BH = BH;
     tl.R = R; tl.rows_valid = p.rows_valid; tl.wtag = (uint32_t)sm[4]; tl.ctag = (uint32_t)sm[5]; tl.geo = geo;
-    tl.s_misc = s_misc; tl.pending = pending; tl.max_pending = kMaxPending; tl.stamps = stamps;
+    tl.pending = pending; tl.max_pending = kMaxPending; tl.stamps = stamps;
     return tl;
   };
   const int r16 = lane & 15;
@@ -224,7 +241,13 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     }
   };
 
-  auto load_q = [&](int x) {
+  // The query rows of a head, pre-scaled, into buffer `buf` of q_s.  A head switch in the middle of the stream must
+  // not stall the consumers: the stage ring holds exactly the bytes that keep this SM's share of HBM busy (Little's
+  // law: 192 KB in flight ~ 4 us of loaded latency), so a 2.5 us stall (finalize + a global load of q + 3 barriers)
+  // drains it and costs the CTA 5-10 us -- and every CTA with a head boundary in its range became the kernel's
+  // straggler (bench_tools/trace_decode.py, profiles/r2_decode/).  Hence: the first TWO heads of the CTA's range are
+  // loaded up front (one latency, overlapped with the first TMA loads); only a third head (short sequences) loads late.
+  auto load_q = [&](int x, int buf) {
     const int b = x / p.Hkv, h = x - b * p.Hkv;
     for (int idx = tid; idx < R * D; idx += kConsumerThreads) {
       const int r = idx / D, d = idx - r * D;
@@ -236,11 +259,20 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
                              (long long)(h * p.G + g) * p.q_sh + (long long)i * p.q_ss + d;
         val = cvt1<BF16>(*qp) * p.scale_log2;
       }
-      if constexpr (KV8) reinterpret_cast<__half*>(q_s)[idx] = __float2half_rn(val);
-      else q_s[idx] = val;
+      if constexpr (KV8) reinterpret_cast<__half*>(q_s + buf * R * D)[idx] = __float2half_rn(val);
+      else q_s[buf * R * D + idx] = val;
     }
-    named_bar_sync(1, kConsumerThreads);
   };
+  const int x_first = t_lo / geo.tph;
+  if (t_lo < t_hi) {
+    load_q(x_first, 0);
+    if ((x_first + 1) * geo.tph < t_hi) load_q(x_first + 1, 1);
+  }
+  named_bar_sync(1, kConsumerThreads);
+  const float* q_cur = q_s;
+  uint32_t wtag = 0;   // launch tag of the partial words (picked up from the producer thread at the first segment end)
+  int n_fin = 0;       // segments finalised so far (selects the merge_s buffer)
+  int n_pend = 0;      // heads queued for the merge in drain (uniform across the threads)
 
   // write a finished (b, kv-head) result (normalised o, log2-domain lse) to the user tensors
   auto store_out = [&](int x, int r, int d, float o_norm, float lse2) {
@@ -257,7 +289,10 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   // per-CTA partial of head x is complete: merge warps, write the partial, then the shared tail (decode_comm.cuh):
   // ticket -> last CTA merges the parts -> output (world == 1) or tagged 8-byte words to every rank + deferred merge
   auto finalize_segment = [&](int x) {
-    // (a) warps -> smem
+    // (a) warps -> smem (double-buffered by segment: a fast warp may start the NEXT segment's (a) while slow threads of
+    // this one are still in (b); two finalizes are at least one tile apart, (b) lasts a fraction of a tile)
+    float* mbuf = merge_s + (kMergeBufs == 2 ? (n_fin & 1) : 0) * (kConsumerWarps * R * (D + 4));
+    ++n_fin;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       float lt = l_run[r];
@@ -265,39 +300,50 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       lt += __shfl_xor_sync(0xffffffffu, lt, 4);
       lt += __shfl_xor_sync(0xffffffffu, lt, 2);
       lt += __shfl_xor_sync(0xffffffffu, lt, 1);
-      float* ms = merge_s + (warp * R + r) * (D + 4);
+      float* ms = mbuf + (warp * R + r) * (D + 4);
 #pragma unroll
       for (int e = 0; e < EPL; ++e) ms[lane * EPL + e] = o_acc[r][e];
       if (lane == 0) { ms[D] = m_run[r]; ms[D + 1] = lt; }
     }
-    named_bar_sync(1, kConsumerThreads);
-    // (b) CTA partial -> workspace as tagged words (no fence, no ticket: every word validates itself)
-    const dcomm::Tail tail = make_tail();
+    named_bar_sync(1, kConsumerThreads);   // the ONLY barrier of a head switch
+    // (b) CTA partial -> workspace as tagged words (no fence, no ticket: every word validates itself).  Nothing here may
+    // call out of line or touch local memory: with 227 KB of shared memory there is no L1 left for spills, and every
+    // microsecond the consumers spend here drains the stage ring (see load_q above)
+    if (wtag == 0) {
+      volatile int* sm = s_misc;
+      while (sm[6] == 0) { }   // launch tags fetched by the producer thread (long done by the first segment end)
+      wtag = (uint32_t)sm[4];
+    }
     int nparts, pidx;
     dcomm::head_parts(geo, x, cta, nparts, pidx);
-    uint64_t* my_part = dcomm::part_ptr<D>(tail, x, pidx);
+    uint64_t* my_part = p.part + ((size_t)x * p.max_parts + pidx) * (size_t)(R * (D + 2));
     for (int idx = tid; idx < R * D; idx += kConsumerThreads) {
       const int r = idx / D, d = idx - r * D;
       float M = neg_inf();
 #pragma unroll
-      for (int w = 0; w < kConsumerWarps; ++w) M = fmaxf(M, merge_s[(w * R + r) * (D + 4) + D]);
+      for (int w = 0; w < kConsumerWarps; ++w) M = fmaxf(M, mbuf[(w * R + r) * (D + 4) + D]);
       const float Ms = (M == neg_inf()) ? 0.f : M;
       float acc = 0.f, Lsum = 0.f;
 #pragma unroll
       for (int w = 0; w < kConsumerWarps; ++w) {
-        const float* ms = merge_s + (w * R + r) * (D + 4);
+        const float* ms = mbuf + (w * R + r) * (D + 4);
         const float sc = fast_exp2(ms[D] - Ms);
         acc = fmaf(ms[d], sc, acc);
         Lsum = fmaf(ms[D + 1], sc, Lsum);
       }
-      dcomm::ll_store_gpu(my_part + r * (D + 2) + d, acc, tail.wtag);
+      dcomm::ll_store_gpu(my_part + r * (D + 2) + d, acc, wtag);
       if (d == 0) {
-        dcomm::ll_store_gpu(my_part + r * (D + 2) + D, M, tail.wtag);
-        dcomm::ll_store_gpu(my_part + r * (D + 2) + D + 1, Lsum, tail.wtag);
+        dcomm::ll_store_gpu(my_part + r * (D + 2) + D, M, wtag);
+        dcomm::ll_store_gpu(my_part + r * (D + 2) + D + 1, Lsum, wtag);
       }
     }
-    // (c) the owner of the head's last tile merges it -- after this CTA's own last tile (drain below)
-    dcomm::segment_done<D, kConsumerThreads, RB>(tail, x, min(t_hi, (x + 1) * geo.tph), tid, 1, store_out);
+    // (c) the owner of the head's last tile merges it -- after this CTA's own last tile (drain below).  The list cannot
+    // overflow: decode_simt_prepare bounds the heads per CTA by kMaxPending
+    if (min(t_hi, (x + 1) * geo.tph) == (x + 1) * geo.tph) {
+      if (tid == 0) pending[n_pend] = x;
+      ++n_pend;
+    }
+    if constexpr (kMergeBufs == 1) named_bar_sync(1, kConsumerThreads);   // single merge buffer: (b) must finish before the next (a)
   };
 
   // KV8: the block scales of the NEXT tile are prefetched into registers one iteration ahead, so that their
@@ -320,14 +366,31 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     [[maybe_unused]] const uint32_t ksc_word = nxt_ksc;
     [[maybe_unused]] const uint32_t vsc_cur = nxt_vsc;
     fetch_scales(t + 1);
+    bool switched = false;
+    long long ts0 = 0, ts1 = 0, ts2 = 0;
     if (x != cur_x) {
+      switched = cur_x >= 0;
+      ts0 = clock64();
       if (cur_x >= 0) finalize_segment(cur_x);
-      load_q(x);
+      ts1 = clock64();
+      const int rel = x - x_first;
+      if (rel >= 2) {   // third+ head of this CTA's range (short sequences): its buffer was last used two heads ago
+        load_q(x, rel & 1);
+        named_bar_sync(1, kConsumerThreads);
+      }
+      q_cur = q_s + (rel & 1) * R * D;
       reset_state();
       cur_x = x;
+      ts2 = clock64();
     }
     if (!tile_visible(j)) continue;
     mbar_wait(&full_bar[stage], phase);
+    if (trc && tid == 0 && t == t_lo) trc[4] = clock64();
+    if (trc && tid == 0 && switched) {   // mid-stream head switch: [14] finalize cycles | load_q cycles << 32, [15] wait for the next tile | t - t_lo << 32
+      trc[14] = (unsigned long long)(ts1 - ts0) | ((unsigned long long)(ts2 - ts1) << 32);
+      trc[15] = (unsigned long long)(clock64() - ts2) | ((unsigned long long)(t - t_lo) << 32);
+      trc[7] = (unsigned long long)ts0;
+    }
     const uint8_t* ks = stage_base + size_t(stage) * L::kStageBytes;
     const uint8_t* vs = ks + L::kTensorBytes;
 
@@ -348,8 +411,8 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         cvt8<BF16>(kw, kf);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const float4 qa = *reinterpret_cast<const float4*>(q_s + r * D + cg * 8);
-          const float4 qb = *reinterpret_cast<const float4*>(q_s + r * D + cg * 8 + 4);
+          const float4 qa = *reinterpret_cast<const float4*>(q_cur + r * D + cg * 8);
+          const float4 qb = *reinterpret_cast<const float4*>(q_cur + r * D + cg * 8 + 4);
           s_acc[r][0] = fmaf(kf[0], qa.x, s_acc[r][0]);
           s_acc[r][1] = fmaf(kf[1], qa.y, s_acc[r][1]);
           s_acc[r][2] = fmaf(kf[2], qa.z, s_acc[r][2]);
@@ -382,8 +445,8 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         const float ksc = __uint_as_float(((ksc_word >> (8 * (cg >> 1))) & 0xffu) << 23);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const uint4 qa = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(q_s) + r * D + cg * 16);
-          const uint4 qb = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(q_s) + r * D + cg * 16 + 8);
+          const uint4 qa = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(q_cur) + r * D + cg * 16);
+          const uint4 qb = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(q_cur) + r * D + cg * 16 + 8);
           const uint32_t qh[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
           __half2 a0 = __float2half2_rn(0.f), a1 = a0;
 #pragma unroll
@@ -504,11 +567,14 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     if (lane == 0) mbar_arrive(&empty_bar[stage]);
     if (++stage == NS) { stage = 0; phase ^= 1; }
   }
+  if (trc && tid == 0) trc[5] = clock64();
   if (cur_x >= 0) finalize_segment(cur_x);
+  if (trc && tid == 0) trc[6] = clock64();
 
   // ------------- deferred cross-GPU merges for the heads this CTA finished, end-of-kernel arrival -----
   const dcomm::Tail tail = make_tail();
-  dcomm::drain<D, kConsumerThreads, RB>(tail, tid, 1, store_out);
+  dcomm::drain<D, kConsumerThreads, RB>(tail, n_pend, tid, 1, store_out);
+  if (trc && tid == 0) { trc[8] = clock64(); trc[9] = globaltimer_ns(); }
 }
 
 template <int D, int R, bool BF16, bool KV8>
@@ -538,7 +604,11 @@ std::function<void(cudaStream_t)> make_pass(const CUtensorMap& kmap, const CUten
 
 int pick_rows(int total_rows) { return total_rows >= 4 ? 4 : (total_rows >= 2 ? 2 : 1); }
 
+unsigned long long* g_decode_trace = nullptr;   // set by decode_simt_set_trace (profiling aid)
+
 }  // namespace
+
+void decode_simt_set_trace(unsigned long long* buf) { g_decode_trace = buf; }
 
 void decode_split(int BH, int cap, int ncta, int* grid, int* max_parts) {
   const int tph = std::max(1, (cap + kTileRows - 1) / kTileRows);
@@ -578,6 +648,10 @@ PreparedLaunch decode_simt_prepare(const AttnShape& s, const void* q, const void
   decode_simt_plan(s, nsm, &grid, &max_parts, &R, &pf, &cf, &cfl);
   const int G = s.Hq / s.Hkv;
   const int total_rows = G * s.Sq;
+  // a CTA queues the heads whose last tile it owns (at most one per head in its range, ranges shrink to one tile per head
+  // for an almost empty cache): (B * Hkv) / grid + 2 of them at worst
+  if ((long long)s.B * s.Hkv / grid + 2 > kMaxPending)
+    throw std::runtime_error("decode_simt: batch x kv-heads too large for one launch (split the batch)");
   if (comm.world > 1) {
     const size_t need_data = (size_t)2 * comm.world * s.B * s.Hkv * R * (s.D + 2) * 8;
     if (need_data > comm.data_bytes)
@@ -589,7 +663,7 @@ PreparedLaunch decode_simt_prepare(const AttnShape& s, const void* q, const void
   CUtensorMap vmap = make_tmap_bhsd(v, eb, s.B, s.Hkv, s.S, s.D, s.v_sb, s.v_sh, s.v_ss, 128 / eb, kTileRows,
                                     CU_TENSOR_MAP_SWIZZLE_128B);
   DecodeParams p;
-  p.kscale = kscale; p.vscale = vscale; p.pdl = pdl; p.kv_len = kv_len;
+  p.kscale = kscale; p.vscale = vscale; p.pdl = pdl; p.kv_len = kv_len; p.trace = g_decode_trace;
   p.q = q; p.out = out; p.lse = lse;
   p.part = reinterpret_cast<uint64_t*>(part); p.wctr = reinterpret_cast<unsigned long long*>(tickets);
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = G; p.Sq = s.Sq; p.S = s.S;

@@ -284,13 +284,14 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       if (d == 0 && p.lse != nullptr) p.lse[((long long)b * p.Hq + (h * p.G + g)) * p.Sq + i] = lse2 * 0.6931471805599453f;
     };
     // split merge + LL-word cross-GPU combine: decode_comm.cuh (shared with decode_simt.cu / decode_tc_sm100.cu)
+    int n_pend = 0;   // heads queued for the merge in drain (uniform across the softmax threads)
     auto make_tail = [&]() {   // built on demand: keeps the tail's bookkeeping out of the tile loop's live registers
       dcomm::Tail tl;
       volatile int* sm = s_tags;
       while (sm[2] == 0) { }    // launch tags fetched by the TMA thread (long done by the first segment end)
       tl.comm = &p.comm; tl.part = p.part; tl.max_parts = p.max_parts; tl.BH = BH;
       tl.R = R; tl.rows_valid = R; tl.wtag = (uint32_t)sm[0]; tl.ctag = (uint32_t)sm[1]; tl.geo = geo;
-      tl.s_misc = s_misc; tl.pending = pending; tl.max_pending = kSwMaxPending; tl.stamps = stamps;
+      tl.pending = pending; tl.max_pending = kSwMaxPending; tl.stamps = stamps;
       return tl;
     };
 
@@ -580,12 +581,12 @@ decode_swap_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
         tc_fence_before();
       }
       it += n;
-      dcomm::segment_done<D, kSmx, 4>(tail, x, tn, tid, 1, store_out);   // the owner of the head's last tile queues the merge
+      dcomm::segment_done<D, kSmx, 4>(tail, x, tn, n_pend, tid, 1, store_out);   // the owner of the head's last tile queues the merge
       named_bar_sync(1, kSmx);  // Q / P^T smem and s_misc reuse by the next segment
       t = tn;
     }
     const dcomm::Tail tail = make_tail();
-    dcomm::drain<D, kSmx, 4>(tail, tid, 1, store_out);
+    dcomm::drain<D, kSmx, 4>(tail, n_pend, tid, 1, store_out);
   }
   tc_fence_before();
   __syncthreads();

@@ -63,6 +63,8 @@ void decode_simt_launch(const AttnShape& s, const void* q, const void* k, const 
                         float* part, uint32_t* tickets, const CommCtxHost& comm, int num_sms,
                         cudaStream_t stream, const uint32_t* kscale = nullptr, const uint32_t* vscale = nullptr,
                         int pdl = 0, const int* kv_len = nullptr);
+// profiling aid: every later decode_simt launch/prepare writes [grid][16] u64 timeline stamps into buf (nullptr = off)
+void decode_simt_set_trace(unsigned long long* buf);
 PreparedLaunch decode_simt_prepare(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                                    float* part, uint32_t* tickets, const CommCtxHost& comm, int num_sms,
                                    const uint32_t* kscale = nullptr, const uint32_t* vscale = nullptr, int pdl = 0,
