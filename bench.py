@@ -275,7 +275,6 @@ def main():
             return 0
         sampler = ClockSampler(local_rank) if rank == 0 else None
         ms, window = timed_loop(torch, dist, ref_step, steps, 0, args.align, world, dev, barrier)
-        clocks = sampled_clocks(torch, dist, sampler, window, ref_step, ms / steps, steps, world, dev, barrier)
         # e2e: pinned q -> device, step, result -> pinned host, every step
         qh = q.cpu().pin_memory()
         oh = torch.empty((B, Hq, 1, D), dtype=dtype).pin_memory()
@@ -290,6 +289,7 @@ def main():
             torch.cuda.synchronize()
         te1 = time.perf_counter()
         e2e_ms = (te1 - te0) * 1e3
+        clocks = sampled_clocks(torch, dist, sampler, window, ref_step, ms / steps, steps, world, dev, barrier)
         if sampler is not None:
             sampler.stop()
         if rank == 0:
@@ -334,17 +334,36 @@ def main():
         return 1
 
     sess.q_static.copy_(q)
+    # this box's copy bandwidth, measured like MEASURED_PEAKS.json (b.copy_(a), read + write bytes, best of 10): boxes of the
+    # pool differ by several percent, so every roofline fraction below is also given against THIS box
+    box_copy_gbs = None
+    try:
+        ca = torch.empty(1 << 29, dtype=torch.bfloat16, device=dev)
+        cb = torch.empty_like(ca)
+        best = 1e9
+        for _ in range(10):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(); cb.copy_(ca); c1.record()
+            torch.cuda.synchronize()
+            best = min(best, c0.elapsed_time(c1))
+        box_copy_gbs = 2 * ca.numel() * 2 / (best * 1e-3) / 1e9
+        del ca, cb
+        torch.cuda.empty_cache()
+    except Exception:
+        pass
     sampler = ClockSampler(local_rank) if rank == 0 else None
     own_step = lambda i: sess.step_device(None, i)
     ms, window = timed_loop(torch, dist, own_step, steps, warmup, args.align, world, dev, barrier)
-    clocks = sampled_clocks(torch, dist, sampler, window, own_step, ms / steps, steps, world, dev, barrier)
 
-    # end-to-end through the public API: pinned host q -> device, step, result -> pinned host, every step
+    # end-to-end through the public API: pinned host q -> device, step, result -> pinned host, every step.  Measured right
+    # after the device-timed region and BEFORE the seconds-long clock-sampling loop below, i.e. in the same thermal / power
+    # state as the device-timed number (the reference arm uses the same order)
     e2e = sess.run_e2e(q, steps, barrier)
     e2e_ms = torch.tensor([e2e["ms"]], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_lat = float(e2e_ms.item()) / steps
+    clocks = sampled_clocks(torch, dist, sampler, window, own_step, ms / steps, steps, world, dev, barrier)
 
     extras = {}
     if world > 1 and not args.no_extras:
@@ -399,6 +418,7 @@ def main():
             "gpu_launches": launches_per_step * steps,
             "decode_tokens_per_s": B / (lat * 1e-3),
             "hbm_gbs_per_gpu": gbs, "hbm_frac_of_measured": gbs / hbm,
+            "box_copy_gbs_rank0": box_copy_gbs, "hbm_frac_of_this_box_copy": (gbs / box_copy_gbs) if box_copy_gbs else None,
             "max_abs_err_vs_oracle": err, "backend": args.backend, "cuda_graph": bool(sess.graphs), "pdl": bool(args.pdl),
             "launch_path": "prepared C++ launch (_C.DecodeStep), one cudaLaunchKernelEx per step" if getattr(sess, "_steps", None) else "python",
             **extras,
