@@ -64,12 +64,6 @@ def main():
             own_clocks = t["clocks"]
             t = time_cuda(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=6), a.steps, a.warmup)
             res["tcgen05_own_v6_q_in_tmem"] = t["median_ms"]
-            try:   # 2-CTA kernel (cta_group::2, half of each B operand per CTA)
-                t = timed_with_clocks(lambda: flash.attention_fwd(q, k, v, scale, bool(causal), 0, 0, variant=7), a.steps, a.warmup)
-                res["tcgen05_own_v7_2cta"] = t["median_ms"]
-                res["tcgen05_own_v7_2cta_sustained"] = t["sustained_ms"]
-            except Exception as e:
-                res["tcgen05_own_v7_2cta_err"] = str(e)[:80]
             if a.libs:
                 try:
                     from flash_attn import flash_attn_func

@@ -77,19 +77,3 @@ def test_public_api_routes_prefill_to_tcgen05():
     out, lse = ta.tree_attention(q, k, v, causal=True, return_lse=True)
     o_ref, l_ref = ref.attention_partial_ref(q, k, v, None, True, 0, 0)
     assert (out.float() - o_ref).abs().max().item() < 2e-2
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("TREE_ATTN_EXPERIMENTAL"),
-                    reason="2-CTA forward (variant 7) is compile-checked only so far (docs/NEXT.md); set TREE_ATTN_EXPERIMENTAL=1")
-@pytest.mark.parametrize("case", [c for c in CASES if c[5] == 128], ids=lambda c: f"{c[3]}x{c[4]}")
-def test_fwd_variant7_two_cta(case):
-    b, hq, hkv, sq, s, d, dtype, causal, q_pos0, kv_pos0, bshd = case
-    q, k, v = _mk(b, hq, hkv, sq, s, d, dtype, bshd=bshd)
-    scale = d ** -0.5
-    if q_pos0 is None:
-        q_pos0 = s - sq
-    out, lse = flash.attention_fwd(q, k, v, scale, causal, q_pos0, kv_pos0, variant=7)
-    torch.cuda.synchronize()
-    o_ref, l_ref = ref.attention_partial_ref(q, k, v, scale, causal, q_pos0, kv_pos0, torch.float32)
-    tol = 2e-2 if dtype == torch.bfloat16 else 5e-3
-    assert (out.float() - o_ref).abs().max().item() < tol

@@ -25,7 +25,7 @@ BUILD_DIR = CSRC / "build"
 SO_PATH = BUILD_DIR / "_C.so"
 HASH_PATH = BUILD_DIR / "_C.hash"
 
-CUDA_SOURCES = ["decode_simt.cu", "decode_tc_sm100.cu", "decode_swap_sm100.cu", "combine.cu", "umma_probe.cu", "attn_fwd_sm100.cu", "attn_fwd7_sm100.cu", "attn_bwd_sm100.cu",
+CUDA_SOURCES = ["decode_simt.cu", "decode_tc_sm100.cu", "decode_swap_sm100.cu", "combine.cu", "umma_probe.cu", "attn_fwd_sm100.cu", "attn_bwd_sm100.cu",
                 "quant.cu", "reduce.cu"]
 CPP_SOURCES = ["bindings.cpp"]
 NVCC_FLAGS = [

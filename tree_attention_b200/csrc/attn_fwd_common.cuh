@@ -1,5 +1,5 @@
-// Shared pieces of the tcgen05 forward kernels (attn_fwd_sm100.cu: M = 128 per CTA; attn_fwd7_sm100.cu: a CTA pair with
-// cta_group::2 MMAs): parameters, the fused-mode merge CTA and the epoch bookkeeping.
+// Shared pieces of the tcgen05 forward kernel (attn_fwd_sm100.cu: M = 128 per CTA): parameters, the fused-mode merge CTA
+// and the epoch bookkeeping.
 // Reference: merge_item() is the combine of /root/reference/model.py:103-124 (global max, exp-rescaled numerator / denominator
 // sums, divide) applied to one 128-row tile across ranks, in fp32 and in fixed rank order.
 #pragma once

@@ -154,16 +154,13 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at:
               "lse must be contiguous fp32 (B, Hq, Sq)");
   CommCtxHost c;
   if (!comm.is_none()) c = comm.cast<Comm&>().h;
-  // variant 0 / 1: the M = 128 kernel with double-buffered S; 6: the same kernel with the query tile kept in TMEM;
-  // 7: EXPERIMENTAL 2-CTA kernel (csrc/attn_fwd7_sm100.cu).  The M = 256 / split-softmax pipelines of round 1
-  // (variants 2-5) measured within +-4 % of variant 1 and were removed (DESIGN.md section 5b keeps the numbers).
-  TORCH_CHECK(variant == 0 || variant == 1 || variant == 6 || variant == 7, "attn_fwd: unknown variant ", variant);
-  if (variant == 7)
-    ta::attn_fwd7_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
-                         at::cuda::getCurrentCUDAStream());
-  else
-    ta::attn_fwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
-                        at::cuda::getCurrentCUDAStream(), variant == 6 ? 1 : 0);
+  // variant 0 / 1: the M = 128 kernel with double-buffered S; 6: the same kernel with the query tile kept in TMEM.
+  // The other pipelines of rounds 1-2 were measured and removed (DESIGN.md section 5b keeps the numbers): M = 256 /
+  // split-softmax variants 2-5 landed within +-4 % of variant 1; the 2-CTA kernel (cta_group::2 MMAs + TMA multicast,
+  // variant 7) passed its tests in round 2 but ran at 734-800 TFLOP/s against 1165 / 1006 for variant 1.
+  TORCH_CHECK(variant == 0 || variant == 1 || variant == 6, "attn_fwd: unknown variant ", variant);
+  ta::attn_fwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
+                      at::cuda::getCurrentCUDAStream(), variant == 6 ? 1 : 0);
 }
 
 py::tuple decode_tc_plan(int B, int Hq, int Hkv, int Sq, int S, int D) {

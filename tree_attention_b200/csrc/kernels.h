@@ -125,9 +125,6 @@ void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const voi
                      const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem = 0);
 void attn_fwd_phase_cycles(unsigned long long* out5);   // profiling aid, see attn_fwd_sm100.cu
 size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
-// EXPERIMENTAL (compile-checked only): cluster of two CTAs, tcgen05.mma.cta_group::2 with M = 256, half of each B operand per CTA
-void attn_fwd7_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                      const CommCtxHost& comm, cudaStream_t stream);
 // ---- tcgen05 flash-attention backward over one KV shard with the GLOBAL o / lse ----
 // dq: fp32 (B, Hq, Sq, D) contiguous (this shard's partial); dk, dv: (B, Hkv, S, D) contiguous, I/O dtype;
 // delta, lse2: fp32 scratch (B, Hq, ceil64(Sq)).
