@@ -166,3 +166,24 @@ def test_kv_len_ragged_gloo(port):
 
 def test_decode_session_gloo(port):
     run_distributed(_worker_session, 2, port)
+
+
+def _worker_sharded_output(rank, world):
+    """output='sharded': this rank's block of query rows, whole 128-row tiles per rank (CPU path: slices the replicated
+    result; the fused GPU path produces the same layout with a reduce-scatter inside the kernel)."""
+    import tree_attention_b200 as ta
+    from tree_attention_b200.ops import reference as ref
+
+    sq = 300
+    q, k, v = ta.make_data((1, 2, 64, 16), rank, "cpu", dtype=torch.float32, sq=sq, log=False)
+    o_full, l_full = ta.tree_attention(q, k, v, return_lse=True, backend="gloo")
+    o_sh, l_sh = ta.tree_attention(q, k, v, return_lse=True, backend="gloo", output="sharded")
+    n = ((sq + 127) // 128 + world - 1) // world * 128
+    assert o_sh.shape == (1, 2, n, 16) and l_sh.shape == (1, 2, n)
+    lo, hi = min(rank * n, sq), min((rank + 1) * n, sq)
+    assert torch.equal(o_sh[:, :, : hi - lo], o_full[:, :, lo:hi])
+    assert torch.equal(l_sh[:, :, : hi - lo], l_full[:, :, lo:hi])
+
+
+def test_sharded_output_gloo(port):
+    run_distributed(_worker_sharded_output, 2, port)

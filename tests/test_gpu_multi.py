@@ -122,11 +122,29 @@ def _worker_prefill(rank, world):
                 dist.all_gather(outs, out.contiguous())
                 for o in outs:
                     assert torch.equal(o, outs[0]), "fused prefill: ranks disagree bitwise"
-    # repeated launches: parity / epoch reuse
+                # Sq-sharded output: the reduce-scatter half only -- this rank's rows, bitwise the replicated result
+                o_sh, l_sh = ta.tree_attention(q, k, v, causal=causal, return_lse=True, backend="fused", output="sharded")
+                torch.cuda.synchronize()
+                n = ((sq + 127) // 128 + world - 1) // world * 128
+                assert o_sh.shape == (b, hq, n, d) and l_sh.shape == (b, hq, n)
+                lo, hi = min(rank * n, sq), min((rank + 1) * n, sq)
+                assert torch.equal(o_sh[:, :, : hi - lo], out[:, :, lo:hi]), "sharded rows differ from the replicated result"
+                assert torch.equal(l_sh[:, :, : hi - lo], lse[:, :, lo:hi])
+    # repeated launches: slot / epoch reuse of both modes, interleaved
     for it in range(50):
         out = ta.tree_attention(q, k, v, causal=True, backend="fused")
+        if it % 5 == 0:
+            o_sh = ta.tree_attention(q, k, v, causal=True, backend="fused", output="sharded")
     torch.cuda.synchronize()
     assert (out.float() - o_ref).abs().max().item() < 3e-2
+    assert torch.equal(o_sh[:, :, : hi - lo], out[:, :, lo:hi])
+    # a long query block in chunks (symmetric buffer capped): same result
+    import os
+    os.environ["TREE_ATTN_FWD_SYMM_CAP_GB"] = "0.004"
+    out_c = ta.tree_attention(q, k, v, causal=True, backend="fused")
+    torch.cuda.synchronize()
+    del os.environ["TREE_ATTN_FWD_SYMM_CAP_GB"]
+    assert torch.equal(out_c, out), "chunked fused prefill differs"
 
 
 @need2

@@ -73,9 +73,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   const int hq = bh % p.Hq, b = bh / p.Hq;
   const int hkv = hq / p.G;
   const int m0 = m_tile * kBlockM;
-  constexpr int kSlotBytes = kBlockM * D * 2 + kBlockM * 4;
-  const size_t slot_off = kComm ? ((size_t)((epoch & 1) * p.comm.world + p.comm.rank) * p.n_items + item) * kSlotBytes : 0;
-  const size_t flag_off = kComm ? ((size_t)((epoch & 1) * p.comm.world + p.comm.rank) * p.n_items + item) : 0;
+  // fused combine: this tile's partial goes to the OWNER of the tile only (reduce-scatter over the query tiles)
+  using SL = FwdSlots<D>;
+  int owner = 0;
+  size_t slot_off = 0, flag_off = 0;
+  if constexpr (kComm) {
+    owner = min(m_tile / p.tiles_per_rank, p.comm.world - 1);
+    const int litem = bh * p.tiles_per_rank + (m_tile - owner * p.tiles_per_rank);
+    slot_off = SL::part_off(p, epoch, p.comm.rank, litem);
+    flag_off = SL::part_flag(p, epoch, p.comm.rank, litem);
+  }
 
   // number of KV tiles this query tile can see
   int n_end = p.S;
@@ -90,13 +97,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
     // nothing visible: the monoid identity (0, -inf)
     if constexpr (kComm) {
       if (!p.comm.skip_publish) {
-        for (int dst = 0; dst < p.comm.world; ++dst) {
-          uint8_t* slot = reinterpret_cast<uint8_t*>(p.comm.data[dst]) + slot_off;
-          for (int c = tid; c < kBlockM * (D / 8); c += kFwdThreads) reinterpret_cast<uint4*>(slot)[c] = make_uint4(0, 0, 0, 0);
-          if (tid < kBlockM) reinterpret_cast<float*>(slot + kBlockM * D * 2)[tid] = neg_inf_f();
-        }
+        uint8_t* slot = reinterpret_cast<uint8_t*>(p.comm.data[owner]) + slot_off;
+        for (int c = tid; c < kBlockM * (D / 8); c += kFwdThreads) reinterpret_cast<uint4*>(slot)[c] = make_uint4(0, 0, 0, 0);
+        if (tid < kBlockM) reinterpret_cast<float*>(slot + kBlockM * D * 2)[tid] = neg_inf_f();
         __syncthreads();
-        if (tid < p.comm.world) { fence_acq_rel_sys(); st_release_sys_u32(p.comm.flags[tid] + flag_off, epoch); }
+        if (tid == 0) { fence_acq_rel_sys(); st_release_sys_u32(p.comm.flags[owner] + flag_off, epoch); }
       }
       comm_kernel_exit(p, epoch);
     } else if (warp < 4) {
@@ -410,25 +415,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         tma_store_wait<0>();
       }
     } else {
-      // fused tree combine, step 1: push this rank's partial tile (o in the I/O dtype, lse fp32) into slot
-      // [parity][my rank][item] of EVERY rank's symmetric buffer with coalesced 16-byte P2P stores, then
-      // release one epoch flag per destination.
+      // fused tree combine, step 1 (reduce-scatter): push this rank's partial tile (o in the I/O dtype, lse fp32) into
+      // slot [my rank][local item] of the tile's OWNER with coalesced 16-byte P2P stores, then release its epoch flag.
       tc_fence_before();
       named_bar_sync(1, kSoftmaxThreads);
       if (!p.comm.skip_publish) {
         constexpr int CPR = D / 8;
-        for (int dst = 0; dst < p.comm.world; ++dst) {
-          uint8_t* slot = reinterpret_cast<uint8_t*>(p.comm.data[dst]) + slot_off;
+        uint8_t* slot = reinterpret_cast<uint8_t*>(p.comm.data[owner]) + slot_off;
 #pragma unroll 4
-          for (int c = tid; c < kBlockM * CPR; c += kSoftmaxThreads) {
-            const int r = c / CPR, ch = c - r * CPR;
-            const uint4 w = *reinterpret_cast<const uint4*>(q_s + (ch >> 3) * SM::kAtomBytes + r * 128 + (((ch & 7) ^ (r & 7)) << 4));
-            *reinterpret_cast<uint4*>(slot + (size_t)r * D * 2 + ch * 16) = w;
-          }
-          reinterpret_cast<float*>(slot + kBlockM * D * 2)[row] = lse_row;
+        for (int c = tid; c < kBlockM * CPR; c += kSoftmaxThreads) {
+          const int r = c / CPR, ch = c - r * CPR;
+          const uint4 w = *reinterpret_cast<const uint4*>(q_s + (ch >> 3) * SM::kAtomBytes + r * 128 + (((ch & 7) ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(slot + (size_t)r * D * 2 + ch * 16) = w;
         }
+        reinterpret_cast<float*>(slot + kBlockM * D * 2)[row] = lse_row;
         named_bar_sync(1, kSoftmaxThreads);
-        if (tid < p.comm.world) { fence_acq_rel_sys(); st_release_sys_u32(p.comm.flags[tid] + flag_off, epoch); }
+        if (tid == 0) { fence_acq_rel_sys(); st_release_sys_u32(p.comm.flags[owner] + flag_off, epoch); }
       }
     }
   }
@@ -443,12 +445,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
 
 template <int D, bool BF16, bool kComm>
 void launch_fwd(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem) {
+                const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem, int comm_mode, int sq_out) {
   using SM = FwdSmem<D>;
   CUtensorMap qmap = make_tmap_bhsd(q, 2, s.B, s.Hq, s.Sq, D, s.q_sb, s.q_sh, s.q_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap kmap = make_tmap_bhsd(k, 2, s.B, s.Hkv, s.S, D, s.k_sb, s.k_sh, s.k_ss, 64, kBlockN, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap vmap = make_tmap_bhsd(v, 2, s.B, s.Hkv, s.S, D, s.v_sb, s.v_sh, s.v_ss, 64, kBlockN, CU_TENSOR_MAP_SWIZZLE_128B);
-  CUtensorMap omap = make_tmap_bhsd(out, 2, s.B, s.Hq, s.Sq, D, s.o_sb, s.o_sh, s.o_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
+  // (fused mode writes `out` with plain stores from the merge CTAs; the TMA store map is only used single-GPU)
+  const int out_rows = (kComm && comm_mode == 2) ? sq_out : s.Sq;
+  CUtensorMap omap = make_tmap_bhsd(out, 2, s.B, s.Hq, out_rows, D, s.o_sb, s.o_sh, s.o_ss, 64, kBlockM, CU_TENSOR_MAP_SWIZZLE_128B);
   FwdParams p;
   p.lse = lse; p.out = out; p.o_sb = s.o_sb; p.o_sh = s.o_sh; p.o_ss = s.o_ss;
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = s.Hq / s.Hkv; p.Sq = s.Sq; p.S = s.S;
@@ -459,11 +463,23 @@ void launch_fwd(const AttnShape& s, const void* q, const void* k, const void* v,
   p.lag = std::min(p.n_items, 2 * num_sms());
   p.q_in_tmem = q_in_tmem;
   p.comm = to_device_ctx(comm);
+  p.mode = 0; p.tiles_per_rank = p.num_m_tiles; p.n_local = p.n_items; p.final_off = 0; p.final_flag_off = 0;
+  p.sq_out = s.Sq;
   if (kComm) {
+    const int W = comm.world;
     const size_t slot = (size_t)kBlockM * D * 2 + kBlockM * 4;
-    if ((size_t)2 * comm.world * p.n_items * slot > comm.data_bytes ||
-        (size_t)2 * comm.world * p.n_items * 4 > comm.flag_bytes)
+    p.mode = comm_mode == 2 ? 2 : 1;
+    p.tiles_per_rank = (p.num_m_tiles + W - 1) / W;
+    p.n_local = s.B * s.Hq * p.tiles_per_rank;
+    const size_t part_bytes = (size_t)(p.mode == 2 ? 2 : 1) * W * p.n_local * slot;
+    const size_t part_flags = (size_t)(p.mode == 2 ? 2 : 1) * W * p.n_local;
+    p.final_off = (long long)part_bytes;
+    p.final_flag_off = (int)part_flags;
+    const size_t need_data = part_bytes + (p.mode == 1 ? (size_t)p.n_items * slot : 0);
+    const size_t need_flags = (part_flags + (p.mode == 1 ? (size_t)p.n_items : 0)) * 4;
+    if (need_data > comm.data_bytes || need_flags > comm.flag_bytes)
       throw std::runtime_error("attn_fwd(fused): symmetric buffer too small");
+    if (p.mode == 2) p.sq_out = sq_out;
   }
   auto kern = attn_fwd_kernel<D, BF16, kComm>;
   static bool configured = false;
@@ -482,22 +498,26 @@ void attn_fwd_phase_cycles(unsigned long long* out5) {
   TA_CUDA_CHECK(cudaMemcpyFromSymbol(out5, g_fwd_phase_cycles, 5 * sizeof(unsigned long long)));
 }
 
-size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes) {
-  const size_t n_items = (size_t)((s.Sq + kBlockM - 1) / kBlockM) * s.Hq * s.B;
+size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes, int comm_mode) {
+  const size_t num_m = (size_t)((s.Sq + kBlockM - 1) / kBlockM);
+  const size_t n_items = num_m * s.Hq * s.B;
+  const size_t tpr = (num_m + world - 1) / world;
+  const size_t n_local = (size_t)s.B * s.Hq * tpr;
   const size_t slot = (size_t)kBlockM * s.D * 2 + kBlockM * 4;
-  *flag_bytes = (size_t)2 * world * n_items * 4;
-  return (size_t)2 * world * n_items * slot;
+  const size_t par = comm_mode == 2 ? 2 : 1;
+  *flag_bytes = (par * world * n_local + (comm_mode == 2 ? 0 : n_items)) * 4;
+  return par * world * n_local * slot + (comm_mode == 2 ? 0 : n_items * slot);
 }
 
 void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                     const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem) {
+                     const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem, int comm_mode, int sq_out) {
   if (s.D != 64 && s.D != 128) throw std::runtime_error("attn_fwd: head_dim must be 64 or 128");
   if (s.Hq % s.Hkv != 0) throw std::runtime_error("attn_fwd: Hq must be a multiple of Hkv");
   if (s.S <= 0 || s.Sq <= 0) throw std::runtime_error("attn_fwd: empty problem");
   const bool fused = comm.world > 1;
 #define TA_FWD(DD, BB)                                                               \
-  if (fused) launch_fwd<DD, BB, true>(s, q, k, v, out, lse, comm, stream, q_in_tmem);           \
-  else launch_fwd<DD, BB, false>(s, q, k, v, out, lse, comm, stream, q_in_tmem);
+  if (fused) launch_fwd<DD, BB, true>(s, q, k, v, out, lse, comm, stream, q_in_tmem, comm_mode, sq_out);           \
+  else launch_fwd<DD, BB, false>(s, q, k, v, out, lse, comm, stream, q_in_tmem, comm_mode, sq_out);
   if (s.D == 128) {
     if (s.is_bf16) { TA_FWD(128, true) } else { TA_FWD(128, false) }
   } else {

@@ -138,20 +138,34 @@ void decode_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, a
                          at::cuda::getCurrentCUDAStream(), nullptr, nullptr, pdl, kv_len_ptr(kv_len, k));
 }
 
-py::tuple attn_fwd_comm_bytes(int B, int Hq, int Sq, int D, int world) {
+py::tuple attn_fwd_comm_bytes(int B, int Hq, int Sq, int D, int world, int comm_mode) {
   AttnShape s;
   s.B = B; s.Hq = Hq; s.Sq = Sq; s.D = D;
   size_t fb = 0;
-  size_t db = ta::attn_fwd_comm_bytes(s, world, &fb);
+  size_t db = ta::attn_fwd_comm_bytes(s, world, &fb, comm_mode);
   return py::make_tuple((int64_t)db, (int64_t)fb);
 }
 
+// comm_mode (with a Comm): 1 = replicated output, 2 = output sharded over Sq -- out is (B, Hq, sq_out, D), lse (B, Hq, sq_out)
+// with sq_out = ceil(ceil(Sq / 128) / world) * 128, the rows [rank * sq_out, ...) of the global result.
 void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out, at::Tensor& lse,
-              double scale, bool causal, int64_t q_pos0, int64_t kv_pos0, py::object comm, int variant) {
+              double scale, bool causal, int64_t q_pos0, int64_t kv_pos0, py::object comm, int variant, int comm_mode) {
   c10::cuda::CUDAGuard guard(q.device());
-  AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
-  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == (int64_t)s.B * s.Hq * s.Sq,
-              "lse must be contiguous fp32 (B, Hq, Sq)");
+  const bool sharded = !comm.is_none() && comm_mode == 2;
+  AttnShape s = make_shape(q, k, v, sharded ? q : out, scale, causal, q_pos0, kv_pos0);
+  int64_t sq_out = s.Sq;
+  if (sharded) {
+    TORCH_CHECK(out.dim() == 4 && out.is_cuda() && out.scalar_type() == q.scalar_type() && out.stride(3) == 1 &&
+                    out.size(0) == q.size(0) && out.size(1) == q.size(1) && out.size(3) == q.size(3),
+                "sharded out must be (B, Hq, sq_out, D) in q's dtype");
+    sq_out = out.size(2);
+    const int world = comm.cast<Comm&>().h.world;
+    const int64_t num_m = (s.Sq + 127) / 128;
+    TORCH_CHECK(sq_out == (num_m + world - 1) / world * 128, "sharded out must have ceil(ceil(Sq/128)/world)*128 rows");
+    s.o_sb = out.stride(0); s.o_sh = out.stride(1); s.o_ss = out.stride(2);
+  }
+  TORCH_CHECK(lse.scalar_type() == at::kFloat && lse.is_contiguous() && lse.numel() == (int64_t)s.B * s.Hq * sq_out,
+              "lse must be contiguous fp32 (B, Hq, Sq) [(B, Hq, sq_out) for a sharded output]");
   CommCtxHost c;
   if (!comm.is_none()) c = comm.cast<Comm&>().h;
   // variant 0 / 1: the M = 128 kernel with double-buffered S; 6: the same kernel with the query tile kept in TMEM.
@@ -160,7 +174,7 @@ void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at:
   // variant 7) passed its tests in round 2 but ran at 734-800 TFLOP/s against 1165 / 1006 for variant 1.
   TORCH_CHECK(variant == 0 || variant == 1 || variant == 6, "attn_fwd: unknown variant ", variant);
   ta::attn_fwd_launch(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr<float>(), c,
-                      at::cuda::getCurrentCUDAStream(), variant == 6 ? 1 : 0);
+                      at::cuda::getCurrentCUDAStream(), variant == 6 ? 1 : 0, comm_mode, (int)sq_out);
 }
 
 py::tuple decode_tc_plan(int B, int Hq, int Hkv, int Sq, int S, int D) {
@@ -558,8 +572,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("quant_mxfp8", &quant_mxfp8);
   m.def("quant_mxfp8_seq", &quant_mxfp8_seq);
   m.def("dequant_mxfp8", &dequant_mxfp8);
-  m.def("attn_fwd", &attn_fwd);
-  m.def("attn_fwd_comm_bytes", &attn_fwd_comm_bytes);
+  m.def("attn_fwd", &attn_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("lse"), py::arg("scale"),
+        py::arg("causal"), py::arg("q_pos0"), py::arg("kv_pos0"), py::arg("comm"), py::arg("variant") = 0, py::arg("comm_mode") = 1);
+  m.def("attn_fwd_comm_bytes", &attn_fwd_comm_bytes, py::arg("B"), py::arg("Hq"), py::arg("Sq"), py::arg("D"), py::arg("world"),
+        py::arg("comm_mode") = 1);
   m.def("attn_fwd_phase_cycles", []() { unsigned long long c[5]; ta::attn_fwd_phase_cycles(c); return py::make_tuple(c[0], c[1], c[2], c[3], c[4]); });
   m.def("attn_bwd", &attn_bwd);
   m.def("symm_allreduce", &symm_allreduce);

@@ -121,10 +121,13 @@ void umma_bs_probe_launch(const void* a8, const void* b8, const void* sfa, const
 // ---- tcgen05 flash-attention forward: shard-local partial (o normalised, lse natural log) ----
 // comm.world > 1: fused mode -- compute CTAs push their partial tiles to every peer, merge CTAs in the same
 // launch produce the final (replicated) output; no NCCL.
+// comm_mode (fused mode only): 1 = replicated output (reduce-scatter of the partial tiles to their owner rank + all-gather
+// of the final tiles), 2 = output sharded over Sq: `out` / `lse` hold sq_out = tiles_per_rank * 128 rows per (b, head), the
+// rows [rank * sq_out, (rank + 1) * sq_out) of the global result.
 void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
-                     const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem = 0);
+                     const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem = 0, int comm_mode = 1, int sq_out = 0);
 void attn_fwd_phase_cycles(unsigned long long* out5);   // profiling aid, see attn_fwd_sm100.cu
-size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes);
+size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes, int comm_mode = 1);
 // ---- tcgen05 flash-attention backward over one KV shard with the GLOBAL o / lse ----
 // dq: fp32 (B, Hq, Sq, D) contiguous (this shard's partial); dk, dv: (B, Hkv, S, D) contiguous, I/O dtype;
 // delta, lse2: fp32 scratch (B, Hq, ceil64(Sq)).

@@ -43,20 +43,31 @@ def attention_fwd(
     out: Optional[torch.Tensor] = None,
     comm=None,
     variant: int = 0,
+    comm_mode: int = 1,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Shard-local partial ``(o, lse)``; with ``comm`` (a ``_C.Comm`` of the ``fwd`` family) the SAME launch
-    also performs the cross-GPU combine and ``(o, lse)`` are the global, replicated results."""
+    """Shard-local partial ``(o, lse)``; with ``comm`` (a ``_C.Comm`` of the ``fwd`` family) the SAME launch also performs
+    the cross-GPU combine: ``comm_mode=1`` -> the global result replicated on every rank, ``comm_mode=2`` -> the global
+    result sharded over Sq (this rank's ``sq_out`` rows, see ``sharded_rows``)."""
     C = _build.load()
     q = q if q.stride(-1) == 1 else q.contiguous()
     k = k if k.stride(-1) == 1 else k.contiguous()
     v = v if v.stride(-1) == 1 else v.contiguous()
     b, hq, sq, d = q.shape
+    rows = sq
+    if comm is not None and comm_mode == 2:
+        rows = sharded_rows(sq, comm.world)
     if out is None:
-        out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
-    lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
+        out = torch.empty((b, hq, rows, d), dtype=q.dtype, device=q.device)
+    lse = torch.empty((b, hq, rows), dtype=torch.float32, device=q.device)
     C.attn_fwd(q, k, v, out, lse, float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0), comm,
-               int(os.environ.get("TREE_ATTN_FWD_VARIANT", variant)))
+               int(os.environ.get("TREE_ATTN_FWD_VARIANT", variant)), int(comm_mode))
     return out, lse
+
+
+def sharded_rows(sq: int, world: int) -> int:
+    """Rows of the Sq-sharded output per rank: whole 128-row query tiles, contiguous blocks in rank order."""
+    tiles = (sq + 127) // 128
+    return (tiles + world - 1) // world * 128
 
 
 def bwd_eligible(q: torch.Tensor, k: torch.Tensor) -> bool:
@@ -99,12 +110,18 @@ def attention_fwd_fused(
     kv_pos0: int = 0,
     group=None,
     return_lse: bool = True,
+    output: str = "replicated",
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """ONE launch per rank: tcgen05 attention over the local KV shard, partial tiles pushed to every peer
-    over NVLink from the epilogue, merge CTAs of the same launch write the replicated result.  No NCCL.
+    """ONE launch per rank: tcgen05 attention over the local KV shard; every 128-row query tile has an owner rank, the
+    partial tiles are pushed to their owner over NVLink from the epilogue (reduce-scatter), merge CTAs of the same launch
+    combine them and -- ``output="replicated"`` -- push the final tiles to every peer (all-gather).  No NCCL.
 
-    Very long query blocks are processed in chunks so that the symmetric buffer (2 x W x |O| in the I/O
-    dtype) stays under ``TREE_ATTN_FWD_SYMM_CAP_GB`` (default 8)."""
+    ``output="sharded"``: returns this rank's rows of the global result, ``(B, Hq, sharded_rows(Sq, W), D)`` = rows
+    ``[rank * n, (rank + 1) * n)`` (the last rank's block may run past Sq; those rows are undefined).  NVLink traffic per
+    rank is ``(W-1)/W |O|`` (sharded) or twice that (replicated); the symmetric buffer is ``2 |O|`` either way.
+
+    Replicated mode processes very long query blocks in chunks so that the symmetric buffer stays under
+    ``TREE_ATTN_FWD_SYMM_CAP_GB`` (default 8)."""
     import os
 
     import torch.distributed as dist
@@ -115,9 +132,16 @@ def attention_fwd_fused(
     world = dist.get_world_size(group)
     b, hq, sq, d = q.shape
     cap = int(float(os.environ.get("TREE_ATTN_FWD_SYMM_CAP_GB", "8")) * (1 << 30))
-    per_row = 2 * world * b * hq * (d * 2 + 4)
-    chunk = max(128, min(sq, (cap // per_row) // 128 * 128))
-    data, flags = C.attn_fwd_comm_bytes(b, hq, min(chunk, sq), d, world)
+    if output == "sharded":
+        data, flags = C.attn_fwd_comm_bytes(b, hq, sq, d, world, 2)
+        reg = symm.get_region("fwd_rs", int(data), int(flags), group, layout=(b, hq, sq, d))
+        o_c, l_c = attention_fwd(q, k, v, softmax_scale, causal, q_pos0, kv_pos0, comm=reg.comm, comm_mode=2)
+        return o_c, (l_c if return_lse else None)
+    if output != "replicated":
+        raise ValueError("output must be 'replicated' or 'sharded'")
+    per_row = 2 * b * hq * (d * 2 + 4)   # partial slots on the owners + final slots: ~2 |O| bytes per query row
+    chunk = max(128 * world, min(sq, (cap // per_row) // (128 * world) * (128 * world)))
+    data, flags = C.attn_fwd_comm_bytes(b, hq, min(chunk, sq), d, world, 1)
     reg = symm.get_region("fwd", int(data), int(flags), group, layout=(b, hq, min(chunk, sq), d))
     out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
     lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)

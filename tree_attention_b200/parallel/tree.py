@@ -208,6 +208,7 @@ def tree_attention(
     layout: str = "bhsd",
     decode_pdl: int = 0,
     kv_len=None,
+    output: str = "replicated",
 ) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
     """Exact attention of replicated ``q`` over a KV sequence sharded across the ranks of ``group``.
 
@@ -227,10 +228,20 @@ def tree_attention(
     the softmax.  The decode kernels read the value on the device, so a CUDA graph captured once follows a growing
     cache; ranks may have different (including zero) fill levels.
 
+    ``output="sharded"``: return only this rank's block of query rows of the global result (and ``lse``):
+    ``n = ceil(ceil(Sq / 128) / W) * 128`` rows ``[rank * n, (rank + 1) * n)`` as a ``(B, Hq, n, D)`` tensor (rows past
+    ``Sq`` in the last block are undefined).  On the fused prefill path this is a reduce-scatter inside the attention
+    kernel -- every rank receives ``(W-1)/W |O|`` bytes instead of sending ``(W-1) |O|`` -- other paths slice.
+
     Returns the global attention output (replicated, bitwise identical across ranks for the fused and
     symm backends) and optionally the global ``lse``.
     """
     from ..ops.quant import FP8ChannelTensor, MXFP8Tensor
+
+    if output not in ("replicated", "sharded"):
+        raise ValueError("output must be 'replicated' or 'sharded'")
+    if output == "sharded" and layout != "bhsd":
+        raise ValueError("output='sharded' needs layout='bhsd'")
 
     quantised = isinstance(k, (MXFP8Tensor, FP8ChannelTensor))
     if layout == "bshd":
@@ -274,7 +285,9 @@ def tree_attention(
                 raise NotImplementedError("kv_len with the fused prefill kernel: slice the shard instead (every rank "
                                           "must still launch; an empty shard is not supported on this path)")
             o, lse = flash.attention_fwd_fused(q, k, v, scale, causal, q_pos0, kv_pos0, group=group,
-                                               return_lse=return_lse)
+                                               return_lse=return_lse, output=output)
+            if output == "sharded":   # already this rank's rows (reduce-scatter inside the kernel)
+                return (o, lse) if return_lse else o
     else:  # symm | collective
         with _nvtx("tree_attention/local_partial"):
             o_p, lse_p = local_ops.attention_partial(q, k, v, scale, causal, q_pos0, kv_pos0, kv_len=kv_len)
@@ -284,9 +297,26 @@ def tree_attention(
         with _nvtx(f"tree_attention/combine[{be}:{sched}]"):
             o, lse = combine_partials(o_p, lse_p, group, "symm" if be == "symm" else "collective", sched,
                                       out_dtype=o_p.dtype)
+    if output == "sharded":
+        o, lse = shard_rows(o, lse, rank, world)
     if layout == "bshd":
         o = o.transpose(1, 2)
     return (o, lse) if return_lse else o
+
+
+def shard_rows(o: torch.Tensor, lse: Optional[torch.Tensor], rank: int, world: int):
+    """This rank's block of query rows of a replicated ``(B, Hq, Sq, D)`` result, padded to whole 128-row tiles per rank
+    (the layout the fused reduce-scatter path produces)."""
+    sq = o.shape[2]
+    n = ((sq + 127) // 128 + world - 1) // world * 128
+    lo, hi = min(rank * n, sq), min((rank + 1) * n, sq)
+    o_s = o.new_zeros((o.shape[0], o.shape[1], n, o.shape[3]))
+    o_s[:, :, : hi - lo] = o[:, :, lo:hi]
+    l_s = None
+    if lse is not None:
+        l_s = lse.new_full((lse.shape[0], lse.shape[1], n), float("-inf"))
+        l_s[:, :, : hi - lo] = lse[:, :, lo:hi]
+    return o_s, l_s
 
 
 def _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset, q_offset, return_lse, backend,
