@@ -190,3 +190,21 @@ def test_seq_blocked_quantiser_kernel_matches_oracle(s, dtype):
     b = quant.MXFP8SeqTensor.from_float_ref(x)
     assert a.scales.shape == b.scales.shape and torch.equal(a.scales, b.scales)
     assert torch.equal(a.data, b.data)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("position,n", [(0, 1), (31, 1), (31, 2), (100, 70), (4090, 6), (4000, 96)])
+def test_seq_blocked_append_kernel_matches_oracle(position, n, dtype):
+    """Device-side KV append into the key-blocked MX cache (csrc/quant.cu mxfp8_seq_append_kernel) == the PyTorch oracle
+    (de-quantise the touched 32-key blocks, insert, re-quantise), bit for bit."""
+    g = torch.Generator(device="cuda").manual_seed(position * 7 + n)
+    x = torch.randn(2, 3, 4096, 128, device="cuda", generator=g).to(dtype)
+    a = quant.MXFP8SeqTensor.from_float(x)
+    b = quant.MXFP8SeqTensor(a.data.clone(), a.scales.clone())
+    new = (torch.randn(2, 3, n, 128, device="cuda", generator=g) * 4).to(dtype)
+    a.write_rows(position, new)          # CUDA kernel
+    b.write_rows_ref(position, new)      # oracle
+    torch.cuda.synchronize()
+    assert torch.equal(a.scales, b.scales)
+    assert torch.equal(a.data, b.data)
+    assert (a.dequantize()[:, :, position:position + n] - new.float()).abs().max().item() < 0.3

@@ -436,6 +436,21 @@ py::tuple quant_mxfp8_seq(const at::Tensor& x) {
   return py::make_tuple(q, sc);
 }
 
+// in-place KV append into a sequence-blocked MX cache (data (B, H, S, D) uint8, scales (B, H, T, D, 4) uint8): x is (B, H, n, D)
+void mxfp8_seq_append(at::Tensor& data, at::Tensor& sc, const at::Tensor& x, int64_t position) {
+  c10::cuda::CUDAGuard guard(data.device());
+  TORCH_CHECK(data.is_cuda() && data.is_contiguous() && data.dim() == 4 && data.scalar_type() == at::kByte, "data must be contiguous uint8 (B, H, S, D)");
+  TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.size(0) == data.size(0) && x.size(1) == data.size(1) && x.size(3) == data.size(3),
+              "x must be (B, H, n, D)");
+  const int64_t B = data.size(0), H = data.size(1), S = data.size(2), D = data.size(3), T = (S + 127) / 128;
+  TORCH_CHECK(sc.is_cuda() && sc.is_contiguous() && sc.scalar_type() == at::kByte && sc.numel() == B * H * T * D * 4, "scales must be uint8 (B, H, T, D, 4)");
+  at::Tensor xc = x.contiguous();
+  int dt = xc.scalar_type() == at::kBFloat16 ? 0 : xc.scalar_type() == at::kHalf ? 1 : 2;
+  TORCH_CHECK(dt != 2 || xc.scalar_type() == at::kFloat, "x must be bf16, fp16 or fp32");
+  ta::mxfp8_seq_append_launch(xc.data_ptr(), dt, data.data_ptr<uint8_t>(), sc.data_ptr<uint8_t>(), B * H, (int)S, (int)D,
+                              (int)position, (int)xc.size(2), at::cuda::getCurrentCUDAStream());
+}
+
 at::Tensor dequant_mxfp8(const at::Tensor& q, const at::Tensor& sc) {
   c10::cuda::CUDAGuard guard(q.device());
   TORCH_CHECK(q.is_cuda() && q.is_contiguous() && sc.is_contiguous() && q.scalar_type() == at::kByte &&
@@ -571,6 +586,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("kv_pos0"), py::arg("kv_len") = py::none());
   m.def("quant_mxfp8", &quant_mxfp8);
   m.def("quant_mxfp8_seq", &quant_mxfp8_seq);
+  m.def("mxfp8_seq_append", &mxfp8_seq_append);
   m.def("dequant_mxfp8", &dequant_mxfp8);
   m.def("attn_fwd", &attn_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("lse"), py::arg("scale"),
         py::arg("causal"), py::arg("q_pos0"), py::arg("kv_pos0"), py::arg("comm"), py::arg("variant") = 0, py::arg("comm_mode") = 1);

@@ -346,20 +346,15 @@ template <int D, int NT, int RB, typename StoreOut>
 __device__ __forceinline__ void segment_done(const Tail& t, int x, int seg_end_tile, int& n_pend, int tid, int bar_id,
                                              StoreOut& store_out) {
   if (seg_end_tile != (x + 1) * t.geo.tph) return;   // not the owner of the head's last tile: nothing else to do
-  if (n_pend < t.max_pending) {
-    if (tid == 0) t.pending[n_pend] = x;
-    ++n_pend;
-    return;
+  // The list cannot overflow: the launchers bound the heads per CTA by max_pending (decode_*_prepare).  Nothing here may
+  // call out of line -- an out-of-line call inside the streaming loop makes ptxas spill around it, and with 227 KB of
+  // shared memory carved out there is no L1 left to catch the spills (round 2: 10 us per head switch).
+  if (n_pend >= t.max_pending) {
+    printf("[tree_attention] pending-merge list overflow block=%d head=%d\n", blockIdx.x, x);
+    __trap();
   }
-  // list full (more than max_pending whole heads in one CTA's range): finish this head now
-  named_bar_sync(bar_id, NT);
-  merge_head<D, NT>(t, x, tid, store_out);
-  if (t.comm->world > 1) {
-    if (tid == 0) t.stamps[1] = globaltimer_ns();
-    named_bar_sync(bar_id, NT);
-    combine_ranks<D, NT, RB>(t, x, tid, bar_id, store_out);
-  }
-  named_bar_sync(bar_id, NT);
+  if (tid == 0) t.pending[n_pend] = x;
+  ++n_pend;
 }
 
 // after the CTA's last tile: merge (and publish) every queued head, THEN wait for the peers' words of those heads --

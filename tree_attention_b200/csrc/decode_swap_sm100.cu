@@ -623,6 +623,8 @@ PreparedLaunch decode_swap_prepare(const AttnShape& s, const void* q, const void
   int grid, max_parts;
   // one persistent CTA per SM (the driver keeps tcgen05 kernels at one resident CTA per SM: a second CTA only queues)
   decode_split(s.B * s.Hkv, s.S, nsm, &grid, &max_parts);
+  if ((long long)s.B * s.Hkv / grid + 2 > kSwMaxPending)
+    throw std::runtime_error("decode_swap: batch x kv-heads too large for one launch (split the batch)");
   if (comm.world > 1) {
     const size_t need = (size_t)2 * comm.world * s.B * s.Hkv * R * (s.D + 2) * 8;
     if (need > comm.data_bytes) throw std::runtime_error("decode_swap: symmetric buffer too small for this problem");

@@ -514,6 +514,8 @@ PreparedLaunch decode_tc_prepare(const AttnShape& s, const void* q, const void* 
   int grid, max_parts, rows;
   size_t pf, cb;
   decode_tc_plan(s, nsm, &grid, &max_parts, &rows, &pf, &cb);
+  if ((long long)s.B * s.Hkv / grid + 2 > kTcMaxPending)
+    throw std::runtime_error("decode_tc: batch x kv-heads too large for one launch (split the batch)");
   if (comm.world > 1) {
     const size_t need = (size_t)2 * comm.world * s.B * s.Hkv * R * (s.D + 2) * 8;
     if (need > comm.data_bytes) throw std::runtime_error("decode_tc: symmetric buffer too small for this problem");

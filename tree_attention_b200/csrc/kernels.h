@@ -144,6 +144,9 @@ void quant_mxfp8_launch(const void* x, int in_dtype /*0 bf16, 1 fp16, 2 fp32*/, 
                         int64_t nblocks, cudaStream_t stream);
 void quant_mxfp8_seq_launch(const void* x, int in_dtype, uint8_t* q, uint8_t* scales, int64_t bh, int S, int D,
                             cudaStream_t stream);
+// KV append into a sequence-blocked MX cache: rows [pos, pos + n) <- x (BH, n, D); the touched 32-key blocks are re-quantised
+void mxfp8_seq_append_launch(const void* x, int in_dtype, uint8_t* q, uint8_t* scales, int64_t bh, int S, int D, int pos, int n,
+                             cudaStream_t stream);
 void dequant_mxfp8_launch(const uint8_t* q, const uint8_t* scales, float* y, int64_t nblocks, cudaStream_t stream);
 
 }  // namespace ta

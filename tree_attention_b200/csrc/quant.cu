@@ -85,6 +85,56 @@ __global__ void quant_mxfp8_seq_kernel(const void* __restrict__ x, uint8_t* __re
   }
 }
 
+// KV append into a sequence-blocked MX cache: rows [pos, pos + n) of every (b, h) are replaced by x (BH, n, D).  A 32-key
+// block shares one scale per channel, so every block the new rows touch is re-quantised as a whole: old rows are
+// de-quantised with the old scale, the new rows come from x, a new power-of-two scale is chosen and all 32 rows are
+// written back.  One CTA per (bh, touched block), one thread per channel (coalesced across channels).
+template <int IN>
+__global__ void mxfp8_seq_append_kernel(const void* __restrict__ x, uint8_t* __restrict__ q, uint8_t* __restrict__ sc,
+                                        int S, int D, int T, int pos, int n, int g0, int nblk) {
+  const int g = g0 + blockIdx.x % nblk;        // 32-key block of the cache
+  const long long bh = blockIdx.x / nblk;
+  const int d = threadIdx.x;
+  uint8_t* scp = sc + ((bh * T + g / 4) * D + d) * 4 + (g & 3);
+  const float s_old = exp2f((float)((int)*scp - 127));
+  float v[32];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int key = g * 32 + i;
+    float val = 0.f;
+    if (key < S) {
+      if (key >= pos && key < pos + n) {
+        val = load_in<IN>(x, (bh * n + (key - pos)) * D + d);
+      } else {
+        uint32_t h2;
+        asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"((uint16_t)q[(bh * S + key) * D + d]));
+        val = f16lo(h2) * s_old;
+      }
+    }
+    v[i] = val;
+    amax = fmaxf(amax, fabsf(val));
+  }
+  int e = 0;
+  if (amax > 0.f && isfinite(amax)) {
+    int ex;
+    const float m = frexpf(amax / 448.f, &ex);
+    e = (m == 0.5f) ? ex - 1 : ex;  // ceil(log2(amax / 448))
+    e = max(-127, min(127, e));
+  }
+  const float inv = exp2f((float)-e);
+  *scp = (uint8_t)(e + 127);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int key = g * 32 + i;
+    if (key < S) {
+      uint16_t b2;
+      asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(b2) : "f"(0.f), "f"(v[i] * inv));
+      q[(bh * S + key) * D + d] = (uint8_t)(b2 & 0xff);
+    }
+  }
+}
+
 __global__ void dequant_mxfp8_kernel(const uint8_t* __restrict__ q, const uint8_t* __restrict__ sc, float* __restrict__ y,
                                      long long nblocks) {
   const long long blk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,6 +169,20 @@ void quant_mxfp8_seq_launch(const void* x, int in_dtype, uint8_t* q, uint8_t* sc
   if (in_dtype == 0) quant_mxfp8_seq_kernel<0><<<grid, D, 0, stream>>>(x, q, scales, S, D, T);
   else if (in_dtype == 1) quant_mxfp8_seq_kernel<1><<<grid, D, 0, stream>>>(x, q, scales, S, D, T);
   else quant_mxfp8_seq_kernel<2><<<grid, D, 0, stream>>>(x, q, scales, S, D, T);
+  TA_CUDA_CHECK(cudaGetLastError());
+}
+
+void mxfp8_seq_append_launch(const void* x, int in_dtype, uint8_t* q, uint8_t* scales, int64_t bh, int S, int D, int pos, int n,
+                             cudaStream_t stream) {
+  if (D % 32 != 0 || D > 1024) throw std::runtime_error("mxfp8_seq_append: head_dim must be a multiple of 32, <= 1024");
+  if (pos < 0 || n <= 0 || pos + n > S) throw std::runtime_error("mxfp8_seq_append: rows out of range");
+  const int T = (S + 127) / 128;
+  const int g0 = pos / 32, g1 = (pos + n - 1) / 32;
+  const int nblk = g1 - g0 + 1;
+  const unsigned grid = (unsigned)(bh * nblk);
+  if (in_dtype == 0) mxfp8_seq_append_kernel<0><<<grid, D, 0, stream>>>(x, q, scales, S, D, T, pos, n, g0, nblk);
+  else if (in_dtype == 1) mxfp8_seq_append_kernel<1><<<grid, D, 0, stream>>>(x, q, scales, S, D, T, pos, n, g0, nblk);
+  else mxfp8_seq_append_kernel<2><<<grid, D, 0, stream>>>(x, q, scales, S, D, T, pos, n, g0, nblk);
   TA_CUDA_CHECK(cudaGetLastError());
 }
 

@@ -138,6 +138,16 @@ class MXFP8SeqTensor:
         new rows touch are de-quantised, updated and re-quantised (at most 32 + n rows of work per call)."""
         n = x.shape[2]
         b, h, s, d = self.data.shape
+        if self.data.is_cuda and x.dtype in (torch.bfloat16, torch.float16, torch.float32) and self.data.is_contiguous() \
+                and self.scales.is_contiguous():
+            _build.load().mxfp8_seq_append(self.data, self.scales, x, int(position))   # csrc/quant.cu: one small launch
+            return
+        self.write_rows_ref(position, x)
+
+    def write_rows_ref(self, position: int, x: torch.Tensor) -> None:
+        """PyTorch oracle / CPU path of ``write_rows``."""
+        n = x.shape[2]
+        b, h, s, d = self.data.shape
         lo = (position // BLOCK) * BLOCK
         hi = min(s, ((position + n + BLOCK - 1) // BLOCK) * BLOCK)
         blk = self.dequantize_rows(lo, hi)
