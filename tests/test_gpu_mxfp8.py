@@ -207,4 +207,5 @@ def test_seq_blocked_append_kernel_matches_oracle(position, n, dtype):
     torch.cuda.synchronize()
     assert torch.equal(a.scales, b.scales)
     assert torch.equal(a.data, b.data)
-    assert (a.dequantize()[:, :, position:position + n] - new.float()).abs().max().item() < 0.3
+    err = (a.dequantize()[:, :, position:position + n] - new.float()).abs()
+    assert (err / new.float().abs().clamp(min=1.0)).max().item() < 0.07      # e4m3: 3 mantissa bits

@@ -361,6 +361,32 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
   };
   fetch_scales(t_lo);
 
+  // bf16 / fp16 hot loop: explicit shared-state-space accesses with 32-bit addresses and per-lane offsets computed ONCE.
+  // (Generic pointers carved out of the dynamic smem block compile to LD.E with 64-bit address arithmetic per access: the
+  // round-2 SASS of this loop spent as many IADD3/IADD3.X/LOP3 on addresses as FFMAs on the math -- and the kernel is
+  // issue / power sensitive: 22 % fewer instructions bought 7 % more HBM bandwidth.)
+  const uint32_t stage_a = smem_u32(stage_base);
+  const uint32_t ps_a = smem_u32(p_s);
+  [[maybe_unused]] uint32_t k_off[D / 16];     // QK: this lane's D/16 16-byte chunks of its key row (128B swizzle applied)
+  [[maybe_unused]] uint32_t v_sw[8];           // PV: swizzled chunk offset of this lane's columns for row & 7 = 0..7
+  [[maybe_unused]] uint32_t q_off[D / 16];     // QK: byte offset of the matching 8 query values
+  if constexpr (!KV8) {
+    const int row = warp * kRowsPerWarp + r16;
+#pragma unroll
+    for (int c = 0; c < D / 16; ++c) {
+      const int cg = half * (D / 16) + c;
+      const int atom = cg >> 3, cia = cg & 7;
+      k_off[c] = uint32_t(atom * (kTileRows * 128) + row * 128 + ((cia ^ (row & 7)) << 4));
+      q_off[c] = uint32_t(cg * 8 * 4);
+    }
+    const int c0 = lane * EPL;
+    const int atom = (c0 * 2) >> 7, inner = (c0 * 2) & 127;
+    const int chunk = inner >> 4, off = inner & 15;
+#pragma unroll
+    for (int k7 = 0; k7 < 8; ++k7)
+      v_sw[k7] = uint32_t(L::kTensorBytes + atom * (kTileRows * 128) + off + ((chunk ^ k7) << 4) + (warp * kRowsPerWarp) * 128);
+  }
+
   for (int t = t_lo; t < t_hi; ++t) {
     const int x = t / geo.tph, j = t - x * geo.tph;
     [[maybe_unused]] const uint32_t ksc_word = nxt_ksc;
@@ -399,32 +425,40 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     float s_sum[R];
     [[maybe_unused]] uint32_t vsc_word = 0;
     if constexpr (!KV8) {
-  float s_acc[R][4];
+      const uint32_t ks_a = stage_a + uint32_t(stage) * L::kStageBytes;
+      const uint32_t q_a = smem_u32(q_cur);
+      uint64_t acc2[R][2];   // packed f32x2 accumulators: fma.rn.f32x2 issues ONE instruction for two FMAs on sm_100
 #pragma unroll
-      for (int r = 0; r < R; ++r) { s_acc[r][0] = s_acc[r][1] = s_acc[r][2] = s_acc[r][3] = 0.f; }
+      for (int r = 0; r < R; ++r) { acc2[r][0] = 0ull; acc2[r][1] = 0ull; }
 #pragma unroll
       for (int c = 0; c < D / 16; ++c) {
-        const int cg = half * (D / 16) + c;
-        const int atom = cg >> 3, cia = cg & 7;
-        const uint4 kw = *reinterpret_cast<const uint4*>(ks + atom * (kTileRows * 128) + row * 128 + ((cia ^ (row & 7)) << 4));
-        float kf[8];
-        cvt8<BF16>(kw, kf);
+        const uint4 kw = ld_shared_v4u(ks_a + k_off[c]);
+        uint64_t k2[4];
+        if constexpr (BF16) {
+          k2[0] = pack_f32x2(bf16lo(kw.x), bf16hi(kw.x)); k2[1] = pack_f32x2(bf16lo(kw.y), bf16hi(kw.y));
+          k2[2] = pack_f32x2(bf16lo(kw.z), bf16hi(kw.z)); k2[3] = pack_f32x2(bf16lo(kw.w), bf16hi(kw.w));
+        } else {
+          k2[0] = pack_f32x2(f16lo(kw.x), f16hi(kw.x)); k2[1] = pack_f32x2(f16lo(kw.y), f16hi(kw.y));
+          k2[2] = pack_f32x2(f16lo(kw.z), f16hi(kw.z)); k2[3] = pack_f32x2(f16lo(kw.w), f16hi(kw.w));
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          const float4 qa = *reinterpret_cast<const float4*>(q_cur + r * D + cg * 8);
-          const float4 qb = *reinterpret_cast<const float4*>(q_cur + r * D + cg * 8 + 4);
-          s_acc[r][0] = fmaf(kf[0], qa.x, s_acc[r][0]);
-          s_acc[r][1] = fmaf(kf[1], qa.y, s_acc[r][1]);
-          s_acc[r][2] = fmaf(kf[2], qa.z, s_acc[r][2]);
-          s_acc[r][3] = fmaf(kf[3], qa.w, s_acc[r][3]);
-          s_acc[r][0] = fmaf(kf[4], qb.x, s_acc[r][0]);
-          s_acc[r][1] = fmaf(kf[5], qb.y, s_acc[r][1]);
-          s_acc[r][2] = fmaf(kf[6], qb.z, s_acc[r][2]);
-          s_acc[r][3] = fmaf(kf[7], qb.w, s_acc[r][3]);
+          uint64_t q01, q23, q45, q67;
+          ld_shared_v2u64(q_a + uint32_t(r * D * 4) + q_off[c], q01, q23);
+          ld_shared_v2u64(q_a + uint32_t(r * D * 4) + q_off[c] + 16, q45, q67);
+          acc2[r][0] = fma2_f32x2(k2[0], q01, acc2[r][0]);
+          acc2[r][1] = fma2_f32x2(k2[1], q23, acc2[r][1]);
+          acc2[r][0] = fma2_f32x2(k2[2], q45, acc2[r][0]);
+          acc2[r][1] = fma2_f32x2(k2[3], q67, acc2[r][1]);
         }
       }
 #pragma unroll
-      for (int r = 0; r < R; ++r) s_sum[r] = (s_acc[r][0] + s_acc[r][1]) + (s_acc[r][2] + s_acc[r][3]);
+      for (int r = 0; r < R; ++r) {
+        float a0, a1, a2, a3;
+        unpack_f32x2(acc2[r][0], a0, a1);
+        unpack_f32x2(acc2[r][1], a2, a3);
+        s_sum[r] = (a0 + a1) + (a2 + a3);
+      }
     } else {
       // block-scaled fp8: this lane covers 64 elements = 4 chunks of 16 = blocks {2*half, 2*half+1}; products are
       // accumulated per chunk in fp16x2 (8 HFMA2), then scaled by the block's UE8M0 scale in fp32.
@@ -482,7 +516,7 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       l_run[r] = fmaf(l_run[r], alpha[r], pv);
       m_run[r] = m_new;
       if constexpr (!KV8) {
-        if (half == 0) p_s[(warp * R + r) * kRowsPerWarp + r16] = pv;
+        if (half == 0) st_shared_f32(ps_a + uint32_t(((warp * R + r) * kRowsPerWarp + r16) * 4), pv);
       } else {
         // P x (V block scale), one copy per 32-wide block of D; this lane owns blocks 2*half and 2*half+1
         const int b0 = 2 * half;
@@ -495,7 +529,24 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
     __syncwarp();
 
     // ---------------- O += P . V : lane = EPL consecutive output columns ---------------------------
-    const int nv = geo.S - (j * kTileRows + warp * kRowsPerWarp);   // valid rows of this warp's 16 (>= 16: all)
+    // Rows past the valid length may hold anything, and 0 x NaN is NaN: on the one tile per head that contains the end of
+    // the valid range, every warp zeroes ITS invalid V rows in the stage buffer first (the hot loop stays branch-free; a
+    // per-row guard inside it cost 18 % more issued instructions and 5 % of the single-GPU time in round 2).
+    {
+      const int nv = geo.S - (j * kTileRows + warp * kRowsPerWarp);   // valid rows of this warp's 16 (>= 16: all)
+      if (nv < kRowsPerWarp) {
+        constexpr int kRowBytes = D * L::kElem;        // 256 (two 128-byte atoms) or 128
+        constexpr int kLanes = kRowBytes / 8;
+        uint8_t* vw = const_cast<uint8_t*>(vs);
+        for (int rr = max(nv, 0); rr < kRowsPerWarp; ++rr) {
+          const int vrow = warp * kRowsPerWarp + rr;
+          if (lane < kLanes)
+            *reinterpret_cast<uint2*>(vw + (lane >> 4) * (kTileRows * 128) + vrow * 128 + (lane & 15) * 8) = make_uint2(0u, 0u);
+        }
+        fence_proxy_async_smem();   // generic-proxy writes to a buffer the TMA (async proxy) will overwrite after the release below
+        __syncwarp();
+      }
+    }
     if constexpr (KV8) {
       // fp8: 4 output columns = 4 bytes; the P x scale coefficients of this lane's block come from smem
       const int blk = lane >> 3;
@@ -508,7 +559,6 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
           pr[r] = *reinterpret_cast<const float4*>(p_s + ((warp * 4 + blk) * R + r) * kRowsPerWarp + jj);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (jj + u >= nv) continue;   // rows past the valid length may hold anything (0 x NaN): skip, never multiply
           const int vrow = warp * kRowsPerWarp + jj + u;
           const uint32_t w = *reinterpret_cast<const uint32_t*>(vs + vrow * 128 + ((chunk ^ (vrow & 7)) << 4) + off);
           uint32_t h0, h1;
@@ -528,29 +578,22 @@ decode_simt_kernel(const __grid_constant__ CUtensorMap kmap, const __grid_consta
       }
     } else
     {
-      const int c0 = lane * EPL;                 // first element of this lane
-      const int atom = (c0 * 2) >> 7;            // 64 elements (128 B) per atom
-      const int inner = (c0 * 2) & 127;
-      const int chunk = inner >> 4, off = inner & 15;
-      const uint8_t* vb = vs + atom * (kTileRows * 128) + off;
+      const uint32_t vs_a = stage_a + uint32_t(stage) * L::kStageBytes;   // v_sw already includes the V tensor offset
 #pragma unroll
       for (int jj = 0; jj < kRowsPerWarp; jj += 4) {
         float4 pr[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r)
-          pr[r] = *reinterpret_cast<const float4*>(p_s + (warp * R + r) * kRowsPerWarp + jj);
+        for (int r = 0; r < R; ++r) pr[r] = ld_shared_v4f(ps_a + uint32_t(((warp * R + r) * kRowsPerWarp + jj) * 4));
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (jj + u >= nv) continue;   // rows past the valid length may hold anything (0 x NaN): skip, never multiply
-          const int vrow = warp * kRowsPerWarp + jj + u;
-          const uint8_t* vp = vb + vrow * 128 + ((chunk ^ (vrow & 7)) << 4);
+          const uint32_t va = vs_a + v_sw[(jj + u) & 7] + uint32_t((jj + u) * 128);
           float vf[EPL];
           if constexpr (EPL == 4) {
-            const uint2 w = *reinterpret_cast<const uint2*>(vp);
+            const uint2 w = ld_shared_v2u(va);
             if constexpr (BF16) { vf[0] = bf16lo(w.x); vf[1] = bf16hi(w.x); vf[2] = bf16lo(w.y); vf[3] = bf16hi(w.y); }
             else { vf[0] = f16lo(w.x); vf[1] = f16hi(w.x); vf[2] = f16lo(w.y); vf[3] = f16hi(w.y); }
           } else {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(vp);
+            const uint32_t w = ld_shared_u32(va);
             if constexpr (BF16) { vf[0] = bf16lo(w); vf[1] = bf16hi(w); }
             else { vf[0] = f16lo(w); vf[1] = f16hi(w); }
           }
