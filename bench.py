@@ -67,6 +67,9 @@ def parse_args():
     p.add_argument("--heavy", default="auto", choices=["auto", "on", "off"],
                    help="also measure the other BASELINE.json configs (full-Sq 128K forward, 256K fp8, 1M GQA fwd+bwd); "
                         "auto = only on 8 GPUs")
+    p.add_argument("--host-io", default="copy", choices=["zero_copy", "copy"],
+                   help="e2e step: the kernel reads q / writes the result in pinned host memory itself (zero_copy), or a CUDA graph "
+                        "[H2D memcpy | attention | D2H memcpy] (copy); the other variant is reported in e2e.other_transfer unless --no-extras")
     p.add_argument("--align", type=int, default=2, help="untimed steps enqueued between the host barrier and the start event")
     return p.parse_args()
 
@@ -313,7 +316,8 @@ def main():
     C = _build.load()
     from tree_attention_b200.models.decoder import TreeDecodeSession
 
-    sess = TreeDecodeSession(kvs, softmax_scale=scale, backend=args.backend, use_graph=args.graph, pdl=args.pdl)
+    sess = TreeDecodeSession(kvs, softmax_scale=scale, backend=args.backend, use_graph=args.graph, pdl=args.pdl,
+                             host_io=args.host_io)
 
     # correctness gate before timing (never time a wrong kernel)
     out = sess.step_device(q, 0)
@@ -358,14 +362,37 @@ def main():
     # end-to-end through the public API: pinned host q -> device, step, result -> pinned host, every step.  Measured right
     # after the device-timed region and BEFORE the seconds-long clock-sampling loop below, i.e. in the same thermal / power
     # state as the device-timed number (the reference arm uses the same order)
-    e2e = sess.run_e2e(q, steps, barrier)
-    e2e_ms = torch.tensor([e2e["ms"]], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_lat = float(e2e_ms.item()) / steps
+    def run_e2e(session):
+        r = session.run_e2e(q, steps, barrier)
+        t = torch.tensor([r["ms"]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # what the host receives from that path, against the fp32 oracle (never report a wrong step's time)
+        r["err"] = None
+        if session.q_host is not None and session.out_host[0] is not None:
+            session.out_host[0].zero_()
+            session.step(session.q_host, session.out_host[0], 0)      # one more (untimed) step on buffer 0, checked
+            r["err"] = float((session.out_host[0].float().to(dev) - o_ref0).abs().max())
+        return r, float(t.item()) / steps
+
+    o_ref0 = o_ref
+    e2e, e2e_lat = run_e2e(sess)
     clocks = sampled_clocks(torch, dist, sampler, window, own_step, ms / steps, steps, world, dev, barrier)
 
     extras = {}
+    e2e_other = None
+    if not args.no_extras:
+        # the other host-I/O variant of the same end-to-end step, same loop, for the record
+        try:
+            other = "copy" if args.host_io == "zero_copy" else "zero_copy"
+            sess2 = TreeDecodeSession(kvs, softmax_scale=scale, backend=args.backend, use_graph=args.graph, pdl=args.pdl, host_io=other)
+            sess2.step_device(q, 0)
+            r2, lat2 = run_e2e(sess2)
+            e2e_other = {"transfer": r2["transfer"], "ms_per_step": lat2, "value": B * S / (lat2 * 1e-3),
+                         "per_step_ms_rank0": {"median": r2["median_ms"], "min": r2["min_ms"], "max": r2["max_ms"]}}
+            sess2.close()
+        except Exception as e:
+            e2e_other = {"error": f"{type(e).__name__}: {e}"[:200]}
     if world > 1 and not args.no_extras:
         # the runnable "reference's own NCCL build" on the same box, same loop, with its own clock record
         try:
@@ -413,7 +440,8 @@ def main():
             "timing": f"CUDA events around {steps} steps after {warmup} warm-ups; {args.align} untimed step(s) between the host barrier "
                       "and the start event align the ranks on the device (every step ends with an all-to-all); max over ranks",
             "e2e": {"value": B * S / (e2e_lat * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_lat,
-                    "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                    "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"], "transfer": e2e["transfer"],
+                    "max_abs_err_vs_oracle": e2e["err"], "other_transfer": e2e_other,
                     "per_step_ms_rank0": {"median": e2e["median_ms"], "min": e2e["min_ms"], "max": e2e["max_ms"]}},
             "gpu_launches": launches_per_step * steps,
             "decode_tokens_per_s": B / (lat * 1e-3),

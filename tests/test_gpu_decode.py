@@ -132,15 +132,17 @@ def test_pdl_back_to_back_steps_match_and_stay_ordered():
         assert (o.float() - exp).abs().max().item() < 1.5e-2
 
 
-def test_session_end_to_end_step_single_graph():
-    """TreeDecodeSession.step: pinned-host query -> [H2D | fused attention | D2H] replayed as one CUDA graph -> pinned
-    host result; a new query every step, results equal the eager device path."""
+@pytest.mark.parametrize("host_io", ["zero_copy", "copy"])
+def test_session_end_to_end_step_single_graph(host_io):
+    """TreeDecodeSession.step, both host-I/O variants: "copy" = pinned-host query -> [H2D | fused attention | D2H] replayed
+    as one CUDA graph -> pinned host result; "zero_copy" = the kernel itself loads q from / stores the result to pinned
+    mapped host memory (one launch).  A new query every step, results equal the oracle."""
     from tree_attention_b200.models.decoder import TreeDecodeSession
 
     g = torch.Generator(device="cuda").manual_seed(5)
     k = torch.randn(1, 4, 3000, 128, device="cuda", generator=g).bfloat16()
     v = torch.randn(1, 4, 3000, 128, device="cuda", generator=g).bfloat16()
-    sess = TreeDecodeSession([(k, v), (v, k)], softmax_scale=0.09, q_shape=(1, 8, 1, 128))
+    sess = TreeDecodeSession([(k, v), (v, k)], softmax_scale=0.09, q_shape=(1, 8, 1, 128), host_io=host_io)
     oh = torch.empty(1, 8, 1, 128, dtype=torch.bfloat16).pin_memory()
     for it in range(4):
         q = torch.randn(1, 8, 1, 128, generator=torch.Generator().manual_seed(it)).bfloat16()
@@ -150,7 +152,10 @@ def test_session_end_to_end_step_single_graph():
         kk, vv = (k, v) if layer == 0 else (v, k)
         exp, _ = ref.attention_partial_ref(q.cuda(), kk, vv, 0.09)
         assert (got.float().cuda() - exp).abs().max().item() < 2e-2
-    assert len(sess.e2e_graphs) == 2
+    if host_io == "copy":
+        assert len(sess.e2e_graphs) == 2 and not sess._steps_zc
+    else:
+        assert len(sess._steps_zc) == 2 and not sess.e2e_graphs
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -308,7 +308,8 @@ def _worker_fill_levels(rank, world):
         n = lens[rank]
         k[:, :, n:] = 0
         v[:, :, n:] = 0
-        sess = TreeDecodeSession([(k, v)], softmax_scale=0.088, q_shape=(1, hq, 1, 128), kv_lens=[n], backend="fused")
+        sess = TreeDecodeSession([(k, v)], softmax_scale=0.088, q_shape=(1, hq, 1, 128), kv_lens=[n], backend="fused",
+                                 host_io="zero_copy")
 
         def oracle():
             cur = torch.tensor([sess.kv_len_host[0]], device=dev)
@@ -339,6 +340,13 @@ def _worker_fill_levels(rank, world):
             dist.all_gather(outs, out.contiguous())
             for o in outs:
                 assert torch.equal(o, outs[0]), "fill levels: ranks disagree bitwise"
+        # latency path: the fused kernel reads q from pinned host memory and posts the combined result into pinned host
+        # memory (zero-copy twin of the prepared step: same workspace, region and launch-tag counters)
+        qh = q.cpu().pin_memory()
+        oh = torch.zeros(1, hq, 1, 128, dtype=torch.bfloat16).pin_memory()
+        got = sess.step(qh, oh, 0).clone()
+        assert sess._steps_zc, "the native session should take the zero-copy latency path"
+        assert torch.equal(got.to(dev), outs[0]), (hq, hkv, "zero-copy step differs from the device-resident step")
         sess.region.check()
         sess.close()
 

@@ -71,9 +71,13 @@ struct Comm {
   }
 };
 
+// host_io: q and out may live in pinned (page-locked, device-mapped) HOST memory -- the decode kernels read the few KB of q
+// and write the result with plain global accesses, so a latency-bound lone step can skip both copy-engine hops.
 AttnShape make_shape(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, const at::Tensor& out,
-                     double scale, bool causal, int64_t q_pos0, int64_t kv_pos0) {
-  TORCH_CHECK(q.is_cuda() && k.is_cuda() && v.is_cuda() && out.is_cuda(), "tensors must be CUDA");
+                     double scale, bool causal, int64_t q_pos0, int64_t kv_pos0, bool host_io = false) {
+  TORCH_CHECK(k.is_cuda() && v.is_cuda(), "k and v must be CUDA tensors");
+  TORCH_CHECK((q.is_cuda() || (host_io && q.is_pinned())) && (out.is_cuda() || (host_io && out.is_pinned())),
+              host_io ? "q / out must be CUDA or pinned host tensors" : "tensors must be CUDA");
   TORCH_CHECK(q.dim() == 4 && k.dim() == 4 && v.dim() == 4 && out.dim() == 4, "expected (B, H, S, D) tensors");
   TORCH_CHECK(q.scalar_type() == at::kBFloat16 || q.scalar_type() == at::kHalf, "q must be bf16 or fp16");
   TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type() &&
@@ -355,12 +359,22 @@ struct DecodeStep {
   }
 };
 
+// device-visible address of a CUDA tensor or of a pinned (mapped) host tensor
+void* io_ptr(const at::Tensor& t) {
+  if (t.is_cuda()) return t.data_ptr();
+  void* d = nullptr;
+  const cudaError_t e = cudaHostGetDevicePointer(&d, t.data_ptr(), 0);
+  TORCH_CHECK(e == cudaSuccess && d != nullptr, "pinned host tensor is not mapped into the device address space: ", cudaGetErrorString(e));
+  return d;
+}
+
 std::shared_ptr<DecodeStep> decode_step(const std::string& impl, const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
                                         at::Tensor& out, c10::optional<at::Tensor> lse, at::Tensor& part, at::Tensor& tickets,
                                         py::object comm, double scale, bool causal, int64_t q_pos0, int64_t kv_pos0,
                                         c10::optional<at::Tensor> kv_len) {
-  c10::cuda::CUDAGuard guard(q.device());
-  AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0);
+  c10::cuda::CUDAGuard guard(k.device());
+  // q / out: device tensors, or pinned host tensors (zero-copy step: the kernel pulls q over PCIe and posts the result back)
+  AttnShape s = make_shape(q, k, v, out, scale, causal, q_pos0, kv_pos0, /*host_io=*/true);
   TORCH_CHECK(part.scalar_type() == at::kFloat && part.is_contiguous(), "part must be contiguous fp32");
   TORCH_CHECK(tickets.scalar_type() == at::kInt && tickets.numel() >= s.B * s.Hkv + 2, "tickets too small");
   float* lse_p = nullptr;
@@ -371,7 +385,7 @@ std::shared_ptr<DecodeStep> decode_step(const std::string& impl, const at::Tenso
   }
   CommCtxHost c;
   if (!comm.is_none()) c = comm.cast<Comm&>().h;
-  auto st = std::make_shared<DecodeStep>(q.device());
+  auto st = std::make_shared<DecodeStep>(k.device());
   st->impl = impl;
   st->comm_keep = comm;
   st->keep = {q, k, v, out, part, tickets};
@@ -385,7 +399,7 @@ std::shared_ptr<DecodeStep> decode_step(const std::string& impl, const at::Tenso
     ta::decode_simt_plan(s, ta::num_sms(), &grid, &mp, &R, &pf, &cf, &cfl);
     TORCH_CHECK((size_t)part.numel() >= pf, "part workspace too small: need ", pf, " floats");
     for (int pdl = 0; pdl < 3; ++pdl) {
-      st->launches[pdl] = ta::decode_simt_prepare(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p,
+      st->launches[pdl] = ta::decode_simt_prepare(s, io_ptr(q), k.data_ptr(), v.data_ptr(), io_ptr(out), lse_p,
                                                   part.data_ptr<float>(), tk, c, ta::num_sms(), nullptr, nullptr, pdl, kvl);
       st->has[pdl] = true;
     }
@@ -397,9 +411,9 @@ std::shared_ptr<DecodeStep> decode_step(const std::string& impl, const at::Tenso
     TORCH_CHECK((size_t)part.numel() >= pf, "part workspace too small: need ", pf, " floats");
     TORCH_CHECK(q.stride(2) % 8 == 0 || q.size(2) == 1, "q rows must be 16-byte aligned");
     st->launches[0] = impl == "swap"
-                          ? ta::decode_swap_prepare(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p,
+                          ? ta::decode_swap_prepare(s, io_ptr(q), k.data_ptr(), v.data_ptr(), io_ptr(out), lse_p,
                                                     part.data_ptr<float>(), tk, c, ta::num_sms(), nullptr, nullptr, nullptr, nullptr, kvl)
-                          : ta::decode_tc_prepare(s, q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse_p,
+                          : ta::decode_tc_prepare(s, io_ptr(q), k.data_ptr(), v.data_ptr(), io_ptr(out), lse_p,
                                                   part.data_ptr<float>(), tk, c, ta::num_sms(), nullptr, nullptr, kvl);
     st->has[0] = true;
   } else {

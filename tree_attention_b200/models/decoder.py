@@ -44,13 +44,20 @@ class TreeDecodeSession:
         pdl: bool = False,
         dtype: Optional[torch.dtype] = None,
         kv_lens: Optional[Sequence[int]] = None,
+        host_io: str = "copy",
     ):
         """``kv_layers``: per layer this rank's preallocated ``(k, v)`` shard, ``(B, Hkv, capacity, D)``.
         ``kv_lens``: per layer the number of rows already filled (default: the shards are full).  Construction is
         collective (every rank of ``group`` builds its session in the same order).
         ``pdl=True``: ``step_device`` launches eagerly with programmatic dependent launch + K/V prefetch (the caches of
         a session are only written through ``append_kv``) -- the next step's prologue and first tile loads overlap
-        the previous step's drain; the e2e path (``step``) replays a CUDA graph."""
+        the previous step's drain; the e2e path (``step``) replays a CUDA graph.
+        ``host_io``: how the latency path (``step``) moves its few KB across PCIe.  ``"copy"`` (default): a CUDA graph
+        [H2D memcpy | attention | D2H memcpy].  ``"zero_copy"`` (native fast path only): the decode kernel itself loads q
+        from the session's pinned, device-mapped staging buffer and stores the result straight into pinned host memory --
+        ONE kernel launch per step, no copy-engine hops.  Measured equal within noise on one B200 at 128K (0.342 vs
+        0.341 ms per step, profiles/r2_decode/e2e_host_io.md): the PCIe read of q inside the kernel costs what the two
+        memcpy nodes cost, the rest of the end-to-end overhead is the lone launch + stream sync."""
         self.kv = list(kv_layers)
         k0 = self.kv[0][0]
         self.device = k0.device
@@ -90,6 +97,9 @@ class TreeDecodeSession:
             self.kv_len_dev = torch.tensor(self.kv_len_host, dtype=torch.int32, device=self.device)
         # native fast path: plain bf16 / fp16 caches on CUDA through the fused (or single-GPU) decode kernels
         self._steps: List[object] = []
+        self._steps_zc: List[object] = []   # zero-copy twins of _steps: q / out in pinned host memory
+        assert host_io in ("zero_copy", "copy")
+        self.host_io = host_io
         self._ws = None
         self.region = None
         self._family = None
@@ -145,6 +155,15 @@ class TreeDecodeSession:
             self._steps.append(C.decode_step(impl, self.q_static, k, v, self.out_static[i], None, self._ws["part"],
                                              self._ws["tickets"], comm, scale, bool(self.causal), int(q_pos0),
                                              int(kv_pos0), self._kv_len_of(i)))
+            if self.host_io == "zero_copy":
+                if self.q_host is None:
+                    self.q_host = torch.zeros(self.q_shape, dtype=self.dtype).pin_memory()
+                self.out_host[i] = torch.zeros(self.q_shape, dtype=self.dtype).pin_memory()
+                # same workspace, same symmetric region, same launch-tag counters as the device-resident step: the two
+                # are interchangeable launch by launch (every rank takes the same path for a given step)
+                self._steps_zc.append(C.decode_step(impl, self.q_host, k, v, self.out_host[i], None, self._ws["part"],
+                                                    self._ws["tickets"], comm, scale, bool(self.causal), int(q_pos0),
+                                                    int(kv_pos0), self._kv_len_of(i)))
         self.launches_per_step = self._steps[0].kernels_per_step
 
     def _launch(self, layer: int, use_pdl: bool = False) -> torch.Tensor:
@@ -175,6 +194,12 @@ class TreeDecodeSession:
                         self.out_static[i] = self._launch(i)
                 self.graphs.append(g)
             torch.cuda.synchronize()
+            if self._steps_zc:          # zero-copy latency path: no e2e graphs needed
+                for i in range(len(self.kv)):
+                    self._steps_zc[i].launch(0)
+                torch.cuda.synchronize()
+                self._prepared = True
+                return
             self.q_host = torch.empty(self.q_shape, dtype=self.dtype).pin_memory()
             self.q_host.copy_(self.q_static.cpu())
             for i in range(len(self.kv)):
@@ -211,6 +236,17 @@ class TreeDecodeSession:
         Uses the CUDA-graph replay when one was captured (lowest host overhead for a lone step)."""
         layer %= len(self.kv)
         self._prepare()
+        if self._steps_zc:
+            # zero-copy: the kernel reads q from the pinned staging buffer over PCIe and posts the result into pinned host
+            # memory; the step is one prepared launch + a stream sync
+            if q_host.data_ptr() != self.q_host.data_ptr():
+                self.q_host.copy_(q_host)
+            self._kv_dirty = False
+            self._steps_zc[layer].launch(0)
+            torch.cuda.current_stream().synchronize()
+            if out_host.data_ptr() != self.out_host[layer].data_ptr():
+                out_host.copy_(self.out_host[layer])
+            return out_host
         if self.e2e_graphs:
             # the query goes through the session's pinned staging buffer (a host memcpy of a few KB); the graph's first
             # node copies it to the device, its last node copies the result into pinned host memory
@@ -259,6 +295,7 @@ class TreeDecodeSession:
         self.graphs.clear()
         self.e2e_graphs.clear()
         self._steps.clear()
+        self._steps_zc.clear()
         if self._family is not None:
             symm.release(self._family, self.group)
             self._family = None
@@ -267,7 +304,7 @@ class TreeDecodeSession:
     def run_e2e(self, q: torch.Tensor, steps: int, barrier) -> dict:
         """Time ``steps`` end-to-end steps (host clock around the whole loop; per-step times are kept for diagnosis)."""
         self._prepare()
-        if self.e2e_graphs:
+        if self.e2e_graphs or self._steps_zc:
             # the caller fills the session's pinned staging buffer and reads the per-layer pinned result buffers directly:
             # the step is then ONE graph launch [H2D copy | attention | D2H copy] + a stream sync, no extra host memcpy
             self.q_host.copy_(q.detach().cpu())
@@ -290,4 +327,8 @@ class TreeDecodeSession:
         barrier()
         per.sort()
         return {"ms": (t1 - t0) * 1e3, "h2d": qh.numel() * qh.element_size(), "d2h": qh.numel() * qh.element_size(),
-                "median_ms": per[len(per) // 2], "max_ms": per[-1], "min_ms": per[0]}
+                "median_ms": per[len(per) // 2], "max_ms": per[-1], "min_ms": per[0],
+                "transfer": ("zero_copy: the decode kernel loads q from pinned mapped host memory and stores the result into "
+                             "pinned host memory (1 launch + stream sync per step)") if self._steps_zc else
+                            ("cuda_graph[H2D memcpy | attention | D2H memcpy] + stream sync" if self.e2e_graphs else
+                             "eager H2D copy, launch, D2H copy, stream sync")}
