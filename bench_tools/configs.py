@@ -102,6 +102,18 @@ def run_all(ta, world, rank, dev, barrier, root, only=None, sampler=None, scale_
                     "note": ("causal with CONTIGUOUS shards: rank 0's keys are visible to every query, so the slowest rank does "
                              "the full (un-halved) work; tflops_per_gpu uses the MEAN work") if causal else "",
                 }
+            if world > 1:
+                # (i) the Sq-sharded output of the reduce-scatter combine (no all-gather of the final tiles), (ii) the same
+                # kernel with the cross-GPU combine switched off (local partial only): what the combine costs end to end
+                from tree_attention_b200.ops import flash
+
+                fn = lambda: ta.tree_attention(q, k, v, causal=False, backend="fused", output="sharded")
+                ms_s, _ = _timed(torch, dist, fn, 3, 1, world, dev, barrier)
+                fn = lambda: flash.attention_fwd(q, k, v, D ** -0.5, False, 0, 0)
+                ms_l, _ = _timed(torch, dist, fn, 3, 1, world, dev, barrier)
+                flops = 4.0 * S * s_local * D * H
+                blk["full_sharded_output"] = {"ms": ms_s, "tflops_per_gpu": flops / (ms_s * 1e-3) / 1e12}
+                blk["local_partial_only_no_combine"] = {"ms": ms_l, "tflops_per_gpu": flops / (ms_l * 1e-3) / 1e12}
             # correctness spot check: 256 query rows against the fp32 oracle over the gathered sequence
             o = ta.tree_attention(q, k, v, causal=False, backend="fused" if world > 1 else "auto")
             from tree_attention_b200.ops import reference as ref

@@ -54,3 +54,25 @@ def _worker(rank, world):
 @pytest.mark.parametrize("world", [2, 3])
 def test_distributed_backward_gloo(world, port):
     run_distributed(_worker, world, port)
+
+
+def test_module_grad_path_passes_backend_and_schedule(monkeypatch):
+    """TreeAttention.forward must hand its backend / schedule to the differentiable path too."""
+    import tree_attention_b200.ops.autograd as ag
+    from tree_attention_b200.models.tree_attention import TreeAttention
+
+    seen = {}
+    real = ag.tree_attention_func
+
+    def spy(*a, **kw):
+        seen.update(kw)
+        return real(*a, **kw)
+
+    monkeypatch.setattr(ag, "tree_attention_func", spy)
+    m = TreeAttention(causal=True, backend="collective", schedule="butterfly")
+    q = torch.randn(1, 2, 3, 16, requires_grad=True)
+    k = torch.randn(1, 2, 9, 16)
+    v = torch.randn(1, 2, 9, 16)
+    m(q, k, v).sum().backward()
+    assert seen.get("backend") == "collective" and seen.get("schedule") == "butterfly"
+    assert q.grad is not None and torch.isfinite(q.grad).all()

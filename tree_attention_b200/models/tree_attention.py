@@ -31,7 +31,8 @@ class TreeAttention(nn.Module):
             from ..ops.autograd import tree_attention_func
 
             return tree_attention_func(q, k, v, causal=self.causal, softmax_scale=self.softmax_scale,
-                                       group=self.group, kv_offset=kv_offset, q_offset=q_offset, layout=self.layout)
+                                       group=self.group, kv_offset=kv_offset, q_offset=q_offset, backend=self.backend,
+                                       schedule=self.schedule, layout=self.layout)
         return tree_attention(q, k, v, group=self.group, causal=self.causal, softmax_scale=self.softmax_scale,
                               kv_offset=kv_offset, q_offset=q_offset, backend=self.backend, schedule=self.schedule,
                               layout=self.layout)
