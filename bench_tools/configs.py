@@ -102,6 +102,15 @@ def run_all(ta, world, rank, dev, barrier, root, only=None, sampler=None, scale_
                     "note": ("causal with CONTIGUOUS shards: rank 0's keys are visible to every query, so the slowest rank does "
                              "the full (un-halved) work; tflops_per_gpu uses the MEAN work") if causal else "",
                 }
+            if world > 1 and (S // (2 * world)) % 128 == 0:
+                # causal with ZIGZAG shards (rank r owns chunks r and 2W-1-r): same total work, balanced over the ranks.  The K/V
+                # values differ from the contiguous runs (same shapes, different order), which does not matter for timing.
+                fn = lambda: ta.tree_attention(q, k, v, causal=True, backend="fused", kv_layout="zigzag")
+                ms_z, win = _timed(torch, dist, fn, 3, 1, world, dev, barrier)
+                flops = 4.0 * S * s_local * D * H * 0.5
+                blk["causal_zigzag"] = {"ms": ms_z, "tokens_per_s": S / (ms_z * 1e-3), "tflops_per_gpu": flops / (ms_z * 1e-3) / 1e12,
+                                        "speedup_vs_contiguous_causal": blk["causal"]["ms"] / ms_z, "clocks": clocks(win),
+                                        "note": "one fused launch per rank over the two-segment shard (kv_seg), combine included"}
             if world > 1:
                 # (i) the Sq-sharded output of the reduce-scatter combine (no all-gather of the final tiles), (ii) the same
                 # kernel with the cross-GPU combine switched off (local partial only): what the combine costs end to end

@@ -187,3 +187,56 @@ def _worker_sharded_output(rank, world):
 
 def test_sharded_output_gloo(port):
     run_distributed(_worker_sharded_output, 2, port)
+
+
+def _worker_zigzag(rank, world):
+    """kv_layout="zigzag": every rank holds chunks r and 2W-1-r of the causal sequence; the result (forward and the
+    gradients) equals plain causal attention over the full sequence."""
+    import torch.distributed as dist
+    import tree_attention_b200 as ta
+    from tree_attention_b200.ops import reference as ref
+    from tree_attention_b200.ops.autograd import tree_attention_func
+
+    g = torch.Generator().manual_seed(3)
+    S, hq, hkv, d = 16 * world, 4, 2, 16
+    q_full = torch.randn(1, hq, S, d, generator=g)
+    k_full = torch.randn(1, hkv, S, d, generator=g)
+    v_full = torch.randn(1, hkv, S, d, generator=g)
+    do = torch.randn(1, hq, S, d, generator=g)
+    k = ta.zigzag_shard(k_full, rank, world).clone().requires_grad_(True)
+    v = ta.zigzag_shard(v_full, rank, world).clone().requires_grad_(True)
+    # round trip of the layout helpers
+    ks = [torch.empty_like(k) for _ in range(world)]
+    dist.all_gather(ks, k.detach())
+    assert torch.equal(ta.zigzag_unshard(ks), k_full)
+    # oracle: causal attention over the whole sequence on one rank, with autograd
+    qo, ko, vo = (t.clone().requires_grad_(True) for t in (q_full, k_full, v_full))
+    o_ref, lse_ref = ref.attention_partial_ref(qo, ko, vo, causal=True, q_pos0=0)
+    o_ref.backward(do)
+    for sched in ("allgather", "butterfly"):
+        o, lse = ta.tree_attention(q_full, k.detach(), v.detach(), causal=True, return_lse=True, kv_layout="zigzag",
+                                   backend="gloo", schedule=sched)
+        assert torch.allclose(o, o_ref.detach(), atol=2e-5), (sched, (o - o_ref).abs().max())
+        assert torch.allclose(lse, lse_ref.detach(), atol=2e-5)
+    # contiguous interpretation of the same tensors must differ (the layout really is honoured)
+    o_wrong = ta.tree_attention(q_full, k.detach(), v.detach(), causal=True, backend="gloo")
+    assert not torch.allclose(o_wrong, o_ref.detach(), atol=1e-3)
+    # sharded output + the module front-end + decode-convention query block (last rows only)
+    o_sh = ta.tree_attention(q_full, k.detach(), v.detach(), causal=True, kv_layout="zigzag", backend="gloo", output="sharded")
+    n = o_sh.shape[2]
+    lo, hi = min(rank * n, S), min((rank + 1) * n, S)
+    assert torch.allclose(o_sh[:, :, : hi - lo], o_ref.detach()[:, :, lo:hi], atol=2e-5)
+    o_tail = ta.tree_attention(q_full[:, :, -5:], k.detach(), v.detach(), causal=True, kv_layout="zigzag", backend="gloo")
+    assert torch.allclose(o_tail, o_ref.detach()[:, :, -5:], atol=2e-5)
+    # backward: dK / dV of my two chunks, dQ summed over ranks
+    q = q_full.clone().requires_grad_(True)
+    o2 = tree_attention_func(q, k, v, causal=True, backend="gloo", kv_layout="zigzag")
+    o2.backward(do)
+    assert torch.allclose(q.grad, qo.grad, atol=5e-5), (q.grad - qo.grad).abs().max()
+    assert torch.allclose(k.grad, ta.zigzag_shard(ko.grad, rank, world), atol=5e-5)
+    assert torch.allclose(v.grad, ta.zigzag_shard(vo.grad, rank, world), atol=5e-5)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_zigzag_causal_layout_gloo(world, port):
+    run_distributed(_worker_zigzag, world, port)

@@ -77,3 +77,39 @@ def test_public_api_routes_prefill_to_tcgen05():
     out, lse = ta.tree_attention(q, k, v, causal=True, return_lse=True)
     o_ref, l_ref = ref.attention_partial_ref(q, k, v, None, True, 0, 0)
     assert (out.float() - o_ref).abs().max().item() < 2e-2
+
+
+SEG_CASES = [
+    # hq, hkv, sq, s, seg_len, d, q_pos0, kv_pos0, seg_gap
+    (2, 2, 1024, 512, 256, 128, 0, 0, 512),        # zigzag shard of rank 0 of 2 over a 1024-long sequence, full query block
+    (2, 2, 1024, 512, 256, 128, 0, 256, 0),        # rank 1 of 2: chunks 1 and 2 are adjacent (gap 0 = contiguous)
+    (4, 2, 700, 768, 384, 128, 900, 384, 1152),    # GQA, ragged query block in the middle of a longer sequence
+    (2, 2, 512, 1024, 512, 64, 300, 0, 2048),      # head_dim 64; second segment entirely in the future for most rows
+    (2, 2, 300, 640, 128, 128, 100, 0, 128),       # unequal segments (128 + 512 rows), ragged q
+]
+
+
+@pytest.mark.parametrize("variant", [1, 6])
+@pytest.mark.parametrize("case", SEG_CASES, ids=[str(i) for i in range(len(SEG_CASES))])
+def test_fwd_two_segment_shard_matches_oracle(case, variant):
+    """kv_seg=(seg_len, seg_gap): local rows >= seg_len sit seg_gap positions further on (zigzag sharding of a causal
+    sequence).  Oracle: the two segments as separate causal partials at their own positions, merged."""
+    hq, hkv, sq, s, seg_len, d, q_pos0, kv_pos0, gap = case
+    q, k, v = _mk(1, hq, hkv, sq, s, d, torch.bfloat16, seed=11)
+    scale = d ** -0.5
+    out, lse = flash.attention_fwd(q, k, v, scale, True, q_pos0, kv_pos0, variant=variant, kv_seg=(seg_len, gap))
+    torch.cuda.synchronize()
+    pa = ref.attention_partial_ref(q, k[:, :, :seg_len], v[:, :, :seg_len], scale, True, q_pos0, kv_pos0, torch.float32)
+    pb = ref.attention_partial_ref(q, k[:, :, seg_len:], v[:, :, seg_len:], scale, True, q_pos0, kv_pos0 + gap + seg_len,
+                                   torch.float32)
+    o_ref, l_ref = ref.merge_many([pa[0], pb[0]], [pa[1], pb[1]])
+    assert not torch.isnan(out).any()
+    assert (out.float() - o_ref).abs().max().item() < 2e-2
+    dead = torch.isinf(l_ref)
+    assert torch.equal(torch.isinf(lse) & (lse < 0), dead)
+    if (~dead).any():
+        assert (lse[~dead] - l_ref[~dead]).abs().max().item() < 5e-3
+    # and the layout is honoured: the one-segment interpretation of the same tensors differs whenever the gap matters
+    if gap > 0 and q_pos0 + sq - 1 >= kv_pos0 + seg_len:
+        o1, _ = flash.attention_fwd(q, k, v, scale, True, q_pos0, kv_pos0, variant=variant)
+        assert (o1.float() - o_ref).abs().max().item() > 1e-3

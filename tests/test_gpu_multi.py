@@ -153,6 +153,60 @@ def test_fused_prefill_tcgen05(world, port):
     run_distributed(_worker_prefill, world, port)
 
 
+def _worker_zigzag(rank, world):
+    """kv_layout="zigzag" on GPUs: every rank owns chunks r and 2W-1-r of a causal sequence.  The fused backend runs ONE
+    tcgen05 launch over the two-segment shard (combine included); symm / nccl merge per-rank partials; all equal plain
+    causal attention over the whole sequence, forward and backward."""
+    import torch.distributed as dist
+    import tree_attention_b200 as ta
+    from tree_attention_b200.ops import reference as ref
+    from tree_attention_b200.ops.autograd import tree_attention_func
+
+    dev = torch.device("cuda", rank)
+    for (hq, hkv, S, d, dtype) in [(4, 4, 256 * 2 * world, 128, torch.bfloat16), (8, 2, 128 * 2 * world, 64, torch.float16),
+                                   (4, 2, 200 * 2 * world, 128, torch.bfloat16)]:   # last: chunks not tile-aligned -> two partials
+        g = torch.Generator(device=dev).manual_seed(5)
+        q = torch.randn(1, hq, S, d, device=dev, generator=g).to(dtype)
+        k_full = torch.randn(1, hkv, S, d, device=dev, generator=g).to(dtype)
+        v_full = torch.randn(1, hkv, S, d, device=dev, generator=g).to(dtype)
+        k, v = ta.zigzag_shard(k_full, rank, world).contiguous(), ta.zigzag_shard(v_full, rank, world).contiguous()
+        o_ref, l_ref = ref.attention_partial_ref(q, k_full, v_full, d ** -0.5, True, 0, 0, torch.float32)
+        for backend in ("fused", "symm", "nccl"):
+            out, lse = ta.tree_attention(q, k, v, causal=True, return_lse=True, backend=backend, kv_layout="zigzag",
+                                         schedule="allgather" if backend == "nccl" else "oneshot")
+            torch.cuda.synchronize()
+            err = (out.float() - o_ref).abs().max().item()
+            assert err < 3e-2, (backend, S, err)
+            assert (lse - l_ref).abs().max().item() < 5e-3, backend
+        out = ta.tree_attention(q, k, v, causal=True, backend="fused", kv_layout="zigzag")
+        o_sh = ta.tree_attention(q, k, v, causal=True, backend="fused", kv_layout="zigzag", output="sharded")
+        torch.cuda.synchronize()
+        n = o_sh.shape[2]
+        lo, hi = min(rank * n, S), min((rank + 1) * n, S)
+        assert (o_sh[:, :, : hi - lo].float() - out[:, :, lo:hi].float()).abs().max().item() < 1e-2
+        # the contiguous interpretation of the same shards is a different (wrong) sequence order
+        o_c = ta.tree_attention(q, k, v, causal=True, backend="fused")
+        assert (o_c.float() - o_ref).abs().max().item() > 1e-2
+    # backward through the zigzag layout (tcgen05 backward per segment, dQ reduced over symmetric memory)
+    qg = q.clone().requires_grad_(True)
+    kg, vg = k.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    do = torch.randn(q.shape, device=dev, generator=g).to(dtype)
+    tree_attention_func(qg, kg, vg, causal=True, kv_layout="zigzag").backward(do)
+    qo, ko, vo = (t.float().clone().requires_grad_(True) for t in (q, k_full, v_full))
+    ref.attention_partial_ref(qo, ko, vo, d ** -0.5, True, 0, 0, torch.float32)[0].backward(do.float())
+    torch.cuda.synchronize()
+    for got, exp, name in ((qg.grad, qo.grad, "dq"), (kg.grad, ta.zigzag_shard(ko.grad, rank, world), "dk"),
+                           (vg.grad, ta.zigzag_shard(vo.grad, rank, world), "dv")):
+        rel = (got.float() - exp).abs().max().item() / max(exp.abs().max().item(), 1e-6)
+        assert rel < 3e-2, (name, rel)
+
+
+@need2
+@pytest.mark.parametrize("world", WORLDS)
+def test_zigzag_causal_prefill(world, port):
+    run_distributed(_worker_zigzag, world, port)
+
+
 def _worker_stress(rank, world):
     """>= 1000 back-to-back fused steps: epoch/parity reuse must never serve stale partials."""
     import tree_attention_b200 as ta

@@ -24,6 +24,8 @@ struct FwdParams {
   float scale_log2;
   int causal;
   long long q_pos0, kv_pos0;
+  int seg_len;         // two-segment shard (zigzag): local rows >= seg_len sit seg_gap positions further on; INT_MAX = one segment
+  long long seg_gap;
   int num_m_tiles;
   int n_items;   // B * Hq * num_m_tiles
   int lag;       // merge CTA of item i is dispatched about `lag` compute CTAs after item i

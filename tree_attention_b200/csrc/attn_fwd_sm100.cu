@@ -85,11 +85,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
   }
 
   // number of KV tiles this query tile can see
+  // (two-segment shards -- zigzag sharding of a causal sequence: rows [0, seg_len) sit at kv_pos0 + row, rows [seg_len, S) at
+  // kv_pos0 + seg_gap + row with seg_gap >= 0, so whatever is visible is still a PREFIX of the local rows)
   int n_end = p.S;
   if (p.causal) {
     const long long last_q = p.q_pos0 + min(m0 + kBlockM - 1, p.Sq - 1);
-    const long long lim = last_q - p.kv_pos0 + 1;
-    n_end = (int)max(0LL, min((long long)p.S, lim));
+    const int len_a = min(p.seg_len, p.S);
+    const long long vis_a = max(0LL, min((long long)len_a, last_q - p.kv_pos0 + 1));
+    const long long vis_b = max(0LL, min((long long)(p.S - len_a), last_q - (p.kv_pos0 + p.seg_gap + len_a) + 1));
+    n_end = (int)(vis_b > 0 ? len_a + vis_b : vis_a);
   }
   const int n_tiles = (n_end + kBlockN - 1) / kBlockN;
 
@@ -251,7 +255,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
       tc_fence_after();
       const long long tp1 = clock64();
       const uint32_t s_tmem = tmem + (j & 1) * 128 + lane_addr;
-      const bool need_mask = (n0 + kBlockN > p.S) || (p.causal && (p.kv_pos0 + n0 + kBlockN - 1 > p.q_pos0 + m0));
+      const long long tile_pos = p.kv_pos0 + n0 + (n0 >= p.seg_len ? p.seg_gap : 0LL);   // global position of the tile's key 0
+      const bool need_mask = (n0 + kBlockN > p.S) || (p.causal && (tile_pos + kBlockN - 1 > p.q_pos0 + m0));
       uint32_t pk[64];
       bool done = false;
       // ---- fast path (interior tiles): exponentiate against the CURRENT reference maximum while the tile maximum is
@@ -305,7 +310,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap qmap, const __grid_constant_
         tmem_ld_wait();
         if (need_mask) {
           long long lim = (long long)p.S - n0 - 1;
-          if (p.causal) lim = min(lim, q_pos - p.kv_pos0 - n0);
+          if (p.causal) lim = min(lim, q_pos - tile_pos);
           const int limc = (int)max(-1LL, min(lim, 127LL));
 #pragma unroll
           for (int c = 0; c < 128; ++c)
@@ -458,6 +463,8 @@ void launch_fwd(const AttnShape& s, const void* q, const void* k, const void* v,
   p.B = s.B; p.Hq = s.Hq; p.Hkv = s.Hkv; p.G = s.Hq / s.Hkv; p.Sq = s.Sq; p.S = s.S;
   p.scale_log2 = s.softmax_scale * 1.4426950408889634f;
   p.causal = s.causal; p.q_pos0 = s.q_pos0; p.kv_pos0 = s.kv_pos0;
+  p.seg_len = s.kv_seg_len > 0 ? s.kv_seg_len : 0x7fffffff;
+  p.seg_gap = s.kv_seg_len > 0 ? s.kv_seg_gap : 0;
   p.num_m_tiles = (s.Sq + kBlockM - 1) / kBlockM;
   p.n_items = p.num_m_tiles * s.Hq * s.B;
   p.lag = std::min(p.n_items, 2 * num_sms());
@@ -512,6 +519,8 @@ size_t attn_fwd_comm_bytes(const AttnShape& s, int world, size_t* flag_bytes, in
 void attn_fwd_launch(const AttnShape& s, const void* q, const void* k, const void* v, void* out, float* lse,
                      const CommCtxHost& comm, cudaStream_t stream, int q_in_tmem, int comm_mode, int sq_out) {
   if (s.D != 64 && s.D != 128) throw std::runtime_error("attn_fwd: head_dim must be 64 or 128");
+  if (s.kv_seg_len < 0 || s.kv_seg_len % kBlockN != 0 || s.kv_seg_gap < 0)
+    throw std::runtime_error("attn_fwd: a two-segment shard needs kv_seg_len % 128 == 0 and kv_seg_gap >= 0");
   if (s.Hq % s.Hkv != 0) throw std::runtime_error("attn_fwd: Hq must be a multiple of Hkv");
   if (s.S <= 0 || s.Sq <= 0) throw std::runtime_error("attn_fwd: empty problem");
   const bool fused = comm.world > 1;

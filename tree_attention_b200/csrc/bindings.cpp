@@ -153,10 +153,12 @@ py::tuple attn_fwd_comm_bytes(int B, int Hq, int Sq, int D, int world, int comm_
 // comm_mode (with a Comm): 1 = replicated output, 2 = output sharded over Sq -- out is (B, Hq, sq_out, D), lse (B, Hq, sq_out)
 // with sq_out = ceil(ceil(Sq / 128) / world) * 128, the rows [rank * sq_out, ...) of the global result.
 void attn_fwd(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v, at::Tensor& out, at::Tensor& lse,
-              double scale, bool causal, int64_t q_pos0, int64_t kv_pos0, py::object comm, int variant, int comm_mode) {
+              double scale, bool causal, int64_t q_pos0, int64_t kv_pos0, py::object comm, int variant, int comm_mode,
+              int64_t kv_seg_len, int64_t kv_seg_gap) {
   c10::cuda::CUDAGuard guard(q.device());
   const bool sharded = !comm.is_none() && comm_mode == 2;
   AttnShape s = make_shape(q, k, v, sharded ? q : out, scale, causal, q_pos0, kv_pos0);
+  s.kv_seg_len = (int)kv_seg_len; s.kv_seg_gap = kv_seg_gap;   // zigzag shards: see kernels.h
   int64_t sq_out = s.Sq;
   if (sharded) {
     TORCH_CHECK(out.dim() == 4 && out.is_cuda() && out.scalar_type() == q.scalar_type() && out.stride(3) == 1 &&
@@ -603,7 +605,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("mxfp8_seq_append", &mxfp8_seq_append);
   m.def("dequant_mxfp8", &dequant_mxfp8);
   m.def("attn_fwd", &attn_fwd, py::arg("q"), py::arg("k"), py::arg("v"), py::arg("out"), py::arg("lse"), py::arg("scale"),
-        py::arg("causal"), py::arg("q_pos0"), py::arg("kv_pos0"), py::arg("comm"), py::arg("variant") = 0, py::arg("comm_mode") = 1);
+        py::arg("causal"), py::arg("q_pos0"), py::arg("kv_pos0"), py::arg("comm"), py::arg("variant") = 0, py::arg("comm_mode") = 1,
+        py::arg("kv_seg_len") = 0, py::arg("kv_seg_gap") = 0);
   m.def("attn_fwd_comm_bytes", &attn_fwd_comm_bytes, py::arg("B"), py::arg("Hq"), py::arg("Sq"), py::arg("D"), py::arg("world"),
         py::arg("comm_mode") = 1);
   m.def("attn_fwd_phase_cycles", []() { unsigned long long c[5]; ta::attn_fwd_phase_cycles(c); return py::make_tuple(c[0], c[1], c[2], c[3], c[4]); });

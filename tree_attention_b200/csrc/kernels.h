@@ -40,6 +40,10 @@ struct AttnShape {
   int causal = 0;
   int64_t q_pos0 = 0;   // global position of query row 0
   int64_t kv_pos0 = 0;  // global position of local key row 0
+  // two-segment shard (zigzag sharding of a causal sequence, forward kernel only): local rows [kv_seg_len, S) sit at
+  // kv_pos0 + kv_seg_gap + row.  kv_seg_len = 0: one contiguous segment.  Needs kv_seg_len % 128 == 0, kv_seg_gap >= 0.
+  int kv_seg_len = 0;
+  int64_t kv_seg_gap = 0;
   // element strides, innermost (D) contiguous
   int64_t q_sb = 0, q_sh = 0, q_ss = 0;
   int64_t k_sb = 0, k_sh = 0, k_ss = 0;

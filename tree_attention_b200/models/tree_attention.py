@@ -21,10 +21,10 @@ from ..parallel.tree import tree_attention
 
 class TreeAttention(nn.Module):
     def __init__(self, causal: bool = False, softmax_scale: Optional[float] = None, backend: str = "auto",
-                 schedule: str = "oneshot", group=None, layout: str = "bhsd"):
+                 schedule: str = "oneshot", group=None, layout: str = "bhsd", kv_layout: str = "contiguous"):
         super().__init__()
         self.causal, self.softmax_scale, self.backend, self.schedule = causal, softmax_scale, backend, schedule
-        self.group, self.layout = group, layout
+        self.group, self.layout, self.kv_layout = group, layout, kv_layout   # kv_layout="zigzag": balanced causal shards
 
     def forward(self, q, k, v, kv_offset: Optional[int] = None, q_offset: Optional[int] = None):
         if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
@@ -32,10 +32,10 @@ class TreeAttention(nn.Module):
 
             return tree_attention_func(q, k, v, causal=self.causal, softmax_scale=self.softmax_scale,
                                        group=self.group, kv_offset=kv_offset, q_offset=q_offset, backend=self.backend,
-                                       schedule=self.schedule, layout=self.layout)
+                                       schedule=self.schedule, layout=self.layout, kv_layout=self.kv_layout)
         return tree_attention(q, k, v, group=self.group, causal=self.causal, softmax_scale=self.softmax_scale,
                               kv_offset=kv_offset, q_offset=q_offset, backend=self.backend, schedule=self.schedule,
-                              layout=self.layout)
+                              layout=self.layout, kv_layout=self.kv_layout)
 
 
 class TreeSelfAttention(nn.Module):

@@ -42,29 +42,48 @@ def _local_bwd(q, k, v, o, lse, do, scale, causal, q_pos0, kv_pos0):
 
 class _TreeAttentionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, causal, softmax_scale, group, kv_offset, q_offset, backend, schedule):
+    def forward(ctx, q, k, v, causal, softmax_scale, group, kv_offset, q_offset, backend, schedule, kv_layout="contiguous"):
         rank, world = _world(group)
         scale = ref.default_scale(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
         s_local = k.shape[2]
-        kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
         q_pos0 = (world * s_local - q.shape[2]) if q_offset is None else int(q_offset)
-        o, lse = tree_attention(q, k, v, group=group, causal=causal, softmax_scale=scale, kv_offset=kv_pos0,
-                                q_offset=q_pos0, return_lse=True, backend=backend, schedule=schedule)
+        zigzag = kv_layout == "zigzag" and causal and world > 1
+        if zigzag:
+            # two equal chunks per rank: chunk r and chunk 2W-1-r of the sequence (parallel/tree.py zigzag_shard)
+            from ..parallel.tree import zigzag_chunks
+
+            half = s_local // 2
+            segs = [(0, half, zigzag_chunks(rank, world)[0] * half), (half, half, zigzag_chunks(rank, world)[1] * half)]
+            o, lse = tree_attention(q, k, v, group=group, causal=True, softmax_scale=scale, q_offset=q_pos0, return_lse=True,
+                                    backend=backend, schedule=schedule, kv_layout="zigzag")
+        else:
+            kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
+            segs = [(0, s_local, kv_pos0)]
+            o, lse = tree_attention(q, k, v, group=group, causal=causal, softmax_scale=scale, kv_offset=kv_pos0,
+                                    q_offset=q_pos0, return_lse=True, backend=backend, schedule=schedule)
         ctx.save_for_backward(q, k, v, o, lse)
-        ctx.meta = (scale, causal, q_pos0, kv_pos0, group, world)
+        ctx.meta = (scale, causal, q_pos0, segs, group, world)
         return o
 
     @staticmethod
     def backward(ctx, do):
         q, k, v, o, lse, = ctx.saved_tensors
-        scale, causal, q_pos0, kv_pos0, group, world = ctx.meta
-        dq, dk, dv = _local_bwd(q, k, v, o, lse, do.contiguous(), scale, causal, q_pos0, kv_pos0)
-        dq = dq.float().contiguous()
+        scale, causal, q_pos0, segs, group, world = ctx.meta
+        do = do.contiguous()
+        dq, dks, dvs = None, [], []
+        for row0, n, pos in segs:   # one local backward per contiguous segment of the shard (two under zigzag sharding)
+            dq_i, dk_i, dv_i = _local_bwd(q, k[:, :, row0:row0 + n], v[:, :, row0:row0 + n], o, lse, do, scale, causal, q_pos0, pos)
+            dq = dq_i.float() if dq is None else dq + dq_i.float()
+            dks.append(dk_i)
+            dvs.append(dv_i)
+        dk = dks[0] if len(dks) == 1 else torch.cat(dks, 2)
+        dv = dvs[0] if len(dvs) == 1 else torch.cat(dvs, 2)
+        dq = dq.contiguous()
         if world > 1:
             from ..parallel.tree import allreduce_sum
 
             dq = allreduce_sum(dq, group)  # symmetric-memory kernel on CUDA, all_reduce on CPU
-        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None, None, None, None, None
+        return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), None, None, None, None, None, None, None, None
 
 
 def tree_attention_func(
@@ -79,9 +98,12 @@ def tree_attention_func(
     backend: str = "auto",
     schedule: str = "oneshot",
     layout: str = "bhsd",
+    kv_layout: str = "contiguous",
 ) -> torch.Tensor:
-    """Differentiable ``tree_attention`` (replicated q, sequence-sharded k/v)."""
+    """Differentiable ``tree_attention`` (replicated q, sequence-sharded k/v; ``kv_layout="zigzag"``: balanced causal shards)."""
     if layout == "bshd":
         q, k, v = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
-    o = _TreeAttentionFn.apply(q, k, v, causal, softmax_scale, group, kv_offset, q_offset, backend, schedule)
+    if kv_layout == "zigzag" and kv_offset is not None:
+        raise ValueError("kv_layout='zigzag' derives the key positions itself: do not pass kv_offset")
+    o = _TreeAttentionFn.apply(q, k, v, causal, softmax_scale, group, kv_offset, q_offset, backend, schedule, kv_layout)
     return o.transpose(1, 2) if layout == "bshd" else o

@@ -44,10 +44,13 @@ def attention_fwd(
     comm=None,
     variant: int = 0,
     comm_mode: int = 1,
+    kv_seg: Optional[Tuple[int, int]] = None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """Shard-local partial ``(o, lse)``; with ``comm`` (a ``_C.Comm`` of the ``fwd`` family) the SAME launch also performs
     the cross-GPU combine: ``comm_mode=1`` -> the global result replicated on every rank, ``comm_mode=2`` -> the global
-    result sharded over Sq (this rank's ``sq_out`` rows, see ``sharded_rows``)."""
+    result sharded over Sq (this rank's ``sq_out`` rows, see ``sharded_rows``).
+    ``kv_seg=(seg_len, seg_gap)``: a two-segment shard (zigzag sharding): local rows ``>= seg_len`` sit ``seg_gap``
+    positions further on in the global sequence (``seg_len % 128 == 0``, ``seg_gap >= 0``)."""
     C = _build.load()
     q = q if q.stride(-1) == 1 else q.contiguous()
     k = k if k.stride(-1) == 1 else k.contiguous()
@@ -60,7 +63,8 @@ def attention_fwd(
         out = torch.empty((b, hq, rows, d), dtype=q.dtype, device=q.device)
     lse = torch.empty((b, hq, rows), dtype=torch.float32, device=q.device)
     C.attn_fwd(q, k, v, out, lse, float(softmax_scale), bool(causal), int(q_pos0), int(kv_pos0), comm,
-               int(os.environ.get("TREE_ATTN_FWD_VARIANT", variant)), int(comm_mode))
+               int(os.environ.get("TREE_ATTN_FWD_VARIANT", variant)), int(comm_mode),
+               int(kv_seg[0]) if kv_seg else 0, int(kv_seg[1]) if kv_seg else 0)
     return out, lse
 
 
@@ -111,6 +115,7 @@ def attention_fwd_fused(
     group=None,
     return_lse: bool = True,
     output: str = "replicated",
+    kv_seg: Optional[Tuple[int, int]] = None,
 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """ONE launch per rank: tcgen05 attention over the local KV shard; every 128-row query tile has an owner rank, the
     partial tiles are pushed to their owner over NVLink from the epilogue (reduce-scatter), merge CTAs of the same launch
@@ -135,7 +140,7 @@ def attention_fwd_fused(
     if output == "sharded":
         data, flags = C.attn_fwd_comm_bytes(b, hq, sq, d, world, 2)
         reg = symm.get_region("fwd_rs", int(data), int(flags), group, layout=(b, hq, sq, d))
-        o_c, l_c = attention_fwd(q, k, v, softmax_scale, causal, q_pos0, kv_pos0, comm=reg.comm, comm_mode=2)
+        o_c, l_c = attention_fwd(q, k, v, softmax_scale, causal, q_pos0, kv_pos0, comm=reg.comm, comm_mode=2, kv_seg=kv_seg)
         return o_c, (l_c if return_lse else None)
     if output != "replicated":
         raise ValueError("output must be 'replicated' or 'sharded'")
@@ -146,12 +151,12 @@ def attention_fwd_fused(
     out = torch.empty((b, hq, sq, d), dtype=q.dtype, device=q.device)
     lse = torch.empty((b, hq, sq), dtype=torch.float32, device=q.device)
     if chunk >= sq:
-        o_c, l_c = attention_fwd(q, k, v, softmax_scale, causal, q_pos0, kv_pos0, out=out, comm=reg.comm)
+        o_c, l_c = attention_fwd(q, k, v, softmax_scale, causal, q_pos0, kv_pos0, out=out, comm=reg.comm, kv_seg=kv_seg)
         return o_c, l_c
     for s0 in range(0, sq, chunk):
         s1 = min(sq, s0 + chunk)
         reg = symm.get_region("fwd", int(data), int(flags), group, layout=(b, hq, s1 - s0, d))  # fences a ragged tail
         o_c, l_c = attention_fwd(q[:, :, s0:s1], k, v, softmax_scale, causal, q_pos0 + s0, kv_pos0,
-                                 out=out[:, :, s0:s1], comm=reg.comm)
+                                 out=out[:, :, s0:s1], comm=reg.comm, kv_seg=kv_seg)
         lse[:, :, s0:s1] = l_c
     return out, lse

@@ -209,6 +209,7 @@ def tree_attention(
     decode_pdl: int = 0,
     kv_len=None,
     output: str = "replicated",
+    kv_layout: str = "contiguous",
 ) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
     """Exact attention of replicated ``q`` over a KV sequence sharded across the ranks of ``group``.
 
@@ -233,6 +234,12 @@ def tree_attention(
     ``Sq`` in the last block are undefined).  On the fused prefill path this is a reduce-scatter inside the attention
     kernel -- every rank receives ``(W-1)/W |O|`` bytes instead of sending ``(W-1) |O|`` -- other paths slice.
 
+    ``kv_layout="zigzag"`` (causal prefill): this rank's shard is ``[chunk r | chunk 2W-1-r]`` of the sequence cut into
+    ``2W`` equal chunks (``zigzag_shard``).  With contiguous shards a causal mask leaves the last rank almost idle while
+    rank 0 does the full work (every rank waits for it in the combine); zigzag gives every rank ``(2W+1)/(4W)`` of that.
+    The tcgen05 forward kernel takes the two-segment shard natively (one launch, fused combine included); other paths
+    compute one partial per segment and merge.  Non-causal calls ignore the layout (positions do not matter).
+
     Returns the global attention output (replicated, bitwise identical across ranks for the fused and
     symm backends) and optionally the global ``lse``.
     """
@@ -254,9 +261,20 @@ def tree_attention(
     scale = ref.default_scale(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
     s_local = k.shape[2]
 
+    if quantised and kv_layout == "zigzag" and causal and world > 1:
+        raise ValueError("kv_layout='zigzag' is not supported for quantised KV caches")
     if quantised:  # fp8 KV cache (block-scaled MX or per-channel scaled)
         return _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset, q_offset, return_lse,
                                      backend, schedule, kv_len)
+    if kv_layout not in ("contiguous", "zigzag"):
+        raise ValueError("kv_layout must be 'contiguous' or 'zigzag'")
+    if kv_layout == "zigzag" and causal and world > 1:
+        if kv_offset is not None or kv_len is not None or quantised:
+            raise ValueError("kv_layout='zigzag' derives the key positions itself: kv_offset / kv_len / quantised caches are not supported")
+        o, lse = _tree_attention_zigzag(q, k, v, group, rank, world, scale, q_offset, return_lse, backend, schedule, output)
+        if layout == "bshd":
+            o = o.transpose(1, 2)
+        return (o, lse) if return_lse else o
     kv_pos0 = rank * s_local if kv_offset is None else int(kv_offset)
     q_pos0 = (world * s_local - q.shape[2]) if q_offset is None else int(q_offset)
     be = _resolve_backend(backend, q, world)
@@ -317,6 +335,70 @@ def shard_rows(o: torch.Tensor, lse: Optional[torch.Tensor], rank: int, world: i
         l_s = lse.new_full((lse.shape[0], lse.shape[1], n), float("-inf"))
         l_s[:, :, : hi - lo] = lse[:, :, lo:hi]
     return o_s, l_s
+
+
+def zigzag_chunks(rank: int, world: int) -> Tuple[int, int]:
+    """The two chunk indices (of ``2 * world`` equal chunks of the sequence) rank ``rank`` owns under zigzag sharding."""
+    return rank, 2 * world - 1 - rank
+
+
+def zigzag_shard(x: torch.Tensor, rank: int, world: int, dim: int = 2) -> torch.Tensor:
+    """This rank's zigzag shard ``[chunk r | chunk 2W-1-r]`` of a full-sequence tensor (sequence along ``dim``, length a
+    multiple of ``2 * world``)."""
+    n = x.shape[dim]
+    if n % (2 * world):
+        raise ValueError(f"zigzag sharding needs a sequence length divisible by 2 * world ({n} % {2 * world} != 0)")
+    c = n // (2 * world)
+    a, b = zigzag_chunks(rank, world)
+    return torch.cat([x.narrow(dim, a * c, c), x.narrow(dim, b * c, c)], dim)
+
+
+def zigzag_unshard(shards, dim: int = 2) -> torch.Tensor:
+    """Inverse of ``zigzag_shard``: the full sequence from the list of all ranks' shards (rank order)."""
+    world = len(shards)
+    c = shards[0].shape[dim] // 2
+    chunks = [None] * (2 * world)
+    for r, sh in enumerate(shards):
+        a, b = zigzag_chunks(r, world)
+        chunks[a], chunks[b] = sh.narrow(dim, 0, c), sh.narrow(dim, c, c)
+    return torch.cat(chunks, dim)
+
+
+def _tree_attention_zigzag(q, k, v, group, rank, world, scale, q_offset, return_lse, backend, schedule, output):
+    """Causal attention over a zigzag-sharded KV sequence (``tree_attention(kv_layout="zigzag")``)."""
+    s_local = k.shape[2]
+    if s_local % 2:
+        raise ValueError("kv_layout='zigzag' needs an even number of local KV rows (two equal chunks)")
+    half = s_local // 2
+    ca, cb = zigzag_chunks(rank, world)
+    pos_a, pos_b = ca * half, cb * half
+    gap = pos_b - pos_a - half            # >= 0: the second chunk always lies further on in the sequence
+    q_pos0 = (world * s_local - q.shape[2]) if q_offset is None else int(q_offset)
+    be = _resolve_backend(backend, q, world)
+    native = False
+    if q.is_cuda and half % 128 == 0 and not local_ops.decode_eligible(q, k):
+        from ..ops import flash
+
+        native = flash.fwd_eligible(q, k)
+    if be == "fused" and native:
+        with _nvtx("tree_attention/zigzag[fused]"):
+            o, lse = flash.attention_fwd_fused(q, k, v, scale, True, q_pos0, pos_a, group=group, return_lse=return_lse,
+                                               output=output, kv_seg=(half, gap))
+        return o, lse
+    with _nvtx("tree_attention/zigzag[local_partial]"):
+        if native:   # one launch over both segments
+            o_p, lse_p = flash.attention_fwd(q, k, v, scale, True, q_pos0, pos_a, kv_seg=(half, gap))
+        else:
+            parts = [local_ops.attention_partial(q, k[:, :, a:a + half], v[:, :, a:a + half], scale, True, q_pos0, pos)
+                     for a, pos in ((0, pos_a), (half, pos_b))]
+            o_p, lse_p = ref.merge_many([p[0].float() for p in parts], [p[1] for p in parts])
+            o_p = o_p.to(parts[0][0].dtype)
+    sched = "allgather" if (be == "collective" and schedule == "oneshot") else schedule
+    with _nvtx("tree_attention/zigzag[combine]"):
+        o, lse = combine_partials(o_p, lse_p, group, "collective" if be == "collective" else "symm", sched, out_dtype=o_p.dtype)
+    if output == "sharded":
+        o, lse = shard_rows(o, lse, rank, world)
+    return o, lse
 
 
 def _tree_attention_mxfp8(q, k, v, group, rank, world, scale, causal, kv_offset, q_offset, return_lse, backend,
