@@ -9,11 +9,12 @@ Public API (names and signatures of ``/root/reference/model.py`` plus ``tree_att
 """
 from .ops.local import attention_partial, flash_res_lse  # noqa: F401
 from .parallel.runtime import cleanup, get_runtime, setup  # noqa: F401
-from .parallel.tree import combine_partials, tree_attention, tree_decode, zigzag_shard, zigzag_unshard  # noqa: F401
+from .parallel.tree import (allreduce_sum, combine_partials, tree_attention, tree_decode, zigzag_shard,  # noqa: F401
+                            zigzag_unshard)
 from .utils.data import make_data  # noqa: F401
 
 __version__ = "0.1.0"
 __all__ = [
     "setup", "cleanup", "get_runtime", "make_data", "flash_res_lse", "attention_partial",
-    "tree_decode", "tree_attention", "combine_partials", "zigzag_shard", "zigzag_unshard",
+    "tree_decode", "tree_attention", "combine_partials", "allreduce_sum", "zigzag_shard", "zigzag_unshard",
 ]
