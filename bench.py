@@ -416,7 +416,7 @@ def main():
     import threading
 
     emitted = threading.Lock()
-    extras_budget_s = float(os.environ.get("TREE_ATTN_BENCH_EXTRAS_BUDGET_S", "300"))
+    extras_budget_s = float(os.environ.get("TREE_ATTN_BENCH_EXTRAS_BUDGET_S", "240"))
 
     def watchdog_fire():
         if not emitted.acquire(blocking=False):
