@@ -7,7 +7,11 @@
 The toy model is one ``TreeSelfAttention`` block + a linear head.  Query tokens are replicated; every rank projects its
 own slice of the context to K/V.  Parameters are replicated, so their gradients are averaged with one all-reduce per
 step (what DDP would do).  The script checks the sharded loss and gradients against a single-process run over the full
-context."""
+context.
+
+``--causal``: causal SELF-attention over the whole sequence (queries = all tokens, replicated) with the K/V tokens in
+ZIGZAG shards (rank r projects chunks r and 2W-1-r, ``ta.zigzag_shard``): every rank then does the same share of the
+causal work instead of rank 0 doing twice the average."""
 from __future__ import annotations
 
 import argparse
@@ -25,9 +29,10 @@ from tree_attention_b200.models.tree_attention import TreeSelfAttention  # noqa:
 
 
 class Block(nn.Module):
-    def __init__(self, e: int, h: int, hkv: int, dtype, device):
+    def __init__(self, e: int, h: int, hkv: int, dtype, device, causal: bool = False):
         super().__init__()
-        self.attn = TreeSelfAttention(e, h, hkv, causal=False, dtype=dtype, device=device)
+        self.attn = TreeSelfAttention(e, h, hkv, causal=causal, dtype=dtype, device=device,
+                                      kv_layout="zigzag" if causal else "contiguous")
         self.head = nn.Linear(e, 1, dtype=dtype, device=device)
 
     def forward(self, x_q, x_kv, kv_offset=None):
@@ -39,14 +44,17 @@ def worker(rank: int, world: int, a) -> None:
     ta.setup(rank, world, master_port=a.port)
     dtype = torch.bfloat16 if dev.type == "cuda" else torch.float32
     torch.manual_seed(0)                        # identical parameters and data on every rank
-    model = Block(a.embed, a.heads, a.kv_heads, dtype, dev)
+    model = Block(a.embed, a.heads, a.kv_heads, dtype, dev, causal=a.causal)
     x_q = torch.randn(1, a.q_tokens, a.embed, device=dev).to(dtype)
     ctx = torch.randn(1, a.ctx_tokens * world, a.embed, device=dev).to(dtype)
     x_kv = ctx[:, rank * a.ctx_tokens:(rank + 1) * a.ctx_tokens]      # this rank's slice of the context
+    if a.causal:                                                       # self-attention: every token is a query
+        x_q = ctx
+        x_kv = ta.zigzag_shard(ctx, rank, world, dim=1)                # chunks r and 2W-1-r of the token sequence
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
     for step in range(a.steps):
         opt.zero_grad(set_to_none=True)
-        loss = model(x_q, x_kv, kv_offset=rank * a.ctx_tokens)
+        loss = model(x_q, x_kv, kv_offset=None if a.causal else rank * a.ctx_tokens)
         loss.backward()
         if world > 1:
             for p in model.parameters():
@@ -57,18 +65,22 @@ def worker(rank: int, world: int, a) -> None:
                 if not is_kv:
                     p.grad /= world
         if step == 0 and a.check:
-            ref = Block(a.embed, a.heads, a.kv_heads, dtype, dev)
+            ref = Block(a.embed, a.heads, a.kv_heads, dtype, dev, causal=a.causal)
             ref.load_state_dict(model.state_dict())
             saved = ta.get_runtime().world_size
             # single-process reference over the full context: plain attention through the same module on a 1-rank view
-            q = ref.attn.q_proj(x_q).view(1, a.q_tokens, a.heads, -1).transpose(1, 2)
+            nq = x_q.shape[1]
+            q = ref.attn.q_proj(x_q).view(1, nq, a.heads, -1).transpose(1, 2)
             kv = ref.attn.kv_proj(ctx).view(1, ctx.shape[1], 2, a.kv_heads, q.shape[-1])
             k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
             g = a.heads // a.kv_heads
             kf, vf = k.float().repeat_interleave(g, dim=1), v.float().repeat_interleave(g, dim=1)
-            p_attn = torch.softmax(q.float() @ kf.transpose(-1, -2) * q.shape[-1] ** -0.5, dim=-1)
+            logits = q.float() @ kf.transpose(-1, -2) * q.shape[-1] ** -0.5
+            if a.causal:
+                logits = logits.masked_fill(torch.ones(nq, nq, dtype=torch.bool, device=dev).triu(1), float("-inf"))
+            p_attn = torch.softmax(logits, dim=-1)
             o = (p_attn @ vf).to(dtype)
-            y = ref.attn.o_proj(o.transpose(1, 2).reshape(1, a.q_tokens, -1))
+            y = ref.attn.o_proj(o.transpose(1, 2).reshape(1, nq, -1))
             loss_ref = ref.head(x_q + y).float().square().mean()
             loss_ref.backward()
             tol = 5e-2 if dtype == torch.bfloat16 else 1e-4
@@ -95,6 +107,7 @@ def main() -> None:
     ap.add_argument("--ctx-tokens", type=int, default=256, help="context tokens PER RANK")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--check", action=argparse.BooleanOptionalAction, default=True)
+    ap.add_argument("--causal", action="store_true", help="causal self-attention over the whole sequence, zigzag K/V shards")
     ap.add_argument("--port", type=int, default=12362)
     a = ap.parse_args()
     if "RANK" in os.environ:

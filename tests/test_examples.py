@@ -20,6 +20,12 @@ def test_context_parallel_training_example(port):
     assert "gradients match (2 rank(s))" in out
 
 
+def test_context_parallel_training_example_causal_zigzag(port):
+    out = _run([os.path.join(ROOT, "examples", "train_context_parallel.py"), "--world", "2", "--steps", "2", "--causal",
+                "--ctx-tokens", "64", "--embed", "128"], port)
+    assert "gradients match (2 rank(s))" in out
+
+
 def test_decode_server_example_quantised_cache(port):
     out = _run([os.path.join(ROOT, "examples", "decode_server.py"), "--tokens-per-rank", "200", "--steps", "3",
                 "--kv-format", "mxfp8", "--kv-heads", "2"], port)

@@ -42,7 +42,7 @@ class TreeSelfAttention(nn.Module):
     """x_q: (B, Sq, E) replicated query tokens; x_kv: (B, S_local, E) this rank's slice of the context."""
 
     def __init__(self, embed_dim: int, num_heads: int, num_kv_heads: Optional[int] = None, causal: bool = False,
-                 bias: bool = False, group=None, dtype=None, device=None):
+                 bias: bool = False, group=None, dtype=None, device=None, kv_layout: str = "contiguous"):
         super().__init__()
         self.h, self.hkv = num_heads, num_kv_heads or num_heads
         assert embed_dim % num_heads == 0 and num_heads % self.hkv == 0
@@ -51,7 +51,7 @@ class TreeSelfAttention(nn.Module):
         self.q_proj = nn.Linear(embed_dim, self.h * self.d, bias=bias, **kw)
         self.kv_proj = nn.Linear(embed_dim, 2 * self.hkv * self.d, bias=bias, **kw)
         self.o_proj = nn.Linear(self.h * self.d, embed_dim, bias=bias, **kw)
-        self.attn = TreeAttention(causal=causal, group=group)
+        self.attn = TreeAttention(causal=causal, group=group, kv_layout=kv_layout)   # "zigzag": x_kv = zigzag_shard(tokens)
 
     def forward(self, x_q: torch.Tensor, x_kv: torch.Tensor, kv_offset: Optional[int] = None,
                 q_offset: Optional[int] = None) -> torch.Tensor:
