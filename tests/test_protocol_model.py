@@ -79,3 +79,87 @@ def test_parity_double_buffering_is_safe_and_live(world, launches):
 def test_single_slot_set_is_caught_by_the_checker():
     violation, _, _ = _explore(2, 3, slot_sets=1)
     assert violation, "negative control: one slot set must be unsafe"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# launch tags from arrival counters (csrc/decode_comm.cuh::launch_tag): every CTA adds 1 to a 64-bit counter when it starts,
+# CTA 0 adds 4096 - (grid - 1); tag = old / 4096 + 1.  Claim: for ANY arrival order inside a launch (launches themselves are
+# ordered: a launch's arrivals happen after the previous launch has completed -- stream order or griddepcontrol.wait) every
+# CTA of launch n computes the same tag n + 1, also when the grid size changes from launch to launch.
+# ----------------------------------------------------------------------------------------------------------------------
+def _tags_of_launch(counter: int, grid: int, order):
+    tags = {}
+    for cta in order:
+        inc = (4096 - (grid - 1)) if cta == 0 else 1
+        tags[cta] = counter // 4096 + 1
+        counter += inc
+    return counter, tags
+
+
+def test_arrival_counter_tags_are_uniform_per_launch_for_any_arrival_order():
+    import random
+
+    rng = random.Random(0)
+    counter = 0
+    for launch in range(200):
+        grid = rng.choice([1, 2, 7, 32, 147, 148, 4096])
+        order = list(range(grid))
+        rng.shuffle(order)
+        if launch % 3 == 0:                       # CTA 0 first / last are the extreme cases
+            order.remove(0)
+            order = ([0] + order) if launch % 2 else (order + [0])
+        counter, tags = _tags_of_launch(counter, grid, order)
+        assert set(tags.values()) == {launch + 1}, (launch, grid)
+        assert counter == 4096 * (launch + 1)      # every launch advances the counter by exactly 4096
+    # the tag's parity (slot set of the cross-GPU words) alternates from launch to launch by construction
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# designated merger of the split merge: the CTA that owns a head's LAST tile merges the head after its own last tile, and only
+# ever waits for CTAs with a LOWER block index.  Model: CTAs become resident in index order (a CTA with index i may start only
+# when all j < i have started -- the hardware's dispatch order; here at most `resident` CTAs run at a time), every CTA first
+# publishes all its partials (never blocks) and then waits for the parts of the heads it merges.  Liveness: the schedule
+# always terminates, for any geometry, even with ONE resident CTA at a time.
+# ----------------------------------------------------------------------------------------------------------------------
+def _split(total, ncta):
+    q, r = divmod(total, ncta)
+    lo = [c * q + min(c, r) for c in range(ncta + 1)]
+    return lo
+
+
+@pytest.mark.parametrize("resident", [1, 2, 148])
+def test_designated_merger_never_waits_for_a_later_cta(resident):
+    import random
+
+    rng = random.Random(1)
+    for _ in range(300):
+        heads = rng.randint(1, 40)
+        tph = rng.randint(1, 70)
+        total = heads * tph
+        ncta = min(total, rng.choice([1, 3, 16, 148]))
+        lo = _split(total, ncta)
+        owner_of_tile = lambda t: max(c for c in range(ncta) if lo[c] <= t)
+        published = set()                 # (cta, head) partials visible
+        done = [False] * ncta
+        started = 0
+        running = []
+        steps = 0
+        while not all(done):
+            steps += 1
+            assert steps < 10 * ncta + 10, "split merge does not terminate"
+            while started < ncta and len(running) < resident:      # dispatch in index order
+                running.append(started)
+                started += 1
+            progressed = False
+            for c in list(running):
+                my_heads = range(lo[c] // tph, (lo[c + 1] - 1) // tph + 1) if lo[c + 1] > lo[c] else []
+                for x in my_heads:                                   # streaming + tagged partial stores never block
+                    published.add((c, x))
+                merges = [x for x in my_heads if owner_of_tile((x + 1) * tph - 1) == c]
+                need = {(owner_of_tile(t), x) for x in merges for t in range(x * tph, (x + 1) * tph)}
+                assert all(src <= c for src, _ in need), "a merger would wait for a CTA dispatched after it"
+                if need <= published:
+                    done[c] = True
+                    running.remove(c)
+                    progressed = True
+            assert progressed, "deadlock: a resident merger waits for a CTA that cannot become resident"
