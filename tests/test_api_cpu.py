@@ -128,3 +128,34 @@ def test_config_defaults_are_reference_literals():
     assert c.master_port == 12355 and c.log_file == "tree_attention_log.log"                      # model.py:21,160
     c2 = from_args(["--seq-len", "128", "--num-kv-heads", "4", "--no-check"])
     assert c2.seq_len == 128 and c2.kv_heads == 4 and c2.check is False
+
+
+def test_zigzag_layout_helpers_and_single_rank_passthrough():
+    """zigzag_shard / zigzag_unshard are inverses; with one rank (or without a causal mask) kv_layout='zigzag' is the
+    contiguous layout; contradictory arguments are rejected."""
+    import pytest
+    import tree_attention_b200 as ta
+    from tree_attention_b200.parallel.tree import zigzag_chunks
+
+    x = torch.arange(2 * 3 * 24 * 4, dtype=torch.float32).view(2, 3, 24, 4)
+    for world in (1, 2, 3, 4):
+        shards = [ta.zigzag_shard(x, r, world) for r in range(world)]
+        assert all(s.shape[2] == 24 // world for s in shards)
+        assert torch.equal(ta.zigzag_unshard(shards), x)
+        owned = sorted(c for r in range(world) for c in zigzag_chunks(r, world))
+        assert owned == list(range(2 * world))           # every chunk owned exactly once
+    y = torch.arange(2 * 24 * 3 * 4, dtype=torch.float32).view(2, 24, 3, 4)       # (B, S, H, D): sequence along dim 1
+    assert torch.equal(ta.zigzag_unshard([ta.zigzag_shard(y, r, 2, dim=1) for r in range(2)], dim=1), y)
+    with pytest.raises(ValueError):
+        ta.zigzag_shard(x, 0, 5)                          # 24 % 10 != 0
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(1, 2, 8, 16, generator=g)
+    k = torch.randn(1, 2, 8, 16, generator=g)
+    v = torch.randn(1, 2, 8, 16, generator=g)
+    a = ta.tree_attention(q, k, v, causal=True, kv_layout="zigzag")               # world 1: chunks 0 and 1 are adjacent
+    b = ta.tree_attention(q, k, v, causal=True)
+    assert torch.equal(a, b)
+    a = ta.tree_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), causal=True, kv_layout="zigzag", layout="bshd")
+    assert torch.allclose(a.transpose(1, 2), b)
+    with pytest.raises(ValueError):
+        ta.tree_attention(q, k, v, causal=True, kv_layout="ring")
