@@ -56,3 +56,51 @@ def test_max_parts_bounds_sharing_for_every_fill_level(b, hkv, cap, frac, ncta):
         owners = [c for c in range(grid) if lo[c + 1] > x * tph and lo[c] < (x + 1) * tph]
         assert owners and owners == list(range(owners[0], owners[-1] + 1))
         assert len(owners) <= max_parts, (len(owners), max_parts, b, hkv, cap, s_eff, ncta)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Executable model of the speed-weighted split that docs/NEXT.md section 1 proposes for the decode kernels (NOT in the kernels
+# yet): each CTA claims a contiguous tile range whose length is proportional to the measured streaming rate of the SM it
+# landed on, with ONE atomicAdd on a packed (claim count | tiles) counter.  The properties below are what the kernel-side
+# merge logic would rely on; they hold for any block -> SM mapping and any claim order.
+# ----------------------------------------------------------------------------------------------------------------------
+def _claim_split(total, weights_by_sm, sm_of_claimer):
+    wsum = sum(weights_by_sm)
+    pieces, cursor = [], 0
+    for k, sm in enumerate(sm_of_claimer):                  # k = claim order = value of the packed counter's count field
+        ln = -(-total * weights_by_sm[sm] // wsum)           # ceil(T * w / W): the lengths sum to >= T
+        pieces.append((min(cursor, total), min(cursor + ln, total)))
+        cursor += ln
+    return pieces
+
+
+def test_weighted_claim_split_model():
+    import random
+
+    rng = random.Random(5)
+    for _ in range(400):
+        nsm = rng.choice([4, 16, 148])
+        heads, tph = rng.randint(1, 64), rng.randint(1, 300)
+        total = heads * tph
+        weights = [rng.choice([100, 100, 100, 92, 87]) for _ in range(nsm)]   # 8 % and 13 % slower SMs, as measured
+        sm_of_claimer = list(range(nsm))
+        rng.shuffle(sm_of_claimer)                            # one CTA per SM, arbitrary claim order (PDL makes it vary)
+        pieces = _claim_split(total, weights, sm_of_claimer)
+        # 1. disjoint, ordered by claim index, covering every tile exactly once
+        assert pieces[0][0] == 0 and pieces[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+        # 2. balanced in TIME: every non-clipped piece costs the same to within one tile of rounding
+        cost = [(hi - lo) / weights[sm] for (lo, hi), sm in zip(pieces, sm_of_claimer) if hi < total and hi > lo]
+        if cost:
+            assert max(cost) - min(cost) <= 1.0 / min(weights) + 1e-9
+        # 3. per head: the pieces that overlap it are a contiguous run of claim indices; the merger (piece holding the head's
+        #    last tile) has the HIGHEST claim index of the run, i.e. it only waits for earlier claimers
+        min_len = min(hi - lo for lo, hi in pieces if hi > lo)
+        for x in range(heads):
+            lo_t, hi_t = x * tph, (x + 1) * tph
+            run = [k for k, (lo, hi) in enumerate(pieces) if lo < hi_t and hi > lo_t]
+            assert run == list(range(run[0], run[-1] + 1))
+            merger = next(k for k, (lo, hi) in enumerate(pieces) if lo <= hi_t - 1 < hi)
+            assert merger == run[-1]
+            # 4. slot bound the workspace would be sized with (every piece but the last of the run is a whole claim)
+            assert len(run) <= -(-tph // min_len) + 1 or pieces[run[-1]][1] == total
