@@ -481,7 +481,22 @@ def main():
         time.sleep(3600)
     if rank == 0:
         emit(main_line())
+    # teardown must not be able to take the (already printed) line down with it: if an extra failed, a peer or the CUDA context
+    # may be in a bad state and the collective barrier inside cleanup() could raise or wait forever -- leave without it
+    def _has_error(v, depth=0):
+        return isinstance(v, dict) and ("error" in v or (depth < 2 and any(_has_error(x, depth + 1) for x in v.values())))
+
+    failed = [k for k, v in extras.items() if _has_error(v)]
+    if failed:
+        print(f"[bench] extras {failed} failed; skipping the collective teardown", file=sys.stderr)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+    bail = threading.Timer(45.0, lambda: os._exit(0))     # a peer that already left would make the teardown barrier wait forever
+    bail.daemon = True
+    bail.start()
     ta.cleanup()
+    bail.cancel()
     return 0
 
 
