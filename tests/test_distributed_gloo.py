@@ -23,7 +23,7 @@ def _worker(rank, world, cfg):
     q, k, v = ta.make_data((b, hq, s, d), rank, "cpu", dtype=torch.float32, sq=sq, num_kv_heads=hkv, log=False)
     kf, vf = _gather_kv(k, v, world)
     o_ref, l_ref = ref.attention_ref(q, kf, vf, causal=causal)
-    for sched in ("allreduce3", "allgather", "butterfly", "oneshot"):
+    for sched in ("allreduce3", "allgather", "butterfly", "oneshot", "ring"):
         out, lse = ta.tree_attention(q, k, v, causal=causal, return_lse=True, schedule=sched)
         assert torch.allclose(out.double(), o_ref, atol=1e-5), (sched, (out.double() - o_ref).abs().max())
         assert torch.allclose(lse.double(), l_ref, atol=1e-5), sched
@@ -32,7 +32,7 @@ def _worker(rank, world, cfg):
         dist.all_gather(outs, out.contiguous())
         for o in outs:
             assert torch.allclose(o, outs[0], atol=1e-6)
-        if sched in ("allgather", "butterfly", "oneshot") and (world & (world - 1)) == 0:
+        if sched in ("allgather", "butterfly", "oneshot", "ring") and (world & (world - 1)) == 0:
             for o in outs:
                 assert torch.equal(o, outs[0]), f"{sched}: not bitwise identical across ranks"
     # reference-compatible shim (scale 1.0, non-causal)

@@ -14,7 +14,8 @@ Backends
 ``nccl`` / ``gloo``  local partial + ``torch.distributed`` collectives: the reference's structure
             (``schedule="allreduce3"`` = MAX, SUM, SUM exactly as model.py:108-115, but with an
             ``|O| + 2``-scalar payload instead of ``3|O|``), or one packed ``allgather``, or a real
-            pairwise ``butterfly`` tree.  This is the baseline and the CPU plumbing path.
+            pairwise ``butterfly`` tree, or a sequential ``ring`` chain (depth 2(W-1): the pattern the Tree Attention
+            paper compares against).  This is the baseline and the CPU plumbing path.
 ``local``   world size 1.
 """
 from __future__ import annotations
@@ -40,7 +41,7 @@ def _nvtx(name: str):
 
 
 _BACKENDS = ("auto", "fused", "symm", "nccl", "gloo", "collective", "local")
-_SCHEDULES = ("oneshot", "butterfly", "allreduce3", "allgather")
+_SCHEDULES = ("oneshot", "butterfly", "allreduce3", "allgather", "ring")
 
 
 def _world(group) -> Tuple[int, int]:
@@ -115,6 +116,27 @@ def _combine_butterfly(o: torch.Tensor, lse: torch.Tensor, group) -> Tuple[torch
     return cur[..., :-1], cur[..., -1]
 
 
+def _combine_ring(o, lse, group):
+    """Sequential chain: rank 0 -> 1 -> ... -> W-1 accumulates the partials in rank order (W-1 dependent hops), then the
+    result travels back along the chain.  This is the communication pattern a ring (blockwise) attention would use to move a
+    decode query's state through the KV shards -- depth ``2 (W-1)`` against ``ceil(log2 W)`` for the butterfly and 1 for the
+    fused one-shot: the comparison the Tree Attention paper draws.  Baseline only; never the product path."""
+    rank, world = _world(group)
+    g = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    acc = torch.cat([o.float(), lse.float()[..., None]], dim=-1).contiguous()
+    if rank > 0:
+        prev = torch.empty_like(acc)
+        dist.recv(prev, src=g(rank - 1), group=group)
+        o_m, l_m = ref.merge_pair(prev[..., :-1], prev[..., -1], acc[..., :-1], acc[..., -1])   # earlier ranks first
+        acc = torch.cat([o_m, l_m[..., None]], dim=-1).contiguous()
+    if rank < world - 1:
+        dist.send(acc, dst=g(rank + 1), group=group)
+        dist.recv(acc, src=g(rank + 1), group=group)                        # the global result on its way back
+    if rank > 0:
+        dist.send(acc, dst=g(rank - 1), group=group)
+    return acc[..., :-1], acc[..., -1]
+
+
 def combine_partials(
     o: torch.Tensor,
     lse: torch.Tensor,
@@ -128,7 +150,7 @@ def combine_partials(
     out_dtype = out_dtype or o.dtype
     if world == 1:
         return o.to(out_dtype), lse
-    use_symm = o.is_cuda and backend in ("auto", "symm", "fused")
+    use_symm = o.is_cuda and backend in ("auto", "symm", "fused") and schedule != "ring"   # ring exists as a collective baseline only
     if use_symm:
         from .. import _build
 
@@ -152,6 +174,8 @@ def combine_partials(
         return out.to(out_dtype), lse_out
     if schedule == "allreduce3":
         out, lse_g = _combine_allreduce3(o, lse, group)
+    elif schedule == "ring":
+        out, lse_g = _combine_ring(o, lse, group)
     elif schedule == "butterfly":
         out, lse_g = _combine_butterfly(o, lse, group)
     else:

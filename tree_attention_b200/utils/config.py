@@ -34,7 +34,7 @@ class TreeAttentionConfig:
     softmax_scale: Optional[float] = None
     # execution
     backend: str = "auto"           # auto | fused | nccl | gloo | local
-    schedule: str = "oneshot"       # oneshot | butterfly | allreduce3 | allgather
+    schedule: str = "oneshot"       # oneshot | butterfly | allreduce3 | allgather | ring (collective baselines)
     steps: int = 1                  # the reference times exactly one call (model.py:149-151)
     warmup: int = 0
     check: bool = True              # validate against the oracle
