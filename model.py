@@ -120,6 +120,7 @@ def main(rank: int, world_size: int) -> None:
             "world_size": world_size, "device": device.type, "dtype": str(dtype).replace("torch.", ""),
             "shape": {"B": cfg.batch, "Hq": cfg.num_heads, "Hkv": cfg.kv_heads, "Sq": cfg.q_len,
                       "S_per_rank": cfg.seq_len, "S_global": s_global, "D": cfg.head_dim},
+            "steps": max(cfg.steps, 1), "warmup": warmup, "timer": "cuda_events" if device.type == "cuda" else "host_clock",
             "latency_us": seconds * 1e6, "decode_tokens_per_s": cfg.batch * cfg.q_len / seconds,
             "kv_tokens_per_s": cfg.batch * s_global / seconds, "max_abs_err": err,
             "backend": cfg.backend, "schedule": cfg.schedule, "kv_format": cfg.kv_format,
